@@ -1,0 +1,478 @@
+// Batched dense scoring on the 5th-generation tensor cores (K2b in SURVEY.md):
+// scores = Q[B,dim] x E[n_rows,dim]^T in bf16 with fp32 accumulation in TMEM, and a fused
+// per-query running top-k in the epilogue so the [B, n_rows] score matrix never exists.
+//
+// Replaces DenseIndex.search -> collection.query (rag_uq/streaming_index.py:353-370) for
+// query batches; the reference answers one query at a time through ChromaDB's HNSW.
+//
+// Roles (192 threads, 1 block per SM, persistent):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles into a ring of
+//               shared-memory stages, completion on mbarriers.
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M = 128 queries).
+//   warps 2..5  epilogue: tcgen05.ld of the accumulator; THREAD r OWNS QUERY r of the
+//               slab for the whole kernel, so its admission threshold is a register and
+//               the common case is "32 scores, one max, one compare".  Survivors are
+//               inserted into the thread's private sorted list in shared memory.
+//   The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the
+//   MMAs of tile i+1.
+//
+// Work split: block c serves query slab (c % n_slabs) and passage group (c / n_slabs); the
+// blocks of one group read the same passages at the same time, so HBM sees each passage
+// row once and L2 serves the other slabs.
+//
+// variant 0 (SS): A = query slab and B = passage tile both streamed through shared memory.
+// variant 1 (TS): the query slab [128 x dim] is stored ONCE into TMEM (dim/2 columns of
+//   packed bf16 pairs) and used as the A operand from there; only passages stream through
+//   shared memory, which halves the L2 -> SM traffic per flop.  Needs dim <= 768.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ragb {
+
+constexpr int MM_BM = 128;
+constexpr int MM_BK = 64;
+constexpr int MM_THREADS = 192;
+constexpr int MM_A_STAGE_BYTES = MM_BM * MM_BK * 2;  // 16 KB
+constexpr int MM_MAX_STAGES = 16;
+constexpr int MM_MAX_SMEM = 227 * 1024;
+
+struct MmaArgs {
+  const uint4* queries;  // raw pointer, used by variant 1 to fill TMEM
+  int64_t n_rows;
+  int64_t id_base;
+  int n_queries;
+  int dim;
+  int k;
+  int n_slabs;
+  int n_groups;
+  int tiles_per_group;
+  int n_tiles;
+  int n_stages;
+  uint64_t* part_keys;  // [n_queries, n_groups, k]
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+// K-major, 128-byte swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);  // start address      bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                       // leading byte offset (unused, swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // stride byte offset  bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void list_insert(uint64_t* list, int k, int& n, uint64_t key, uint64_t& thr_key,
+                                            float& thr_score) {
+  int j = n < k ? n : k - 1;
+  while (j > 0) {
+    const uint64_t prev = list[(j - 1) * MM_BM];
+    if (prev >= key) break;
+    list[j * MM_BM] = prev;
+    --j;
+  }
+  list[j * MM_BM] = key;
+  if (n < k) ++n;
+  if (n == k) {
+    thr_key = list[(k - 1) * MM_BM];
+    thr_score = key_score(thr_key);
+  }
+}
+
+template <int BN, bool A_IN_TMEM>
+__global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                                                                  const __grid_constant__ CUtensorMap tmap_e,
+                                                                  const MmaArgs a) {
+  constexpr int B_STAGE_BYTES = BN * MM_BK * 2;
+  constexpr int STAGE_BYTES = (A_IN_TMEM ? 0 : MM_A_STAGE_BYTES) + B_STAGE_BYTES;
+  constexpr uint32_t IDESC = make_idesc(MM_BM, BN);
+
+  const int n_slabs = a.n_slabs;
+  if (static_cast<int>(blockIdx.x) >= n_slabs * a.n_groups) return;
+  const int slab = blockIdx.x % n_slabs;
+  const int group = blockIdx.x / n_slabs;
+  const int tile_begin = min(a.n_tiles, group * a.tiles_per_group);
+  const int tile_end = min(a.n_tiles, tile_begin + a.tiles_per_group);
+  const int n_kb = a.dim / MM_BK;
+  const int a_cols = A_IN_TMEM ? a.dim / 2 : 0;  // TMEM columns holding the packed query slab
+  const uint32_t tmem_cols = A_IN_TMEM ? 512u : (2 * BN <= 32 ? 32u : (2 * BN <= 64 ? 64u : (2 * BN <= 128 ? 128u : 256u)));
+
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* stages = base;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(base + static_cast<size_t>(a.n_stages) * STAGE_BYTES);
+  __shared__ __align__(8) uint64_t bar_full[MM_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[MM_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_tmem_full[2];
+  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
+  __shared__ __align__(8) uint64_t bar_a_ready;
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.n_stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tmem_full[b]), 1);
+      mbar_init(smem_u32(&bar_tmem_empty[b]), 4);
+    }
+    mbar_init(smem_u32(&bar_a_ready), 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_e)) : "memory");
+    if (!A_IN_TMEM) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  const uint32_t acc_col0 = static_cast<uint32_t>(a_cols);
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          unsigned char* st = stages + static_cast<size_t>(stage) * STAGE_BYTES;
+          mbar_expect_tx(full, STAGE_BYTES);
+          if (!A_IN_TMEM) {
+            tma_load_2d(smem_u32(st), &tmap_q, full, kb * MM_BK, slab * MM_BM);
+            tma_load_2d(smem_u32(st + MM_A_STAGE_BYTES), &tmap_e, full, kb * MM_BK, tile * BN);
+          } else {
+            tma_load_2d(smem_u32(st), &tmap_e, full, kb * MM_BK, tile * BN);
+          }
+          if (++stage == static_cast<uint32_t>(a.n_stages)) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      if (A_IN_TMEM) {
+        mbar_wait(smem_u32(&bar_a_ready), 0);
+        tc_fence_after();
+      }
+      uint32_t stage = 0, phase = 0, buf = 0, acc_phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        mbar_wait(smem_u32(&bar_tmem_empty[buf]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc_col0 + buf * BN;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          unsigned char* st = stages + static_cast<size_t>(stage) * STAGE_BYTES;
+          const uint32_t a_addr = smem_u32(st);
+          const uint32_t b_addr = smem_u32(st + (A_IN_TMEM ? 0 : MM_A_STAGE_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < MM_BK / 16; ++kk) {
+            const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
+            const uint64_t b_desc = make_sw128_desc(b_addr + kk * 32);
+            if (A_IN_TMEM) {
+              tc_mma_ts(d_tmem, tmem_base + kb * (MM_BK / 2) + kk * 8, b_desc, IDESC, acc);
+            } else {
+              tc_mma_ss(d_tmem, make_sw128_desc(a_addr + kk * 32), b_desc, IDESC, acc);
+            }
+          }
+          tc_commit(smem_u32(&bar_empty[stage]));  // frees the stage once these MMAs retire
+          if (++stage == static_cast<uint32_t>(a.n_stages)) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(smem_u32(&bar_tmem_full[buf]));
+        buf ^= 1;
+        if (buf == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================= epilogue: thread owns one query =================
+    const int quad = warp & 3;
+    const int tslot = quad * 32 + lane;  // TMEM lane == query row inside the slab
+    const int query = slab * MM_BM + tslot;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    uint64_t* my_list = lists + tslot;
+
+    if (A_IN_TMEM) {
+      // store the thread's query row (packed bf16 pairs, K ascending) into its TMEM lane
+      const uint4* qrow = a.queries + static_cast<int64_t>(query) * (a.dim / 8);
+      for (int c = 0; c < a_cols / 32; ++c) {
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 x = make_uint4(0u, 0u, 0u, 0u);
+          if (query < a.n_queries) x = __ldg(qrow + c * 8 + i);
+          v[4 * i] = x.x;
+          v[4 * i + 1] = x.y;
+          v[4 * i + 2] = x.z;
+          v[4 * i + 3] = x.w;
+        }
+        tc_st32(tmem_base + lane_addr + c * 32, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_a_ready));
+    }
+
+    int n = 0;
+    uint64_t thr_key = 0ull;
+    float thr_score = -INFINITY;
+    uint32_t buf = 0, acc_phase = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_phase);
+      tc_fence_after();
+      const int64_t row0 = static_cast<int64_t>(tile) * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + lane_addr + acc_col0 + buf * BN + c * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float m = __uint_as_float(v[0]);
+#pragma unroll
+        for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+        if (m >= thr_score) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int64_t row = row0 + c * 32 + i;
+            const float s = __uint_as_float(v[i]);
+            if (s >= thr_score && row < a.n_rows) {
+              const uint64_t key = make_key(s, static_cast<int32_t>(a.id_base + row));
+              if (key > thr_key) list_insert(my_list, a.k, n, key, thr_key, thr_score);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+      buf ^= 1;
+      if (buf == 0) acc_phase ^= 1;
+    }
+    if (query < a.n_queries) {
+      uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.n_groups + group) * a.k;
+      for (int j = 0; j < a.k; ++j) dst[j] = j < n ? my_list[j * MM_BM] : 0ull;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// [rows, dim] bf16 row-major -> 2-D map, box = 64 columns (128 bytes) x box_rows, 128B swizzle
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int dim, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  RAGB_REQUIRE(fn, RAGB_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(dim) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(MM_BK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t elem[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, elem,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RAGB_REQUIRE(r == CUDA_SUCCESS, RAGB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return RAGB_OK;
+}
+
+template <int BN, bool A_IN_TMEM>
+static int launch_mma(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
+                      int64_t id_base, uint64_t* part, int* n_groups_out, cudaStream_t stream) {
+  constexpr int STAGE_BYTES = (A_IN_TMEM ? 0 : MM_A_STAGE_BYTES) + BN * MM_BK * 2;
+  CUtensorMap map_q, map_e;
+  int rc = make_map(&map_q, queries, n_queries, dim, MM_BM);
+  if (rc != RAGB_OK) return rc;
+  rc = make_map(&map_e, passages, n_rows, dim, BN);
+  if (rc != RAGB_OK) return rc;
+
+  MmaArgs a{};
+  a.queries = static_cast<const uint4*>(queries);
+  a.n_rows = n_rows;
+  a.id_base = id_base;
+  a.n_queries = n_queries;
+  a.dim = dim;
+  a.k = k;
+  a.n_slabs = (n_queries + MM_BM - 1) / MM_BM;
+  const int sms = device_sm_count();
+  RAGB_REQUIRE(a.n_slabs <= sms, RAGB_ELIMIT, "ragb_dense_mma_topk: n_queries=%d needs more than %d slabs of 128",
+               n_queries, sms);
+  a.n_tiles = static_cast<int>(ceil_div64(n_rows, BN));
+  a.n_groups = sms / a.n_slabs;
+  if (a.n_groups > a.n_tiles) a.n_groups = a.n_tiles;
+  a.tiles_per_group = (a.n_tiles + a.n_groups - 1) / a.n_groups;
+  a.n_groups = (a.n_tiles + a.tiles_per_group - 1) / a.tiles_per_group;
+  a.part_keys = part;
+  const size_t list_bytes = static_cast<size_t>(k) * MM_BM * sizeof(uint64_t);
+  int stages = static_cast<int>((MM_MAX_SMEM - 1024 - 256 - list_bytes) / STAGE_BYTES);
+  if (stages > MM_MAX_STAGES) stages = MM_MAX_STAGES;
+  RAGB_REQUIRE(stages >= 2, RAGB_ELIMIT, "ragb_dense_mma_topk: k=%d leaves no room for a 2-stage pipeline", k);
+  a.n_stages = stages;
+  const size_t smem = 1024 + static_cast<size_t>(stages) * STAGE_BYTES + list_bytes;
+  RAGB_CUDA(cudaFuncSetAttribute(dense_mma_kernel<BN, A_IN_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  dense_mma_kernel<BN, A_IN_TMEM><<<a.n_slabs * a.n_groups, MM_THREADS, smem, stream>>>(map_q, map_e, a);
+  RAGB_AFTER_LAUNCH(1);
+  *n_groups_out = a.n_groups;
+  return RAGB_OK;
+}
+
+}  // namespace ragb
+
+using namespace ragb;
+
+extern "C" {
+
+size_t ragb_dense_mma_workspace_bytes(int32_t n_queries, int32_t k) {
+  if (n_queries <= 0 || k <= 0) return 0;
+  return static_cast<size_t>(n_queries) * 148 * k * sizeof(uint64_t);
+}
+
+int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
+                        int32_t n_queries, int32_t k, int64_t id_base, int32_t variant, float* out_score,
+                        int32_t* out_id, void* workspace, size_t workspace_bytes, ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(passages_bf16 && queries_bf16 && out_score && out_id && workspace, RAGB_EINVAL,
+               "ragb_dense_mma_topk: null pointer");
+  RAGB_REQUIRE(((reinterpret_cast<uintptr_t>(passages_bf16) | reinterpret_cast<uintptr_t>(queries_bf16)) & 15) == 0,
+               RAGB_EINVAL, "ragb_dense_mma_topk: inputs must be 16-byte aligned");
+  RAGB_REQUIRE(n_rows > 0 && n_queries > 0, RAGB_EINVAL, "ragb_dense_mma_topk: empty shape");
+  RAGB_REQUIRE(dim >= MM_BK && dim % MM_BK == 0, RAGB_EINVAL, "ragb_dense_mma_topk: dim=%d must be a multiple of %d", dim,
+               MM_BK);
+  RAGB_REQUIRE(k > 0 && k <= 128, RAGB_ELIMIT, "ragb_dense_mma_topk: k=%d outside [1,128]", k);
+  RAGB_REQUIRE(variant == 0 || variant == 1, RAGB_EINVAL, "ragb_dense_mma_topk: variant must be 0 or 1");
+  RAGB_REQUIRE(variant == 0 || dim <= 768, RAGB_ELIMIT, "ragb_dense_mma_topk: variant 1 keeps the query slab in TMEM and needs dim <= 768");
+  RAGB_REQUIRE(id_base >= 0 && id_base + n_rows < (1ll << 31), RAGB_ELIMIT, "ragb_dense_mma_topk: ids must fit int32");
+  RAGB_REQUIRE(workspace_bytes >= ragb_dense_mma_workspace_bytes(n_queries, k), RAGB_ENOSPC,
+               "ragb_dense_mma_topk: workspace too small");
+  uint64_t* part = static_cast<uint64_t*>(workspace);
+  int n_groups = 0;
+  int rc;
+  if (variant == 0)
+    rc = launch_mma<128, false>(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, &n_groups, stream);
+  else
+    rc = launch_mma<64, true>(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, &n_groups, stream);
+  if (rc != RAGB_OK) return rc;
+  return launch_merge_keys(part, n_queries, n_groups, k, k, out_score, out_id, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Block-level exact top-k over a stream of 64-bit candidate keys.
+//
+// Replaces np.argsort(scores)[::-1][:k] (rag_uq/streaming_index.py:172), torch.topk
+// (rag_uq/router.py:202) and the Python sort in hybrid_search (streaming_index.py:521).
+//
+// Algorithm: threshold filter + deferred bitonic merge.  The block keeps its current best
+// k keys sorted at keys[0..k) and appends every candidate whose key beats the running
+// k-th best ("threshold") to keys[k..).  When the append region could overflow, the whole
+// live prefix is bitonic-sorted (descending), the tail beyond k is cleared and the
+// threshold tightens.  After the first few hundred candidates almost nothing passes the
+// filter (expected appends ~ k ln(n/k)), so the sort cost is amortised to nothing.
+#pragma once
+#include "common.cuh"
+
+namespace ragb {
+
+// Sort keys[0..n) descending; n is a power of two; all NT threads of the block call this.
+template <int NT>
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (n >> 1); i += NT) {
+        int lo = 2 * i - (i & (stride - 1));
+        int hi = lo + stride;
+        bool descending = ((lo & size) == 0);
+        uint64_t a = keys[lo], b = keys[hi];
+        if ((a < b) == descending) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int NT>
+struct BlockTopK {
+  uint64_t* keys;      // shared, capacity entries, zero = empty
+  int* count;          // shared, number of appended candidates
+  uint64_t* threshold; // shared, candidates must be strictly greater
+  int k;
+  int capacity;        // power of two, > k
+  uint64_t floor_key;
+
+  __device__ __forceinline__ void init(uint64_t* keys_, int* count_, uint64_t* thr_, int k_, int capacity_,
+                                       uint64_t floor_key_) {
+    keys = keys_;
+    count = count_;
+    threshold = thr_;
+    k = k_;
+    capacity = capacity_;
+    floor_key = floor_key_;
+    for (int i = threadIdx.x; i < capacity; i += NT) keys[i] = 0ull;
+    if (threadIdx.x == 0) {
+      *count = 0;
+      *threshold = floor_key;
+    }
+    __syncthreads();
+  }
+
+  __device__ __forceinline__ int room() const { return capacity - k; }
+
+  // Caller guarantees (through reserve) that the append region cannot overflow.
+  __device__ __forceinline__ void offer(uint64_t key, uint64_t thr) {
+    if (key > thr) {
+      int slot = atomicAdd(count, 1);
+      keys[k + slot] = key;
+    }
+  }
+
+  // Block-wide: make room for `incoming` further appends.  Contains barriers.
+  __device__ __forceinline__ void reserve(int incoming) {
+    __syncthreads();
+    if (*count + incoming > room()) flush();
+  }
+
+  // Block-wide: fold the appended candidates into the sorted top-k.  Contains barriers;
+  // every thread must reach it after a barrier that ordered the last appends.
+  __device__ __forceinline__ void flush() {
+    int appended = *count;
+    if (appended == 0) return;
+    int n = 2;
+    while (n < k + appended) n <<= 1;
+    __syncthreads();  // everyone has read *count before thread 0 resets it
+    bitonic_sort_desc<NT>(keys, n);
+    for (int i = k + threadIdx.x; i < n; i += NT) keys[i] = 0ull;
+    if (threadIdx.x == 0) {
+      *count = 0;
+      uint64_t kth = keys[k - 1];
+      *threshold = kth > floor_key ? kth : floor_key;
+    }
+    __syncthreads();
+  }
+
+  // Final result for this block: keys[0..k) sorted best first, zero = empty.
+  __device__ __forceinline__ void finish() {
+    __syncthreads();
+    flush();
+  }
+};
+
+// Capacity used for a given k (entries of 8 bytes).
+__host__ __device__ constexpr int topk_capacity(int k) { return k <= 64 ? 1024 : 2048; }
+
+}  // namespace ragb

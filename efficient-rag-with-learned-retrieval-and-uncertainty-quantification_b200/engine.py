@@ -1,0 +1,110 @@
+"""Tensor-level hybrid retrieval over one row shard of the corpus, optionally one of G shards.
+
+This is the batched form of ``HybridRetriever.hybrid_search`` (rag_uq/streaming_index.py:464-523)
+and ``get_scores_for_router`` (:525-557): BM25 pool + dense pool -> union / max-normalised
+average -> top-k.  The string-level drop-in classes in ``retrieval.py`` sit on top of it.
+
+Sharding: passages are independent, so GPU g owns global rows
+[g*N/G, (g+1)*N/G): its slice of the embedding matrix and a document-partitioned inverted index
+built with GLOBAL statistics (df all-reduced once at build time).  Queries are replicated.  Per
+batch there is exactly one exchange: each rank all-gathers its local [B, pool] candidate lists
+(fp32 score + int32 global id; NCCL over NVLink) and every rank merges G*pool candidates per
+query.  Pool fusion needs the GLOBAL pools (max-normalisation and the 0.0-for-missing rule), so
+it runs after the merge.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import _lib, ops
+from .sparse import SparseShard
+
+
+def shard_rows(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range of ``rank``; the first ``n_rows % world`` ranks get one extra row."""
+    base, extra = divmod(n_rows, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def global_bm25_statistics(df_local: Tensor, n_local: int, len_local: int, group=None):
+    """Sum document frequencies, document count and total length over the shards."""
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return df_local, n_local, len_local
+    df = df_local.clone()
+    scal = torch.tensor([n_local, len_local], dtype=torch.int64, device=df_local.device)
+    dist.all_reduce(df, group=group)
+    dist.all_reduce(scal, group=group)
+    return df, int(scal[0]), int(scal[1])
+
+
+def gather_candidates(score: Tensor, ids: Tensor, group=None) -> Tuple[Tensor, Tensor]:
+    """All-gather local candidate lists [B, k] into [B, G, k] (rank-major inside a query)."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return score.unsqueeze(1), ids.unsqueeze(1)
+    b, k = score.shape
+    all_s = torch.empty((world, b, k), dtype=score.dtype, device=score.device)
+    all_i = torch.empty((world, b, k), dtype=ids.dtype, device=ids.device)
+    dist.all_gather_into_tensor(all_s, score.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, ids.contiguous(), group=group)
+    return all_s.permute(1, 0, 2).contiguous(), all_i.permute(1, 0, 2).contiguous()
+
+
+class HybridEngine:
+    def __init__(self, sparse: Optional[SparseShard], passages: Optional[Tensor], id_base: int = 0, group=None,
+                 mma_variant: int = 0):
+        if passages is not None:
+            if passages.dtype != torch.bfloat16 or passages.dim() != 2:
+                raise TypeError("passages must be a bf16 [rows, dim] tensor")
+            if not passages.is_cuda:
+                raise NotImplementedError("rag_uq_b200 scores on CUDA (sm_100) only; there is no CPU path")
+        self.sparse = sparse
+        self.passages = passages
+        self.id_base = id_base
+        self.group = group
+        self.mma_variant = mma_variant
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    # ---- single-retriever pools --------------------------------------------------------
+    def _merge(self, score: Tensor, ids: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+        if self.world == 1:
+            return score, ids
+        s, i = gather_candidates(score, ids, self.group)
+        return ops.topk_merge(s, i, k)
+
+    def bm25_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int) -> Tuple[Tensor, Tensor]:
+        """BM25Index.search for a batch: (score [B,k], global id [B,k]); score > 0 only, id -1 pads."""
+        score, ids = self.sparse.score_topk(q_terms, q_off, max_terms, k)
+        return self._merge(score, ids, k)
+
+    def dense_local_topk(self, q_emb: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+        if q_emb.shape[0] <= _lib.GEMV_MAX_BATCH:
+            return ops.dense_gemv_topk(self.passages, q_emb, k, self.id_base)
+        return ops.dense_mma_topk(self.passages, q_emb, k, self.id_base, self.mma_variant)
+
+    def dense_topk(self, q_emb: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+        """DenseIndex.search for a batch, exact instead of HNSW."""
+        score, ids = self.dense_local_topk(q_emb, k)
+        return self._merge(score, ids, k)
+
+    # ---- hybrid ------------------------------------------------------------------------
+    def hybrid_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, k: int = 10,
+                    pool: int = 50):
+        """-> ids int32 [B,k] (-1 pads), bm25 [B,k], dense [B,k], hybrid [B,k]."""
+        bs, bi = self.sparse.score_topk(q_terms, q_off, max_terms, pool)
+        ds, di = self.dense_local_topk(q_emb, pool)
+        if self.world > 1:
+            # one exchange for both pools: [B, 2, pool] score + id
+            s = torch.stack([bs, ds], dim=1).reshape(bs.shape[0], 2 * pool)
+            i = torch.stack([bi, di], dim=1).reshape(bs.shape[0], 2 * pool)
+            gs, gi = gather_candidates(s, i, self.group)          # [B, G, 2*pool]
+            gs = gs.view(bs.shape[0], self.world, 2, pool)
+            gi = gi.view(bs.shape[0], self.world, 2, pool)
+            bs, bi = ops.topk_merge(gs[:, :, 0].contiguous(), gi[:, :, 0].contiguous(), pool)
+            ds, di = ops.topk_merge(gs[:, :, 1].contiguous(), gi[:, :, 1].contiguous(), pool)
+        return ops.hybrid_fuse_topk(bs, bi, ds, di, k)

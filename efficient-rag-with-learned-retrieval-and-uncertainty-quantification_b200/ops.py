@@ -1,0 +1,348 @@
+"""PyTorch custom ops (torch.library) over the C ABI of libragb200.so.
+
+Every op is registered for the CUDA device only (``device_types="cuda"``): calling one with
+CPU tensors raises NotImplementedError from the dispatcher - there is no CPU implementation
+on purpose.  torch is used for memory, streams and dispatch; all arithmetic happens in the
+hand-written sm_100a kernels.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, lib
+
+NS = "rag_uq_b200"
+
+
+def _ptr(t: Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t: Tensor, dtype: torch.dtype, name: str) -> Tensor:
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_cuda:
+        raise NotImplementedError(f"{name}: rag_uq_b200 ops run on CUDA (sm_100) tensors only")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------
+# BM25
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op(f"{NS}::bm25_build_idf", mutates_args=(), device_types="cuda")
+def bm25_build_idf(df: Tensor, corpus_size: int, epsilon: float) -> Tensor:
+    df = _need(df, torch.int32, "df")
+    out = torch.empty(df.shape[0], dtype=torch.float32, device=df.device)
+    nbytes = lib.ragb_bm25_idf_scratch_bytes(df.shape[0])
+    scratch = _workspace(nbytes, df.device)
+    with torch.cuda.device(df.device):
+        check(lib.ragb_bm25_build_idf(_ptr(df), df.shape[0], corpus_size, epsilon, _ptr(out), _ptr(scratch),
+                                      scratch.numel(), _stream()))
+    return out
+
+
+@bm25_build_idf.register_fake
+def _(df, corpus_size, epsilon):
+    return df.new_empty(df.shape, dtype=torch.float32)
+
+
+@torch.library.custom_op(f"{NS}::bm25_build_norm", mutates_args=(), device_types="cuda")
+def bm25_build_norm(doc_len: Tensor, avgdl: float, k1: float, b: float) -> Tensor:
+    doc_len = _need(doc_len, torch.int32, "doc_len")
+    out = torch.empty(doc_len.shape[0], dtype=torch.float32, device=doc_len.device)
+    with torch.cuda.device(doc_len.device):
+        check(lib.ragb_bm25_build_norm(_ptr(doc_len), doc_len.shape[0], avgdl, k1, b, _ptr(out), _stream()))
+    return out
+
+
+@bm25_build_norm.register_fake
+def _(doc_len, avgdl, k1, b):
+    return doc_len.new_empty(doc_len.shape, dtype=torch.float32)
+
+
+def _bm25_args(term_off, post_doc, post_tf, norm, idf, q_terms, q_off):
+    term_off = _need(term_off, torch.int64, "term_off")
+    post_doc = _need(post_doc, torch.int32, "post_doc")
+    post_tf = _need(post_tf, torch.int16, "post_tf")  # bit pattern of uint16
+    norm = _need(norm, torch.float32, "norm")
+    idf = _need(idf, torch.float32, "idf")
+    q_terms = _need(q_terms, torch.int32, "q_terms")
+    q_off = _need(q_off, torch.int32, "q_off")
+    if term_off.shape[0] != idf.shape[0] + 1:
+        raise ValueError("term_off must have vocab + 1 entries")
+    return term_off, post_doc, post_tf, norm, idf, q_terms, q_off
+
+
+@torch.library.custom_op(f"{NS}::bm25_score_topk", mutates_args=(), device_types="cuda")
+def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
+                    q_terms: Tensor, q_off: Tensor, max_query_terms: int, id_base: int,
+                    k: int) -> Tuple[Tensor, Tensor]:
+    term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
+                                                                        q_terms, q_off)
+    n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
+    score = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.ragb_bm25_topk_workspace_bytes(n_q, n_docs, k), dev)
+    with torch.cuda.device(dev):
+        check(lib.ragb_bm25_score_topk(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf),
+                                       idf.shape[0], k1, _ptr(q_terms), _ptr(q_off), n_q, max_query_terms, n_docs,
+                                       id_base, k, _ptr(score), _ptr(ids), _ptr(ws), ws.numel(), _stream()))
+    return score, ids
+
+
+@bm25_score_topk.register_fake
+def _(term_off, post_doc, post_tf, norm, idf, k1, q_terms, q_off, max_query_terms, id_base, k):
+    n_q = q_off.shape[0] - 1
+    return norm.new_empty((n_q, k)), norm.new_empty((n_q, k), dtype=torch.int32)
+
+
+@torch.library.custom_op(f"{NS}::bm25_scores", mutates_args=(), device_types="cuda")
+def bm25_scores(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
+                q_terms: Tensor, q_off: Tensor, max_query_terms: int) -> Tensor:
+    term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
+                                                                        q_terms, q_off)
+    n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
+    out = torch.empty((n_q, n_docs), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.ragb_bm25_scores(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf),
+                                   idf.shape[0], k1, _ptr(q_terms), _ptr(q_off), n_q, max_query_terms, n_docs,
+                                   _ptr(out), _stream()))
+    return out
+
+
+@bm25_scores.register_fake
+def _(term_off, post_doc, post_tf, norm, idf, k1, q_terms, q_off, max_query_terms):
+    return norm.new_empty((q_off.shape[0] - 1, norm.shape[0]))
+
+
+# ------------------------------------------------------------------------------------------
+# dense
+# ------------------------------------------------------------------------------------------
+def _dense_args(passages: Tensor, queries: Tensor):
+    passages = _need(passages, torch.bfloat16, "passages")
+    queries = _need(queries, torch.bfloat16, "queries")
+    if passages.dim() != 2 or queries.dim() != 2 or passages.shape[1] != queries.shape[1]:
+        raise ValueError("passages [N, dim] and queries [B, dim] must share dim")
+    return passages, queries
+
+
+@torch.library.custom_op(f"{NS}::dense_gemv_topk", mutates_args=(), device_types="cuda")
+def dense_gemv_topk(passages: Tensor, queries: Tensor, k: int, id_base: int) -> Tuple[Tensor, Tensor]:
+    passages, queries = _dense_args(passages, queries)
+    n_q, dev = queries.shape[0], passages.device
+    score = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.ragb_dense_gemv_workspace_bytes(n_q, k), dev)
+    with torch.cuda.device(dev):
+        check(lib.ragb_dense_gemv_topk(_ptr(passages), passages.shape[0], passages.shape[1], _ptr(queries), n_q, k,
+                                       id_base, _ptr(score), _ptr(ids), _ptr(ws), ws.numel(), _stream()))
+    return score, ids
+
+
+@dense_gemv_topk.register_fake
+def _(passages, queries, k, id_base):
+    n_q = queries.shape[0]
+    return (queries.new_empty((n_q, k), dtype=torch.float32), queries.new_empty((n_q, k), dtype=torch.int32))
+
+
+@torch.library.custom_op(f"{NS}::dense_mma_topk", mutates_args=(), device_types="cuda")
+def dense_mma_topk(passages: Tensor, queries: Tensor, k: int, id_base: int, variant: int) -> Tuple[Tensor, Tensor]:
+    passages, queries = _dense_args(passages, queries)
+    n_q, dev = queries.shape[0], passages.device
+    score = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.ragb_dense_mma_workspace_bytes(n_q, k), dev)
+    with torch.cuda.device(dev):
+        check(lib.ragb_dense_mma_topk(_ptr(passages), passages.shape[0], passages.shape[1], _ptr(queries), n_q, k,
+                                      id_base, variant, _ptr(score), _ptr(ids), _ptr(ws), ws.numel(), _stream()))
+    return score, ids
+
+
+@dense_mma_topk.register_fake
+def _(passages, queries, k, id_base, variant):
+    n_q = queries.shape[0]
+    return (queries.new_empty((n_q, k), dtype=torch.float32), queries.new_empty((n_q, k), dtype=torch.int32))
+
+
+@torch.library.custom_op(f"{NS}::dense_scores", mutates_args=(), device_types="cuda")
+def dense_scores(passages: Tensor, queries: Tensor) -> Tensor:
+    passages, queries = _dense_args(passages, queries)
+    out = torch.empty((queries.shape[0], passages.shape[0]), dtype=torch.float32, device=passages.device)
+    with torch.cuda.device(passages.device):
+        check(lib.ragb_dense_scores(_ptr(passages), passages.shape[0], passages.shape[1], _ptr(queries),
+                                    queries.shape[0], _ptr(out), _stream()))
+    return out
+
+
+@dense_scores.register_fake
+def _(passages, queries):
+    return queries.new_empty((queries.shape[0], passages.shape[0]), dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------
+# selection / fusion
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op(f"{NS}::topk_rows", mutates_args=(), device_types="cuda")
+def topk_rows(scores: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    scores = _need(scores, torch.float32, "scores")
+    if scores.dim() != 2:
+        raise ValueError("scores must be [rows, cols]")
+    n_rows, n_cols = scores.shape
+    val = torch.empty((n_rows, k), dtype=torch.float32, device=scores.device)
+    idx = torch.empty((n_rows, k), dtype=torch.int32, device=scores.device)
+    ws = _workspace(lib.ragb_topk_rows_workspace_bytes(n_rows, n_cols, k), scores.device)
+    with torch.cuda.device(scores.device):
+        check(lib.ragb_topk_rows(_ptr(scores), n_rows, n_cols, k, _ptr(val), _ptr(idx), _ptr(ws), ws.numel(),
+                                 _stream()))
+    return val, idx
+
+
+@topk_rows.register_fake
+def _(scores, k):
+    return scores.new_empty((scores.shape[0], k)), scores.new_empty((scores.shape[0], k), dtype=torch.int32)
+
+
+@torch.library.custom_op(f"{NS}::topk_merge", mutates_args=(), device_types="cuda")
+def topk_merge(scores: Tensor, ids: Tensor, k_out: int) -> Tuple[Tensor, Tensor]:
+    """scores / ids [B, n_lists, k_in] -> [B, k_out]"""
+    scores = _need(scores, torch.float32, "scores")
+    ids = _need(ids, torch.int32, "ids")
+    if scores.dim() != 3 or scores.shape != ids.shape:
+        raise ValueError("scores and ids must both be [B, n_lists, k_in]")
+    n_q, n_lists, k_in = scores.shape
+    val = torch.empty((n_q, k_out), dtype=torch.float32, device=scores.device)
+    out = torch.empty((n_q, k_out), dtype=torch.int32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        check(lib.ragb_topk_merge(_ptr(scores), _ptr(ids), n_q, n_lists, k_in, k_out, _ptr(val), _ptr(out),
+                                  _stream()))
+    return val, out
+
+
+@topk_merge.register_fake
+def _(scores, ids, k_out):
+    return scores.new_empty((scores.shape[0], k_out)), ids.new_empty((scores.shape[0], k_out))
+
+
+@torch.library.custom_op(f"{NS}::hybrid_fuse_topk", mutates_args=(), device_types="cuda")
+def hybrid_fuse_topk(bm25_score: Tensor, bm25_id: Tensor, dense_score: Tensor, dense_id: Tensor,
+                     k: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Pools [B, pool] each -> (ids, bm25, dense, hybrid) [B, k]."""
+    bm25_score = _need(bm25_score, torch.float32, "bm25_score")
+    dense_score = _need(dense_score, torch.float32, "dense_score")
+    bm25_id = _need(bm25_id, torch.int32, "bm25_id")
+    dense_id = _need(dense_id, torch.int32, "dense_id")
+    if not (bm25_score.shape == bm25_id.shape == dense_score.shape == dense_id.shape) or bm25_score.dim() != 2:
+        raise ValueError("the two pools must be [B, pool] tensors of equal shape")
+    n_q, pool = bm25_score.shape
+    dev = bm25_score.device
+    ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    ob = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    od = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    oh = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.ragb_hybrid_fuse_topk(_ptr(bm25_score), _ptr(bm25_id), _ptr(dense_score), _ptr(dense_id), n_q, pool,
+                                        k, _ptr(ids), _ptr(ob), _ptr(od), _ptr(oh), _stream()))
+    return ids, ob, od, oh
+
+
+@hybrid_fuse_topk.register_fake
+def _(bm25_score, bm25_id, dense_score, dense_id, k):
+    n_q = bm25_score.shape[0]
+    f = bm25_score.new_empty((n_q, k))
+    return bm25_id.new_empty((n_q, k)), f, f.clone(), f.clone()
+
+
+# ------------------------------------------------------------------------------------------
+# router
+# ------------------------------------------------------------------------------------------
+def _router_args(bm25, dense, w1, b1, w2, b2, stats):
+    bm25 = _need(bm25, torch.float32, "bm25")
+    dense = _need(dense, torch.float32, "dense")
+    if bm25.dim() != 2 or bm25.shape != dense.shape:
+        raise ValueError("bm25 and dense must both be [B, P]")
+    w1 = _need(w1, torch.float32, "w1")
+    b1 = _need(b1, torch.float32, "b1")
+    w2 = _need(w2, torch.float32, "w2").reshape(-1)
+    b2 = _need(b2, torch.float32, "b2").reshape(-1)
+    stats = _need(stats, torch.float32, "stats").reshape(-1)
+    hidden = b1.shape[0]
+    if w1.shape != (hidden, 3) or w2.shape[0] != hidden or b2.shape[0] != 1 or stats.shape[0] != 4:
+        raise ValueError("router weights must be w1 [H,3], b1 [H], w2 [H] or [1,H], b2 [1], stats [4]")
+    return bm25, dense, w1, b1, w2, b2, stats, hidden
+
+
+@torch.library.custom_op(f"{NS}::router_forward", mutates_args=(), device_types="cuda")
+def router_forward(bm25: Tensor, dense: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, stats: Tensor,
+                   norm_mode: int) -> Tuple[Tensor, Tensor]:
+    """-> (gate [B,P], fused [B,P])"""
+    bm25, dense, w1, b1, w2, b2, stats, hidden = _router_args(bm25, dense, w1, b1, w2, b2, stats)
+    n_rows, n_cand = bm25.shape
+    gate = torch.empty_like(bm25)
+    fused = torch.empty_like(bm25)
+    scratch = _workspace(lib.ragb_router_scratch_bytes(n_rows, norm_mode), bm25.device)
+    with torch.cuda.device(bm25.device):
+        check(lib.ragb_router_forward(_ptr(bm25), _ptr(dense), n_rows, n_cand, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2),
+                                      _ptr(stats), hidden, norm_mode, _ptr(gate), _ptr(fused), _ptr(scratch),
+                                      _stream()))
+    return gate, fused
+
+
+@router_forward.register_fake
+def _(bm25, dense, w1, b1, w2, b2, stats, norm_mode):
+    return torch.empty_like(bm25), torch.empty_like(bm25)
+
+
+@torch.library.custom_op(f"{NS}::router_mc_dropout", mutates_args=(), device_types="cuda")
+def router_mc_dropout(bm25: Tensor, dense: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, stats: Tensor,
+                      norm_mode: int, n_samples: int, p_drop: float, seed: int, offset: int, mask_layout: int,
+                      dump: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> mean_gate, std_gate, mean_fused, std_fused [B,P]; variance [B]; consensus [B];
+    mask_dump uint8 [T, B*P, H] and gate_dump [T,B,P] (empty unless ``dump``)."""
+    bm25, dense, w1, b1, w2, b2, stats, hidden = _router_args(bm25, dense, w1, b1, w2, b2, stats)
+    n_q, n_cand = bm25.shape
+    dev = bm25.device
+    outs = [torch.empty_like(bm25) for _ in range(4)]
+    variance = torch.empty(n_q, dtype=torch.float32, device=dev)
+    consensus = torch.empty(n_q, dtype=torch.int32, device=dev)
+    if dump:
+        mask = torch.empty((n_samples, n_q * n_cand, hidden), dtype=torch.uint8, device=dev)
+        gates = torch.empty((n_samples, n_q, n_cand), dtype=torch.float32, device=dev)
+    else:
+        mask = torch.empty(0, dtype=torch.uint8, device=dev)
+        gates = torch.empty(0, dtype=torch.float32, device=dev)
+    scratch = _workspace(lib.ragb_router_scratch_bytes(n_q, norm_mode), dev)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    with torch.cuda.device(dev):
+        check(lib.ragb_router_mc_dropout(_ptr(bm25), _ptr(dense), n_q, n_cand, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2),
+                                         _ptr(stats), hidden, norm_mode, n_samples, p_drop, seed, offset, mask_layout,
+                                         sm_count, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]),
+                                         _ptr(variance), _ptr(consensus), _ptr(mask) if dump else None,
+                                         _ptr(gates) if dump else None, _ptr(scratch), _stream()))
+    return outs[0], outs[1], outs[2], outs[3], variance, consensus, mask, gates
+
+
+@router_mc_dropout.register_fake
+def _(bm25, dense, w1, b1, w2, b2, stats, norm_mode, n_samples, p_drop, seed, offset, mask_layout, dump):
+    n_q, n_cand = bm25.shape
+    e = [torch.empty_like(bm25) for _ in range(4)]
+    hidden = b1.shape[0]
+    mask = bm25.new_empty((n_samples, n_q * n_cand, hidden) if dump else (0,), dtype=torch.uint8)
+    gates = bm25.new_empty((n_samples, n_q, n_cand) if dump else (0,))
+    return (e[0], e[1], e[2], e[3], bm25.new_empty((n_q,)), bm25.new_empty((n_q,), dtype=torch.int32), mask, gates)
+
+
+def launch_count() -> int:
+    """Number of kernels libragb200 has launched in this process (bench.py's gpu_launches)."""
+    return _lib.launch_count()

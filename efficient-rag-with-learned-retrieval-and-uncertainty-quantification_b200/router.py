@@ -1,0 +1,187 @@
+"""Drop-in ``RetrievalRouter`` whose inference path runs in libragb200's kernels.
+
+Mirrors rag_uq/router.py:34-232: same ``RouterConfig``, same parameter / buffer names
+(``scorer.0.weight`` [H,3], ``scorer.0.bias`` [H], ``scorer.3.weight`` [1,H], ``scorer.3.bias``
+[1], ``bm25_mean``, ``bm25_std``, ``dense_mean``, ``dense_std``) so ``load_state_dict`` of a
+reference checkpoint (router.py:499-517, loaded at experiments/run_evaluation.py:128-131) works
+unchanged, same ``forward`` / ``hybrid_rerank`` / ``get_routing_decision`` signatures and return
+types.  As in the reference, ``stats_initialized`` is a plain attribute that is NOT part of the
+state dict: straight after ``load_state_dict`` the gate normalises with the statistics of the
+call itself (router.py:133-136) until the caller sets ``stats_initialized = True``.
+
+Training (``ApproxNDCGLoss`` / ``RouterTrainer``, router.py:235-561) is outside the hot path:
+the kernels produce no autograd graph.  ``forward`` raises if a gradient is requested.
+
+New on top of the reference: ``mc_dropout`` - T stochastic passes with the Dropout of
+router.py:78 active, drawn in-kernel from Philox4x32-10, aggregated with the arithmetic of
+``MCDropoutConfidence`` (rag_uq/confidence.py:195-202, 258-264).
+"""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .confidence import ConfidenceResult, RouterUncertainty
+
+logger = logging.getLogger(__name__)
+
+
+@dataclass
+class RouterConfig:
+    """rag_uq/router.py:34-41, field for field (checkpoints pickle this class by value)."""
+    hidden_dim: int = 64
+    dropout: float = 0.1
+    temperature: float = 1.0
+    num_layers: int = 2
+    use_batch_norm: bool = False
+
+
+NORM_BATCH, NORM_RUNNING, NORM_PER_QUERY = 0, 1, 2
+
+
+class RetrievalRouter(nn.Module):
+    def __init__(self, config: Optional[Any] = None):
+        super().__init__()
+        self.config = config or RouterConfig()
+        hidden = int(self.config.hidden_dim)
+        if int(self.config.num_layers) != 2 or bool(getattr(self.config, "use_batch_norm", False)):
+            raise ValueError("rag_uq_b200.RetrievalRouter implements num_layers=2, use_batch_norm=False "
+                             "(the reference defaults, router.py:40-41); there is no fallback for other shapes")
+        if hidden % 4 or not (4 <= hidden <= 128):
+            raise ValueError("hidden_dim must be a multiple of 4 in [4, 128]")
+        # identical module tree => identical state-dict keys and identical default initialisation
+        self.scorer = nn.Sequential(
+            nn.Linear(3, hidden), nn.ReLU(), nn.Dropout(float(self.config.dropout)), nn.Linear(hidden, 1), nn.Sigmoid()
+        )
+        self.register_buffer("bm25_mean", torch.tensor(0.0))
+        self.register_buffer("bm25_std", torch.tensor(1.0))
+        self.register_buffer("dense_mean", torch.tensor(0.0))
+        self.register_buffer("dense_std", torch.tensor(1.0))
+        self.stats_initialized = False
+        logger.info(f"Initialized RetrievalRouter with {self._count_params()} parameters")
+
+    def _count_params(self) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    # ------------------------------------------------------------------------------------
+    def _weights(self):
+        lin1, lin2 = self.scorer[0], self.scorer[3]
+        stats = torch.stack([self.bm25_mean, self.bm25_std, self.dense_mean, self.dense_std]).to(torch.float32)
+        return (lin1.weight.detach(), lin1.bias.detach(), lin2.weight.detach().reshape(-1), lin2.bias.detach(), stats)
+
+    def _check(self, bm25_scores: torch.Tensor, dense_scores: torch.Tensor):
+        if not bm25_scores.is_cuda:
+            raise NotImplementedError("rag_uq_b200.RetrievalRouter runs on CUDA (sm_100) tensors only; "
+                                      "move the module and its inputs to the GPU (there is no CPU path)")
+        if self.scorer[0].weight.device != bm25_scores.device:
+            raise RuntimeError("router parameters and scores live on different devices")
+        if torch.is_grad_enabled() and (bm25_scores.requires_grad or dense_scores.requires_grad or
+                                        (self.training and any(p.requires_grad for p in self.parameters()))):
+            raise NotImplementedError("the B200 router kernels are inference-only (no autograd); train with the "
+                                      "reference RouterTrainer and load its checkpoint, or call under torch.no_grad()")
+        return bm25_scores.to(torch.float32), dense_scores.to(torch.float32)
+
+    def _update_running_stats(self, bm25_scores, dense_scores):
+        """EMA of router.py:114-128 (training-mode side effect; tiny host-driven reductions)."""
+        eps, momentum = 1e-6, 0.1
+        with torch.no_grad():
+            self.bm25_mean = (1 - momentum) * self.bm25_mean + momentum * bm25_scores.mean()
+            self.bm25_std = (1 - momentum) * self.bm25_std + momentum * (bm25_scores.std() + eps)
+            self.dense_mean = (1 - momentum) * self.dense_mean + momentum * dense_scores.mean()
+            self.dense_std = (1 - momentum) * self.dense_std + momentum * (dense_scores.std() + eps)
+            self.stats_initialized = True
+
+    def forward(self, bm25_scores: torch.Tensor, dense_scores: torch.Tensor, update_stats: bool = True,
+                per_query_stats: bool = False) -> torch.Tensor:
+        """Gate weights [B, P] in (0, 1); 0 favours BM25, 1 favours dense (router.py:140-177).
+
+        ``per_query_stats`` (extension): when running statistics are not armed, normalise every
+        row with its own mean / std - what the reference's evaluation loop gets by calling the
+        router once per query with a [1, P] tensor.
+        """
+        bm25_scores, dense_scores = self._check(bm25_scores, dense_scores)
+        if update_stats and self.training:
+            self._update_running_stats(bm25_scores, dense_scores)
+        mode = NORM_RUNNING if self.stats_initialized else (NORM_PER_QUERY if per_query_stats else NORM_BATCH)
+        w1, b1, w2, b2, stats = self._weights()
+        if self.training and self.config.dropout > 0:
+            seed, offset = _philox_state(bm25_scores.device, bm25_scores.numel() * w1.shape[0])
+            out = ops.router_mc_dropout(bm25_scores, dense_scores, w1, b1, w2, b2, stats, mode, 1,
+                                        float(self.config.dropout), seed, offset, 1, True)
+            return out[7][0]
+        gate, _ = ops.router_forward(bm25_scores, dense_scores, w1, b1, w2, b2, stats, mode)
+        return gate
+
+    def hybrid_rerank(self, bm25_scores: torch.Tensor, dense_scores: torch.Tensor,
+                      top_k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(top-k fused scores, int64 indices), fused = w*dense + (1-w)*bm25 (router.py:179-202)."""
+        bm25_scores, dense_scores = self._check(bm25_scores, dense_scores)
+        mode = NORM_RUNNING if self.stats_initialized else NORM_BATCH
+        w1, b1, w2, b2, stats = self._weights()
+        _, fused = ops.router_forward(bm25_scores, dense_scores, w1, b1, w2, b2, stats, mode)
+        k = min(top_k, fused.size(-1))
+        values, indices = ops.topk_rows(fused, k)
+        return torch.return_types.topk((values, indices.to(torch.int64)))
+
+    def get_routing_decision(self, bm25_scores: torch.Tensor, dense_scores: torch.Tensor,
+                             threshold: float = 0.5) -> Dict[str, Any]:
+        """router.py:204-232."""
+        with torch.no_grad():
+            was_training = self.training
+            self.eval()
+            weights = self.forward(bm25_scores, dense_scores, update_stats=False)
+            self.train(was_training)
+            return {
+                "avg_dense_weight": weights.mean().item(),
+                "weight_std": weights.std().item(),
+                "dense_preferred_ratio": (weights > threshold).float().mean().item(),
+                "bm25_preferred_ratio": (weights <= threshold).float().mean().item(),
+                "routing_weights": weights.cpu().numpy(),
+            }
+
+    # ------------------------------------------------------------------------------------
+    def mc_dropout(self, bm25_scores: torch.Tensor, dense_scores: torch.Tensor, n_samples: int = 30,
+                   seed: Optional[int] = None, offset: int = 0, torch_layout: bool = False,
+                   per_query_stats: bool = False, return_samples: bool = False) -> RouterUncertainty:
+        """T stochastic gate evaluations per candidate with the router's Dropout active.
+
+        ``seed`` None draws (seed, offset) from torch's CUDA generator and advances it the way T
+        ``F.dropout`` calls would.  ``torch_layout`` maps elements to Philox counters exactly as
+        torch's fused CUDA dropout does for the [B*P, H] hidden tensor, so sample t equals the
+        t-th ``router(..., update_stats=False)`` call of a reference module in train mode.
+        """
+        bm25_scores, dense_scores = self._check(bm25_scores, dense_scores)
+        mode = NORM_RUNNING if self.stats_initialized else (NORM_PER_QUERY if per_query_stats else NORM_BATCH)
+        w1, b1, w2, b2, stats = self._weights()
+        if seed is None:
+            seed, offset = _philox_state(bm25_scores.device, bm25_scores.numel() * w1.shape[0], n_samples)
+        out = ops.router_mc_dropout(bm25_scores, dense_scores, w1, b1, w2, b2, stats, mode, int(n_samples),
+                                    float(self.config.dropout), int(seed), int(offset), 1 if torch_layout else 0,
+                                    bool(return_samples))
+        return RouterUncertainty(mean_gate=out[0], std_gate=out[1], mean_fused=out[2], std_fused=out[3],
+                                 variance=out[4], consensus=out[5].to(torch.int64), n_samples=int(n_samples),
+                                 masks=out[6] if return_samples else None, gates=out[7] if return_samples else None)
+
+
+def torch_dropout_increment(n_elements: int, sm_count: int) -> int:
+    """Philox offset consumed by one torch fused-dropout call over n float elements."""
+    block = 256
+    grid = min(sm_count * (2048 // block), (n_elements + block - 1) // block)
+    return ((n_elements - 1) // (block * grid * 4) + 1) * 4
+
+
+def _philox_state(device, n_elements: int, n_calls: int = 1) -> Tuple[int, int]:
+    """(seed, offset) of torch's CUDA generator, advanced as n_calls dropout launches would."""
+    gen = torch.cuda.default_generators[torch.device(device).index or 0]
+    seed, offset = int(gen.initial_seed()), int(gen.get_offset())
+    inc = torch_dropout_increment(n_elements, torch.cuda.get_device_properties(device).multi_processor_count)
+    gen.set_offset(offset + inc * n_calls)
+    return seed & ((1 << 63) - 1) if seed >= (1 << 63) else seed, offset
+
+
+__all__ = ["RouterConfig", "RetrievalRouter", "ConfidenceResult", "RouterUncertainty"]

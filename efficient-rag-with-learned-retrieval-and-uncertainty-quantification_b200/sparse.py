@@ -1,0 +1,134 @@
+"""Term-major CSR inverted index resident in HBM, and its builders.
+
+GPU equivalent of what ``BM25Okapi.__init__`` builds per ``BM25Index.add_documents`` /
+``_load`` (rag_uq/streaming_index.py:140-142, 219-220): per-document term counts, document
+lengths, average length and idf with the epsilon floor.  Raw term frequencies and lengths are
+kept (not baked impacts), so global statistics can be refreshed in O(V + N) when documents
+are added or when shards exchange their document frequencies.
+
+Layout (one shard = a contiguous range of global passage rows):
+    term_off [V+1] int64   postings of term t are [term_off[t], term_off[t+1])
+    post_doc [nnz] int32   LOCAL row of the posting, ascending inside a term
+    post_tf  [nnz] int16   bit pattern of a uint16 term frequency (clipped at 65535)
+    doc_len  [N]   int32
+    df       [V]   int32   LOCAL document frequency (summed over shards -> global)
+    idf      [V]   float32, norm [N] float32   set by ``finalize``
+The sorting / segmenting below is torch plumbing (sort, unique_consecutive, cumsum); the
+statistics and all scoring run in the library's own kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+
+
+@dataclass
+class SparseShard:
+    term_off: Tensor
+    post_doc: Tensor
+    post_tf: Tensor
+    doc_len: Tensor
+    df: Tensor
+    n_docs: int
+    vocab: int
+    id_base: int = 0
+    k1: float = 1.5
+    b: float = 0.75
+    epsilon: float = 0.25
+    idf: Optional[Tensor] = None
+    norm: Optional[Tensor] = None
+    corpus_size: int = 0
+    avgdl: float = 0.0
+
+    @property
+    def nnz(self) -> int:
+        return int(self.post_doc.shape[0])
+
+    def finalize(self, df_global: Optional[Tensor] = None, corpus_size: Optional[int] = None,
+                 total_len: Optional[int] = None) -> "SparseShard":
+        """(Re)compute idf[V] and norm[N] from GLOBAL statistics (defaults: this shard alone)."""
+        df_global = self.df if df_global is None else df_global
+        self.corpus_size = self.n_docs if corpus_size is None else int(corpus_size)
+        total = int(self.doc_len.sum()) if total_len is None else int(total_len)
+        self.avgdl = total / self.corpus_size
+        self.idf = ops.bm25_build_idf(df_global.to(torch.int32), self.corpus_size, self.epsilon)
+        self.norm = ops.bm25_build_norm(self.doc_len, self.avgdl, self.k1, self.b)
+        return self
+
+    def score_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int):
+        return ops.bm25_score_topk(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1,
+                                   q_terms, q_off, max_terms, self.id_base, k)
+
+    def scores(self, q_terms: Tensor, q_off: Tensor, max_terms: int) -> Tensor:
+        return ops.bm25_scores(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1, q_terms,
+                               q_off, max_terms)
+
+
+def _segment(doc_off: Tensor, doc_tok: Tensor, vocab: int):
+    """(term, local doc, tf) triples sorted by (term, doc) + per-term posting counts for one block of documents."""
+    n = doc_off.shape[0] - 1
+    lens = doc_off[1:] - doc_off[:-1]
+    owner = torch.repeat_interleave(torch.arange(n, device=doc_tok.device, dtype=torch.int64), lens)
+    key = doc_tok.to(torch.int64) * n + owner
+    key = torch.sort(key).values
+    pair, tf = torch.unique_consecutive(key, return_counts=True)
+    term = pair // n
+    doc = (pair - term * n).to(torch.int32)
+    counts = torch.bincount(term, minlength=vocab)
+    return term, doc, tf.clamp_(max=65535).to(torch.int16), counts, lens.to(torch.int32)
+
+
+def build_shard(doc_off: Tensor, doc_tok: Tensor, vocab: int, id_base: int = 0, k1: float = 1.5, b: float = 0.75,
+                epsilon: float = 0.25) -> SparseShard:
+    """CSR from a doc-major token list (doc_off int64 [N+1], doc_tok int32 [total]) on doc_tok's device."""
+    if doc_tok.numel() and (int(doc_tok.min()) < 0 or int(doc_tok.max()) >= vocab):
+        raise ValueError("token id outside [0, vocab)")
+    term, doc, tf, counts, lens = _segment(doc_off.to(doc_tok.device), doc_tok, vocab)
+    term_off = torch.zeros(vocab + 1, dtype=torch.int64, device=doc_tok.device)
+    torch.cumsum(counts, 0, out=term_off[1:])
+    return SparseShard(term_off, doc.contiguous(), tf.contiguous(), lens.contiguous(), counts.to(torch.int32),
+                       n_docs=int(lens.shape[0]), vocab=vocab, id_base=id_base, k1=k1, b=b, epsilon=epsilon)
+
+
+def build_shard_blocked(block_iter, n_docs: int, vocab: int, device, id_base: int = 0, k1: float = 1.5,
+                        b: float = 0.75, epsilon: float = 0.25) -> SparseShard:
+    """Same result as ``build_shard`` for corpora too large to sort at once.
+
+    ``block_iter`` yields (doc_off, doc_tok) for consecutive blocks of documents.  Every block
+    is segmented on its own; blocks are then scattered into the term-major layout in document
+    order, which keeps post_doc ascending inside each term.
+    """
+    blocks: List[tuple] = []
+    total_counts = torch.zeros(vocab, dtype=torch.int64, device=device)
+    first = 0
+    for doc_off, doc_tok in block_iter:
+        term, doc, tf, counts, lens = _segment(doc_off.to(device), doc_tok.to(device), vocab)
+        blocks.append((term.to(torch.int32), doc, tf, counts, lens, first))
+        total_counts += counts
+        first += int(lens.shape[0])
+    if first != n_docs:
+        raise ValueError(f"blocks hold {first} documents, expected {n_docs}")
+    term_off = torch.zeros(vocab + 1, dtype=torch.int64, device=device)
+    torch.cumsum(total_counts, 0, out=term_off[1:])
+    nnz = int(term_off[-1])
+    post_doc = torch.empty(nnz, dtype=torch.int32, device=device)
+    post_tf = torch.empty(nnz, dtype=torch.int16, device=device)
+    doc_len = torch.empty(n_docs, dtype=torch.int32, device=device)
+    placed = torch.zeros(vocab, dtype=torch.int64, device=device)
+    while blocks:
+        term, doc, tf, counts, lens, base = blocks.pop(0)
+        t64 = term.to(torch.int64)
+        start_in_block = torch.cumsum(counts, 0) - counts
+        dst = term_off[:-1][t64] + placed[t64] + (torch.arange(t64.shape[0], device=device) - start_in_block[t64])
+        post_doc[dst] = doc + base
+        post_tf[dst] = tf
+        doc_len[base:base + lens.shape[0]] = lens
+        placed += counts
+        del term, doc, tf, counts, lens, t64, dst
+    return SparseShard(term_off, post_doc, post_tf, doc_len, total_counts.to(torch.int32), n_docs=n_docs, vocab=vocab,
+                       id_base=id_base, k1=k1, b=b, epsilon=epsilon)

@@ -1,0 +1,169 @@
+/*
+ * ragb200.h - C ABI of the B200-native retrieval-scoring hot path.
+ *
+ * One shared library (libragb200.so, sm_100a only).  Every entry point
+ *   - is extern "C", takes plain pointers and sizes (no torch / C++ types),
+ *   - returns 0 (RAGB_OK) or a negative RAGB_E* code; ragb_last_error() holds the text,
+ *   - enqueues work on the caller's stream and never synchronises it,
+ *   - never allocates device memory: the caller owns every buffer, including the
+ *     workspace whose size the matching ragb_*_workspace_bytes() reports,
+ *   - refuses to run (RAGB_EARCH) on a device whose compute capability is not 10.x.
+ *     There is no CPU or generic-GPU fallback.
+ *
+ * The reference (manikya7022/Efficient-RAG-with-Learned-Retrieval-and-Uncertainty-
+ * Quantification) is pure Python and has no FFI boundary of its own;
+ * each function below cites the reference call site (file:line under the reference
+ * root) whose arithmetic it replaces.  Candidate ids are int32 GLOBAL passage row
+ * numbers (id_base + local row); -1 marks an empty slot.  Score ties are broken the
+ * same way everywhere: higher score first, then lower id.
+ */
+#ifndef RAGB200_H_
+#define RAGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAGB_OK        0
+#define RAGB_EINVAL  (-1)   /* bad argument (null pointer, size out of range, misalignment) */
+#define RAGB_EARCH   (-2)   /* device is not sm_100 (B200); nothing was launched            */
+#define RAGB_ECUDA   (-3)   /* a CUDA runtime / driver call failed; see ragb_last_error()   */
+#define RAGB_ELIMIT  (-4)   /* argument exceeds a documented kernel limit                   */
+#define RAGB_ENOSPC  (-5)   /* workspace too small                                          */
+
+#define RAGB_MAX_TOPK          256    /* k accepted by every *_topk entry point             */
+#define RAGB_MAX_QUERY_TERMS   64     /* tokens per query accepted by ragb_bm25_*           */
+#define RAGB_GEMV_MAX_BATCH    8      /* queries per call of ragb_dense_gemv_topk           */
+#define RAGB_ROUTER_MAX_HIDDEN 128    /* RouterConfig.hidden_dim accepted (router.py:37)    */
+
+typedef void* ragb_stream_t;          /* a cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------- */
+int         ragb_abi_version(void);
+const char* ragb_last_error(void);                 /* thread-local, valid until next call  */
+int         ragb_device_check(int device);         /* RAGB_OK iff cc major == 10           */
+int64_t     ragb_launch_count(void);               /* kernels launched by this library     */
+
+/* ---- BM25 statistics : rank_bm25 BM25Okapi._calc_idf / _initialize
+ *      (reached from rag_uq/streaming_index.py:142,220) ------------------------------- */
+/* idf[t] = ln(N-df+.5) - ln(df+.5) in float64; terms with idf < 0 get epsilon * mean(idf)
+ * (mean over terms with df > 0, negatives included); df == 0 -> 0.  Output float32.
+ * scratch: >= ragb_bm25_idf_scratch_bytes(vocab) bytes. */
+size_t ragb_bm25_idf_scratch_bytes(int64_t vocab);
+int ragb_bm25_build_idf(const int32_t* df, int64_t vocab, int64_t corpus_size, double epsilon,
+                        float* idf_out, void* scratch, size_t scratch_bytes, ragb_stream_t stream);
+/* norm[d] = k1 * (1 - b + b * doc_len[d] / avgdl), evaluated in float64, stored float32 */
+int ragb_bm25_build_norm(const int32_t* doc_len, int64_t n_docs, double avgdl, double k1, double b,
+                         float* norm_out, ragb_stream_t stream);
+
+/* ---- BM25 scoring : rank_bm25 BM25Okapi.get_scores + BM25Index.search
+ *      (rag_uq/streaming_index.py:165-179) --------------------------------------------
+ * Term-major CSR over the LOCAL shard: postings of term t are
+ * post_doc/post_tf[term_off[t] .. term_off[t+1]) with post_doc ascending local rows.
+ * Queries are ragged lists of term ids q_terms[q_off[i] .. q_off[i+1]); every OCCURRENCE
+ * contributes; ids outside [0, vocab) are out-of-vocabulary and contribute 0.
+ * max_query_terms (<= RAGB_MAX_QUERY_TERMS) is the caller's bound on the longest query;
+ * it sizes the per-warp cursor table and longer queries are cut to it.
+ * score = sum idf[t] * tf * (k1 + 1) / (tf + norm[d]).   Only score > 0 is returned
+ * (streaming_index.py:176); short lists are padded with id -1 / score 0. */
+size_t ragb_bm25_topk_workspace_bytes(int32_t n_queries, int64_t n_docs, int32_t k);
+int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf,
+                         const float* norm, const float* idf, int64_t vocab, double k1,
+                         const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
+                         int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
+                         float* out_score, int32_t* out_id,
+                         void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+/* Same arithmetic, full score vectors out_scores[n_queries, n_docs] (get_scores itself). */
+int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf,
+                     const float* norm, const float* idf, int64_t vocab, double k1,
+                     const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
+                     int32_t max_query_terms, int64_t n_docs, float* out_scores, ragb_stream_t stream);
+
+/* ---- dense scoring : DenseIndex.search (rag_uq/streaming_index.py:353-370) -----------
+ * Exact inner product of bf16 query rows with bf16 passage rows (unit rows -> cosine,
+ * i.e. the reference's 1 - distance), fp32 accumulation, fused per-query top-k.
+ * passages [n_rows, dim] row-major bf16, 16-byte aligned; dim % 64 == 0. */
+size_t ragb_dense_gemv_workspace_bytes(int32_t n_queries, int32_t k);
+int ragb_dense_gemv_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
+                         const void* queries_bf16, int32_t n_queries, int32_t k, int64_t id_base,
+                         float* out_score, int32_t* out_id,
+                         void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+/* tcgen05 / TMEM / TMA path for query batches.  n_queries is padded internally to a
+ * multiple of 128 (queries_bf16 must hold n_queries rows; padding rows are zero-filled
+ * by TMA out-of-bounds handling).  variant: 0 = A (queries) and B (passages) both
+ * streamed through shared memory; 1 = query slab resident in TMEM.  */
+size_t ragb_dense_mma_workspace_bytes(int32_t n_queries, int32_t k);
+int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
+                        const void* queries_bf16, int32_t n_queries, int32_t k, int64_t id_base,
+                        int32_t variant, float* out_score, int32_t* out_id,
+                        void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+/* Plain score matrix out[n_queries, n_rows] fp32 (small shapes, tests, full-fusion mode). */
+int ragb_dense_scores(const void* passages_bf16, int64_t n_rows, int32_t dim,
+                      const void* queries_bf16, int32_t n_queries, float* out_scores,
+                      ragb_stream_t stream);
+
+/* ---- selection ------------------------------------------------------------------------
+ * np.argsort(scores)[::-1][:k] (streaming_index.py:172) / torch.topk (router.py:202) */
+size_t ragb_topk_rows_workspace_bytes(int32_t n_rows, int64_t n_cols, int32_t k);
+int ragb_topk_rows(const float* scores, int32_t n_rows, int64_t n_cols, int32_t k,
+                   float* out_score, int32_t* out_index,
+                   void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+/* Merge n_lists candidate lists per query ([n_queries, n_lists, k_in], id -1 = empty) into
+ * one top-k_out; used for intra-GPU stripes and for the lists all-gathered across GPUs. */
+int ragb_topk_merge(const float* in_score, const int32_t* in_id, int32_t n_queries, int32_t n_lists,
+                    int32_t k_in, int32_t k_out, float* out_score, int32_t* out_id,
+                    ragb_stream_t stream);
+
+/* ---- pool fusion : HybridRetriever.hybrid_search (rag_uq/streaming_index.py:484-523)
+ * Union of the two pools by id, missing score = 0.0, each score divided by the union
+ * maximum ("max(...) or 1"), averaged, sorted descending, cut to k.  Padded with id -1. */
+int ragb_hybrid_fuse_topk(const float* bm25_score, const int32_t* bm25_id,
+                          const float* dense_score, const int32_t* dense_id,
+                          int32_t n_queries, int32_t pool, int32_t k,
+                          int32_t* out_id, float* out_bm25, float* out_dense, float* out_hybrid,
+                          ragb_stream_t stream);
+
+/* ---- router gate : RetrievalRouter.forward / hybrid_rerank (rag_uq/router.py:100-202)
+ * Inputs bm25 / dense [n_rows, n_cand] fp32.  w1 [hidden,3], b1 [hidden], w2 [hidden],
+ * b2 [1], stats [4] = bm25_mean, bm25_std, dense_mean, dense_std - all DEVICE float32
+ * (the reference's state-dict tensors, untouched).  norm_mode:
+ *   1 = running statistics (stats_initialized == True, router.py:130-132)
+ *   0 = statistics of this very call over the whole [n_rows, n_cand] input
+ *       (router.py:133-136; torch.std is the unbiased estimator, one element -> NaN)
+ *   2 = the same, per row: what the reference's evaluation loop computes when it calls
+ *       the router once per query with a [1, P] tensor (experiments/run_evaluation.py:171-177)
+ * out_gate = sigmoid(...) in (0,1); out_fused = gate*dense + (1-gate)*bm25 on the RAW
+ * scores (router.py:199).  Either output may be NULL.  scratch: device memory of at least
+ * ragb_router_scratch_bytes(n_rows, norm_mode) bytes (unused for norm_mode 1). */
+size_t ragb_router_scratch_bytes(int32_t n_rows, int32_t norm_mode);
+int ragb_router_forward(const float* bm25, const float* dense, int32_t n_rows, int32_t n_cand,
+                        const float* w1, const float* b1, const float* w2, const float* b2,
+                        const float* stats, int32_t hidden, int32_t norm_mode,
+                        float* out_gate, float* out_fused, void* scratch, ragb_stream_t stream);
+
+/* ---- MC-Dropout : nn.Dropout (router.py:78) sampled T times, aggregated as
+ *      MCDropoutConfidence does (rag_uq/confidence.py:195-202, 258-264) ----------------
+ * One Philox4x32-10 stream (curand layout) seeded (seed, offset); mask_layout 1
+ * reproduces torch's fused CUDA dropout element->counter mapping for a [B*P, hidden]
+ * tensor on a device with sm_count SMs, pass t using offset + t * increment;
+ * mask_layout 0 is the library's own (subsequence = candidate, draw = t*hidden/4+u/4).
+ * Outputs [n_queries, n_cand]: mean/std (population) of gate and fused score;
+ * per query: variance (std of L2 distances of the T gate vectors to their centroid),
+ * consensus sample index.  mask_dump (uint8 [T, B*P, hidden]) and gate_dump
+ * (float [T, B, P]) may be NULL.  norm_mode and scratch as for ragb_router_forward. */
+int ragb_router_mc_dropout(const float* bm25, const float* dense, int32_t n_queries, int32_t n_cand,
+                           const float* w1, const float* b1, const float* w2, const float* b2,
+                           const float* stats, int32_t hidden, int32_t norm_mode,
+                           int32_t n_samples, double p_drop, uint64_t seed, uint64_t offset,
+                           int32_t mask_layout, int32_t sm_count,
+                           float* mean_gate, float* std_gate, float* mean_fused, float* std_fused,
+                           float* variance, int32_t* consensus,
+                           uint8_t* mask_dump, float* gate_dump, void* scratch, ragb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAGB200_H_ */

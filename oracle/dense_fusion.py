@@ -1,0 +1,79 @@
+"""CPU restatement of dense scoring, top-k and pool fusion.  TEST INFRASTRUCTURE ONLY.
+
+Follows
+  * ``DenseIndex.search``                  ``rag_uq/streaming_index.py:338-370``
+    (ChromaDB cosine-space HNSW, ``score = 1 - distance``).  The oracle is the
+    EXACT cosine the approximate index is trying to reach, evaluated on the
+    bf16-rounded unit rows the product stores, accumulated in float64.
+  * ``HybridRetriever.hybrid_search``      ``rag_uq/streaming_index.py:464-523``
+  * ``HybridRetriever.get_scores_for_router`` ``rag_uq/streaming_index.py:525-557``
+
+PARITY UNPINNED for all three: the reference has no test or fixture for
+``streaming_index.py`` and chromadb is not installable in this image.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+
+def dense_scores(passages_f32: np.ndarray, queries_f32: np.ndarray) -> np.ndarray:
+    """[B, N] float64 inner products of already bf16-rounded (float32-held) rows."""
+    return queries_f32.astype(np.float64) @ passages_f32.astype(np.float64).T
+
+
+def topk_desc(scores: np.ndarray, k: int, positive_only: bool = False) -> List[List[Tuple[int, float]]]:
+    """Row-wise top-k with the framework's tie rule: score desc, then index asc.
+
+    ``positive_only`` reproduces ``if scores[idx] > 0`` (streaming_index.py:176).
+    """
+    out = []
+    idx = np.arange(scores.shape[1])
+    for row in scores:
+        order = np.lexsort((idx, -row))[:k]
+        out.append([(int(i), float(row[i])) for i in order if (row[i] > 0 or not positive_only)])
+    return out
+
+
+def hybrid_search(bm25_pool: Sequence[Tuple[int, float]], dense_pool: Sequence[Tuple[int, float]],
+                  top_k: int = 10) -> List[Tuple[int, float, float, float]]:
+    """Pool fusion, streaming_index.py:484-523.  Returns (id, bm25, dense, hybrid) rows.
+
+    Union of the two pools, a score missing from one pool is 0.0 (:498-499), each
+    score divided by the pool-union maximum - ``max(...) or 1`` (:513-514) -
+    averaged (:517-519), sorted descending (:521), cut to top_k (:523).  Tie order
+    in the reference depends on set iteration order; we fix it to id ascending.
+    """
+    b: Dict[int, float] = dict(bm25_pool)
+    d: Dict[int, float] = dict(dense_pool)
+    ids = sorted(set(b) | set(d))
+    if not ids:
+        return []
+    rows = [(i, b.get(i, 0.0), d.get(i, 0.0)) for i in ids]
+    max_b = max(r[1] for r in rows) or 1
+    max_d = max(r[2] for r in rows) or 1
+    fused = [(i, sb, sd, (sb / max_b + sd / max_d) / 2) for (i, sb, sd) in rows]
+    fused.sort(key=lambda r: (-r[3], r[0]))
+    return fused[:top_k]
+
+
+def scores_for_router(bm25_pool, dense_pool, num_passages: int = 20):
+    """streaming_index.py:537-557: hybrid_search(top_k=num_passages) split into aligned
+    lists and padded with 0.0 / id -1 (the reference pads ids with "")."""
+    rows = hybrid_search(bm25_pool, dense_pool, top_k=num_passages)
+    bm = [r[1] for r in rows]
+    de = [r[2] for r in rows]
+    ids = [r[0] for r in rows]
+    while len(bm) < num_passages:
+        bm.append(0.0)
+        de.append(0.0)
+        ids.append(-1)
+    return bm, de, ids
+
+
+def merge_topk(parts: Sequence[Sequence[Tuple[int, float]]], k: int) -> List[Tuple[int, float]]:
+    """Merge per-shard candidate lists into one global top-k (score desc, id asc)."""
+    flat = [c for part in parts for c in part]
+    flat.sort(key=lambda c: (-c[1], c[0]))
+    return flat[:k]

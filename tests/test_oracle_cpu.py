@@ -1,0 +1,211 @@
+"""The oracle against its pins: golden vectors, known answers, the live reference (when mounted)."""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bm25_okapi, dense_fusion, philox, router as router_oracle
+
+REFERENCE = Path("/root/reference")
+
+
+# ------------------------------------------------------------------------------------ BM25
+@pytest.fixture(scope="module")
+def known(golden_dir):
+    with open(golden_dir / "bm25_known_answers.json") as fh:
+        return json.load(fh)
+
+
+def _csr_from_text(corpus):
+    docs = [bm25_okapi.tokenize(t) for t in corpus]
+    vocab = {}
+    ids = [[vocab.setdefault(w, len(vocab)) for w in d] for d in docs]
+    off = np.concatenate([[0], np.cumsum([len(d) for d in ids])])
+    return vocab, bm25_okapi.OkapiCsr(off, np.concatenate(ids), len(vocab)), docs
+
+
+def test_bm25_known_answers_literal(known):
+    model = bm25_okapi.OkapiLiteral([bm25_okapi.tokenize(t) for t in known["corpus"]])
+    assert model.avgdl == pytest.approx(known["avgdl"], rel=1e-15)
+    assert model.average_idf == pytest.approx(known["average_idf"], rel=1e-13)
+    for word, val in known["idf"].items():
+        assert model.idf[word] == pytest.approx(val, rel=1e-12, abs=1e-15)
+    for query, want in known["queries"].items():
+        got = model.get_scores(bm25_okapi.tokenize(query))
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-15, err_msg=query)
+
+
+def test_bm25_known_answers_csr(known):
+    vocab, model, _ = _csr_from_text(known["corpus"])
+    for query, want in known["queries"].items():
+        terms = [vocab.get(w, -1) for w in bm25_okapi.tokenize(query)]
+        np.testing.assert_allclose(model.get_scores(terms), want, rtol=1e-12, atol=1e-15, err_msg=query)
+
+
+def test_bm25_survey_special_cases(known):
+    """idf == 0 stays 0 (df == N/2), negative idf gets the epsilon floor, OOV query -> no result."""
+    model = bm25_okapi.OkapiLiteral([bm25_okapi.tokenize(t) for t in known["corpus"]])
+    assert model.idf["sun"] == 0.0 and model.idf["bright"] == 0.0
+    assert model.idf["the"] == pytest.approx(0.25 * model.average_idf)
+    assert model.idf["is"] == pytest.approx(0.25 * model.average_idf)
+    assert bm25_okapi.index_search(model.get_scores(["zzz"]), 10) == []
+    # duplicates count once per occurrence
+    one = model.get_scores(["python", "language"])
+    two = model.get_scores(["python", "python", "language"])
+    assert two[4] - one[4] == pytest.approx(model.get_scores(["python"])[4])
+
+
+def test_bm25_literal_equals_csr_random():
+    rng = np.random.default_rng(5)
+    vocab_n = 300
+    docs = [list(rng.zipf(1.3, size=rng.integers(5, 60)) % vocab_n) for _ in range(400)]
+    lit = bm25_okapi.OkapiLiteral(docs)
+    off = np.concatenate([[0], np.cumsum([len(d) for d in docs])])
+    csr = bm25_okapi.OkapiCsr(off, np.concatenate(docs), vocab_n)
+    assert csr.average_idf == pytest.approx(lit.average_idf, rel=1e-12)
+    for _ in range(20):
+        q = list(rng.integers(0, vocab_n + 5, size=rng.integers(1, 9)))
+        np.testing.assert_allclose(csr.get_scores(q), lit.get_scores(q), rtol=1e-11, atol=1e-14)
+
+
+def test_index_search_order_and_positivity():
+    scores = np.array([0.0, 2.0, 2.0, -1.0, 3.0, 0.0])
+    assert bm25_okapi.index_search(scores, 10) == [(4, 3.0), (1, 2.0), (2, 2.0)]
+    assert bm25_okapi.index_search(scores, 2) == [(4, 3.0), (1, 2.0)]
+
+
+# ---------------------------------------------------------------------------------- fusion
+def test_hybrid_search_restatement():
+    bm = [(3, 4.0), (7, 2.0), (9, 1.0)]
+    de = [(7, 0.9), (1, 0.6), (3, 0.3)]
+    rows = dense_fusion.hybrid_search(bm, de, top_k=10)
+    want = {3: (4 / 4 + 0.3 / 0.9) / 2, 7: (2 / 4 + 0.9 / 0.9) / 2, 9: (1 / 4 + 0) / 2, 1: (0 + 0.6 / 0.9) / 2}
+    assert [r[0] for r in rows] == sorted(want, key=lambda i: (-want[i], i))
+    for r in rows:
+        assert r[3] == pytest.approx(want[r[0]])
+    assert dense_fusion.hybrid_search([], [], 5) == []
+    # "max(...) or 1": an all-zero side divides by 1
+    rows = dense_fusion.hybrid_search([], [(5, 0.0), (6, 0.0)], 5)
+    assert [r[3] for r in rows] == [0.0, 0.0] and [r[0] for r in rows] == [5, 6]
+    b, d, ids = dense_fusion.scores_for_router(bm, de, num_passages=6)
+    assert len(b) == len(d) == len(ids) == 6 and ids[-2:] == [-1, -1] and b[-1] == 0.0
+
+
+def test_topk_desc_ties():
+    s = np.array([[1.0, 5.0, 5.0, 0.0, 5.0]])
+    assert [i for i, _ in dense_fusion.topk_desc(s, 3)[0]] == [1, 2, 4]
+    assert [i for i, _ in dense_fusion.topk_desc(s, 10, positive_only=True)[0]] == [1, 2, 4, 0]
+
+
+# ---------------------------------------------------------------------------------- router
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(golden_dir / "router_golden.npz")
+
+
+def _state(gold, tag):
+    pre = f"{tag}/state/"
+    return {k[len(pre):]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith(pre)}
+
+
+@pytest.mark.parametrize("tag", ["h64", "h32"])
+def test_router_oracle_matches_golden(gold, tag):
+    state = _state(gold, tag)
+    b, d = torch.from_numpy(gold[f"{tag}/bm25"]), torch.from_numpy(gold[f"{tag}/dense"])
+    g0 = router_oracle.gate(b, d, state, stats_initialized=False)
+    assert torch.equal(g0, torch.from_numpy(gold[f"{tag}/gate_batchstat"]))
+    vals, idx = router_oracle.hybrid_rerank(b, d, state, False, 10)
+    torch.testing.assert_close(vals, torch.from_numpy(gold[f"{tag}/rerank_batchstat_vals"]), rtol=0, atol=0)
+    assert torch.equal(idx, torch.from_numpy(gold[f"{tag}/rerank_batchstat_idx"]))
+
+    run = dict(state)
+    for name, val in zip(["bm25_mean", "bm25_std", "dense_mean", "dense_std"], gold[f"{tag}/running_stats"]):
+        run[name] = torch.tensor(float(val))
+    g1 = router_oracle.gate(b, d, run, stats_initialized=True)
+    assert torch.equal(g1, torch.from_numpy(gold[f"{tag}/gate_running"]))
+    vals, idx = router_oracle.hybrid_rerank(b, d, run, True, 10)
+    assert torch.equal(idx, torch.from_numpy(gold[f"{tag}/rerank_running_idx"]))
+    bb, bd = torch.from_numpy(gold[f"{tag}/big_bm25"]), torch.from_numpy(gold[f"{tag}/big_dense"])
+    vals, idx = router_oracle.hybrid_rerank(bb, bd, run, True, 500)      # k > P clamps to P
+    assert vals.shape == (2, 300)
+    torch.testing.assert_close(vals, torch.from_numpy(gold[f"{tag}/big_rerank_vals"]), rtol=0, atol=0)
+
+    masks = torch.from_numpy(gold[f"{tag}/mc_masks"]).float()
+    for t in range(masks.shape[0]):
+        g = router_oracle.gate(b, d, run, True, keep_mask=masks[t])
+        torch.testing.assert_close(g, torch.from_numpy(gold[f"{tag}/mc_gates"][t]), rtol=1e-6, atol=1e-7)
+
+
+def test_router_oracle_mc_aggregation_matches_confidence_math(gold):
+    state = _state(gold, "h64")
+    b, d = torch.from_numpy(gold["h64/bm25"]), torch.from_numpy(gold["h64/dense"])
+    masks = torch.from_numpy(gold["h64/mc_masks"]).float()
+    out = router_oracle.mc_dropout(b, d, state, False, masks)
+    gates = torch.stack([router_oracle.gate(b, d, state, False, masks[t]) for t in range(masks.shape[0])]).numpy()
+    for q in range(b.shape[0]):
+        emb = gates[:, q, :]                                  # the T "embeddings" of query q
+        centroid = emb.mean(axis=0)                           # confidence.py:196
+        dist = np.linalg.norm(emb - centroid, axis=1)         # :199
+        assert float(out["variance"][q]) == pytest.approx(float(dist.std()), rel=1e-5)   # :200
+        assert float(out["uncertainty"][q]) == pytest.approx(min(1.0, float(dist.std()) / 2.0), rel=1e-5)
+        assert int(out["consensus"][q]) == int(np.argmin(dist))
+    np.testing.assert_allclose(out["std_w"].numpy(), gates.std(axis=0), rtol=1e-4, atol=1e-7)
+
+
+def test_router_single_element_is_nan_like_reference(gold):
+    state = _state(gold, "h64")
+    g = router_oracle.gate(torch.tensor([[1.0]]), torch.tensor([[0.5]]), state, False)
+    assert torch.isnan(g).all()      # torch.std of one element (router.py:135) -> NaN, SURVEY 8(a10)
+
+
+@pytest.mark.skipif(not REFERENCE.exists(), reason="live reference only exists in the build container")
+def test_router_oracle_matches_live_reference():
+    sys.path.insert(0, str(REFERENCE))
+    try:
+        from rag_uq.router import RetrievalRouter, RouterConfig
+    finally:
+        sys.path.remove(str(REFERENCE))
+    torch.manual_seed(3)
+    live = RetrievalRouter(RouterConfig(hidden_dim=64)).eval()
+    state = {k: v.detach().clone() for k, v in live.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    b, d = torch.rand(8, 50, generator=g) * 12, torch.rand(8, 50, generator=g) * 2 - 1
+    with torch.no_grad():
+        assert torch.equal(live(b, d), router_oracle.gate(b, d, state, False))
+        lv, li = live.hybrid_rerank(b, d, top_k=7)
+        ov, oi = router_oracle.hybrid_rerank(b, d, state, False, 7)
+        assert torch.equal(lv, ov) and torch.equal(li, oi)
+        live.train()
+        torch.manual_seed(99)
+        mask = torch.empty(b.numel(), 64).bernoulli_(0.9)
+        torch.manual_seed(99)
+        lw = live(b, d, update_stats=False)
+        torch.testing.assert_close(lw, router_oracle.gate(b, d, state, False, keep_mask=mask), rtol=1e-6, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------- philox
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    cases = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, want in cases:
+        got = philox.philox4x32_10(np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32))
+        assert tuple(int(x) for x in got) == want
+
+
+def test_philox_uniform_and_geometry():
+    u = philox.uniform_from_bits(np.array([0, 0xFFFFFFFF], dtype=np.uint32))
+    assert u[0] == np.float32(2.0 ** -33) and u[1] <= 1.0
+    grid, threads, inc = philox.torch_dropout_geometry(6400, 148)
+    assert (grid, threads, inc) == (25, 6400, 4)
+    grid, threads, inc = philox.torch_dropout_geometry(1024 * 100 * 64, 148)
+    assert grid == 1184 and inc == ((6553600 - 1) // (256 * 1184 * 4) + 1) * 4
+    keep = philox.keep_mask_torch_layout(6400, seed=123, offset=0, keep_prob=0.9, sm_count=148)
+    assert keep.shape == (6400,) and 0.85 < keep.mean() < 0.95
