@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Headline benchmark: hybrid top-10 queries/sec over a 10M x 768 synthetic passage corpus.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N=1 default)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+One step = one batch of 1024 queries through the whole hot path (BASELINE.json configs[2], the
+configuration the metric is quoted on; it fits one B200): BM25 pool-50 over the CSR index +
+exact dense pool-50 on the tcgen05 kernel + (N>1: one NCCL all-gather of the pools + merge) +
+pool fusion to the top-10 + router gate / rerank of those 10 (experiments/run_evaluation.py:165-184).
+The corpus is row-sharded over the N ranks (strong scaling: the 10M rows and the 1024 queries are
+fixed).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "hybrid top-10 queries/sec over 10Mx768 passages"
+UNIT = "queries/s"
+DIM = 768
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--passages", type=int, default=10_000_000)
+    p.add_argument("--batch", type=int, default=1024)
+    p.add_argument("--k", type=int, default=10)
+    p.add_argument("--pool", type=int, default=50)
+    p.add_argument("--variant", type=int, default=int(os.environ.get("RAGB_MMA_VARIANT", "0")))
+    p.add_argument("--cpu-sample-docs", type=int, default=20_000)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        d = json.loads(path.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the reference path restated (oracle port), bounded sample, extrapolated in N
+# ------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_setup(sample_docs: int, n_queries: int):
+    import numpy as np
+    import torch
+
+    from oracle import bm25_okapi
+    from rag_uq_b200 import synth  # generators are torch ops and run on the CPU as well
+
+    cdf = synth.zipf_cdf(synth.vocab_size(sample_docs), "cpu")
+    doc_off, doc_tok = synth.doc_tokens(0, sample_docs, cdf)
+    off, tok = doc_off.numpy(), doc_tok.numpy()
+    docs = [tok[off[i]:off[i + 1]].tolist() for i in range(sample_docs)]
+    _CPU["okapi"] = bm25_okapi.OkapiLiteral(docs)                # what BM25Index.add_documents builds (:142)
+    _CPU["emb"] = synth.passage_embeddings(0, sample_docs, DIM, "cpu").float().numpy()
+    qb = synth.make_queries(n_queries, sample_docs, DIM, cdf, "cpu")
+    _CPU["terms"] = qb.q_terms.view(n_queries, -1).numpy()
+    _CPU["qemb"] = qb.q_emb.float().numpy()
+    torch.manual_seed(7)
+    sys.path.insert(0, str(ROOT))
+    from oracle import router as router_oracle
+    lin1, lin2 = torch.nn.Linear(3, 64), torch.nn.Linear(64, 1)
+    _CPU["state"] = {"scorer.0.weight": lin1.weight.detach(), "scorer.0.bias": lin1.bias.detach(),
+                     "scorer.3.weight": lin2.weight.detach(), "scorer.3.bias": lin2.bias.detach()}
+    _CPU["router"] = router_oracle
+
+
+def _cpu_one_query(qi: int, k: int = 10, pool: int = 50):
+    """hybrid_search + router rerank for one query, exactly the reference's per-query call chain."""
+    import torch
+
+    from oracle import bm25_okapi, dense_fusion
+    bm = bm25_okapi.index_search(_CPU["okapi"].get_scores(_CPU["terms"][qi].tolist()), pool)     # :169-179
+    dense = dense_fusion.dense_scores(_CPU["emb"], _CPU["qemb"][qi:qi + 1])                       # exact stand-in for :355
+    de = dense_fusion.topk_desc(dense, pool)[0]
+    b, d, ids = dense_fusion.scores_for_router(bm, de, k)                                         # :537-557
+    with torch.no_grad():
+        _CPU["router"].hybrid_rerank(torch.tensor([b]), torch.tensor([d]), _CPU["state"], False, k)  # run_evaluation.py:171-180
+    return ids
+
+
+def cpu_baseline(args, n_queries: int, workers: int):
+    """Returns (queries/s on the sample, queries/s extrapolated to args.passages, description)."""
+    import multiprocessing as mp
+    _cpu_setup(args.cpu_sample_docs, max(n_queries, workers))
+    t0 = time.perf_counter()
+    if workers <= 1:
+        for qi in range(n_queries):
+            _cpu_one_query(qi, args.k, args.pool)
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            pool.map(_cpu_one_query, range(n_queries))
+    dt = time.perf_counter() - t0
+    sample_qps = n_queries / dt
+    # rank_bm25.get_scores is O(|q| * N) and exact dense scoring O(N * dim): linear in N
+    full_qps = sample_qps * args.cpu_sample_docs / args.passages
+    desc = (f"{n_queries} queries x {args.cpu_sample_docs} passages x {DIM}-d (same generators), {workers} process(es); "
+            f"measured {sample_qps:.3f} q/s on the sample, scaled linearly in N to {args.passages} passages")
+    return sample_qps, full_qps, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    n_q = workers * 2
+    values = []
+    for step in range(args.warmup + args.steps):
+        if step == 0:
+            _, full, desc = cpu_baseline(args, n_q, workers)
+        else:
+            import multiprocessing as mp
+            t0 = time.perf_counter()
+            with mp.get_context("fork").Pool(workers) as pool:
+                pool.map(_cpu_one_query, range(n_q))
+            full = n_q / (time.perf_counter() - t0) * args.cpu_sample_docs / args.passages
+        if step >= args.warmup:
+            values.append(full)
+    value = sum(values) / len(values)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"hybrid top-{args.k} (BM25 pool {args.pool} + exact dense pool {args.pool} + fusion + router), "
+                               f"{args.passages} passages x {DIM}, batch {args.batch}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.file.read().splitlines():
+            cells = [c.strip() for c in row.split(",")]
+            if len(cells) < 9:
+                continue
+            try:
+                sm.append(float(cells[1]))
+                out["sm_max_mhz"] = float(cells[2])
+            except ValueError:
+                continue
+            for name, cell in zip(names, cells[5:9]):
+                if cell.lower() == "active":
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["reasons"] = sorted(reasons)
+        os.unlink(self.file.name)
+        return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import rag_uq_b200 as rq
+    from rag_uq_b200 import ops, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    t_build = time.perf_counter()
+    engine, cdf = synth.build_synthetic_engine(args.passages, DIM, dev, rank, world, group, mma_variant=args.variant)
+    torch.manual_seed(7)
+    router = rq.RetrievalRouter().to(dev).eval()
+    router.bm25_mean.fill_(8.0); router.bm25_std.fill_(6.0); router.dense_mean.fill_(0.2); router.dense_std.fill_(0.3)
+    router.stats_initialized = True
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t_build
+
+    n_sets = 4
+    batches = [synth.make_queries(args.batch, args.passages, DIM, cdf, dev, first_query=i * args.batch) for i in range(n_sets)]
+    host = [(b.q_terms.cpu().pin_memory(), b.q_off.cpu().pin_memory(), b.q_emb.cpu().pin_memory()) for b in batches]
+    max_terms = batches[0].max_terms
+    n_local = engine.passages.shape[0]
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    dense_ms, bm25_ms = [], []
+
+    def step(q_terms, q_off, q_emb, probes=None):
+        with torch.no_grad():
+            if probes is not None:
+                e0, e1, e2 = ev(), ev(), ev()
+                e0.record()
+            bs, bi = engine.sparse.score_topk(q_terms, q_off, max_terms, args.pool)
+            if probes is not None:
+                e1.record()
+            ds, di = engine.dense_local_topk(q_emb, args.pool)
+            if probes is not None:
+                e2.record()
+                probes.append((e0, e1, e2))
+            if world > 1:
+                s = torch.stack([bs, ds], dim=1).reshape(bs.shape[0], 2 * args.pool)
+                i = torch.stack([bi, di], dim=1).reshape(bs.shape[0], 2 * args.pool)
+                gs, gi = rq.gather_candidates(s, i, group)
+                gs = gs.view(bs.shape[0], world, 2, args.pool)
+                gi = gi.view(bs.shape[0], world, 2, args.pool)
+                bs, bi = ops.topk_merge(gs[:, :, 0].contiguous(), gi[:, :, 0].contiguous(), args.pool)
+                ds, di = ops.topk_merge(gs[:, :, 1].contiguous(), gi[:, :, 1].contiguous(), args.pool)
+            ids, sb, sd, sh = ops.hybrid_fuse_topk(bs, bi, ds, di, args.k)
+            vals, order = router.hybrid_rerank(sb, sd, top_k=args.k)
+            return torch.gather(ids, 1, order.to(torch.int64)), vals
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, from_host):
+        probes = []
+        barrier()
+        launches0 = ops.launch_count()
+        start, stop = ev(), ev()
+        start.record()
+        out = None
+        for s in range(n_steps):
+            if from_host:
+                ht, ho, he = host[s % n_sets]
+                qt, qo, qe = ht.to(dev, non_blocking=True), ho.to(dev, non_blocking=True), he.to(dev, non_blocking=True)
+                ids, vals = step(qt, qo, qe)
+                out = (ids.cpu(), vals.cpu())          # device -> host read of the step's result
+            else:
+                b = batches[s % n_sets]
+                out = step(b.q_terms, b.q_off, b.q_emb, probes)
+        stop.record()
+        barrier()
+        ms = start.elapsed_time(stop)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), ops.launch_count() - launches0, probes, out
+
+    timed(args.warmup, False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, probes, _ = timed(args.steps, False)
+    clocks = sampler.stop() if sampler else None
+    for e0, e1, e2 in probes:
+        bm25_ms.append(e0.elapsed_time(e1))
+        dense_ms.append(e1.elapsed_time(e2))
+    timed(max(1, args.warmup // 2), True)
+    e2e_ms, _, _, last = timed(args.steps, True)
+
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = sum(t.numel() * t.element_size() for t in last)
+    value = args.batch * args.steps / (ms / 1000.0)
+    e2e = args.batch * args.steps / (e2e_ms / 1000.0)
+
+    if rank == 0:
+        pk = peaks()
+        dense_avg = sum(dense_ms) / len(dense_ms)
+        bm25_avg = sum(bm25_ms) / len(bm25_ms)
+        flops = 2.0 * args.batch * n_local * DIM
+        achieved = flops / (dense_avg / 1000.0) / 1e12
+        # realised BM25 postings of one batch: sum of document frequencies of the query terms (local shard)
+        qt = batches[0].q_terms.to(torch.int64)
+        ok = (qt >= 0) & (qt < engine.sparse.vocab)
+        toff = engine.sparse.term_off
+        sum_df = int((toff[qt[ok] + 1] - toff[qt[ok]]).sum())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"hybrid top-{args.k}: BM25 pool {args.pool} over CSR + exact dense pool {args.pool} "
+                                   f"(tcgen05 variant {args.variant}) + fusion + router rerank; {args.passages} passages x {DIM} "
+                                   f"bf16 row-sharded over {world} GPU(s), batch {args.batch} queries x 8 terms",
+                       "l2": "inputs exceed L2 (embedding shard %.1f GB, postings %.1f GB per GPU); 4 rotating query batches"
+                             % (n_local * DIM * 2 / 1e9, engine.sparse.nnz * 6 / 1e9),
+                       "build_seconds": round(build_s, 1)},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "dense_mma_kernel (+ stripe merge)", "achieved": achieved,
+                         "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
+                         "traffic": None, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
+                         "ms_per_launch": dense_avg, "flops_per_launch": flops},
+            "kernels": {"bm25_ms": bm25_avg, "bm25_postings_per_batch": sum_df,
+                        "bm25_posting_gbs": sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9,
+                        "bm25_frac_of_hbm_peak": sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9 / pk["hbm_gbs"],
+                        "dense_ms": dense_avg, "other_ms": ms / args.steps - dense_avg - bm25_avg},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            _, full, desc = cpu_baseline(args, 6, 1)
+            line["cpu_baseline"] = {"value": full, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

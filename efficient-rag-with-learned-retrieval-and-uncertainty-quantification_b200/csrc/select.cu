@@ -54,6 +54,25 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_rows_kernel(const float* __r
   }
 }
 
+// Full descending sort of short rows (n_cols <= 8192): serves top-k requests with k beyond
+// RAGB_MAX_TOPK, e.g. hybrid_rerank(top_k >= P) which the reference clamps to P (router.py:202).
+__global__ void __launch_bounds__(SEL_THREADS) sort_rows_kernel(const float* __restrict__ scores, int n_cols, int k,
+                                                                int sort_n, float* __restrict__ out_score,
+                                                                int32_t* __restrict__ out_index) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  const int row = blockIdx.x;
+  const float* src = scores + static_cast<int64_t>(row) * n_cols;
+  for (int i = threadIdx.x; i < sort_n; i += SEL_THREADS) keys[i] = i < n_cols ? make_key(src[i], i) : 0ull;
+  __syncthreads();
+  bitonic_sort_desc<SEL_THREADS>(keys, sort_n);
+  for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
+    uint64_t key = i < sort_n ? keys[i] : 0ull;
+    out_score[static_cast<int64_t>(row) * k + i] = key ? key_score(key) : 0.0f;
+    out_index[static_cast<int64_t>(row) * k + i] = key ? key_id(key) : -1;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Merge candidate lists.  Input either packed keys [n_queries, n_lists, k_in] or separate
 // (score, id) arrays with id -1 = empty.  One block per query.
@@ -246,7 +265,7 @@ using namespace ragb;
 extern "C" {
 
 size_t ragb_topk_rows_workspace_bytes(int32_t n_rows, int64_t n_cols, int32_t k) {
-  if (n_rows <= 0 || n_cols <= 0 || k <= 0) return 0;
+  if (n_rows <= 0 || n_cols <= 0 || k <= 0 || k > RAGB_MAX_TOPK) return 0;
   return static_cast<size_t>(n_rows) * rows_split(n_rows, n_cols) * k * sizeof(uint64_t);
 }
 
@@ -256,7 +275,19 @@ int ragb_topk_rows(const float* scores, int32_t n_rows, int64_t n_cols, int32_t 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RAGB_REQUIRE(scores && out_score && out_index, RAGB_EINVAL, "ragb_topk_rows: null pointer");
   RAGB_REQUIRE(n_rows > 0 && n_cols > 0 && n_cols < (1ll << 31), RAGB_EINVAL, "ragb_topk_rows: bad shape");
-  RAGB_REQUIRE(k > 0 && k <= RAGB_MAX_TOPK, RAGB_ELIMIT, "ragb_topk_rows: k=%d outside [1,%d]", k, RAGB_MAX_TOPK);
+  RAGB_REQUIRE(k > 0, RAGB_EINVAL, "ragb_topk_rows: k must be positive");
+  if (k > RAGB_MAX_TOPK) {
+    RAGB_REQUIRE(n_cols <= 8192, RAGB_ELIMIT, "ragb_topk_rows: k=%d > %d is only served for rows of at most 8192 columns",
+                 k, RAGB_MAX_TOPK);
+    int sort_n = 2;
+    while (sort_n < n_cols) sort_n <<= 1;
+    const size_t smem = sort_n * sizeof(uint64_t);
+    RAGB_CUDA(cudaFuncSetAttribute(sort_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    sort_rows_kernel<<<n_rows, SEL_THREADS, smem, stream>>>(scores, static_cast<int>(n_cols), k, sort_n, out_score,
+                                                            out_index);
+    RAGB_AFTER_LAUNCH(1);
+    return RAGB_OK;
+  }
   const int split = rows_split(n_rows, n_cols);
   const int capacity = topk_capacity(k);
   const int64_t span = ceil_div64(n_cols, split);

