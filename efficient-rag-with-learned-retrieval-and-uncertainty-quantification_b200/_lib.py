@@ -15,7 +15,7 @@ RAGB_OK, RAGB_EINVAL, RAGB_EARCH, RAGB_ECUDA, RAGB_ELIMIT, RAGB_ENOSPC = 0, -1, 
 MAX_TOPK = 256
 MAX_QUERY_TERMS = 64
 GEMV_MAX_BATCH = 8
-MMA_MAX_TOPK = 128
+MMA_MAX_TOPK = 100
 FUSE_MAX_POOL = 256
 ROUTER_MAX_HIDDEN = 128
 

@@ -14,8 +14,8 @@
 // it in ranges of 256 documents.  Per range the warp keeps a 256-float accumulator in
 // shared memory and streams, term after term, the postings that fall in the range:
 // posting lists are sorted by document, so every warp simply continues reading where it
-// stopped (one cursor per term), 128-byte coalesced, up to 4 independent 32-posting chunks
-// in flight for dense lists.  Within one 32-posting chunk all documents are distinct, so
+// stopped (one cursor per term), 128-byte coalesced, 1 to 8 independent 32-posting chunks in
+// flight per pass depending on the list's density.  Within one 32-posting chunk all documents are distinct, so
 // the accumulation is a plain shared-memory read-modify-write: no atomics anywhere.
 // Terms whose next posting lies beyond the range are skipped without touching memory.
 // The block-wide running top-k (topk.cuh) then filters the 8x256 scores: one barrier per
@@ -30,7 +30,6 @@ namespace ragb {
 constexpr int BM_THREADS = 256;
 constexpr int BM_WARPS = BM_THREADS / 32;
 constexpr int BM_RANGE = 256;          // documents per warp range
-constexpr int BM_DENSE_POSTINGS = 48;  // expected postings per range above which 4 chunks are kept in flight
 constexpr int BM_MAX_TERMS = 64;
 constexpr int BM_SEARCH = 4;  // posting lists searched concurrently while placing the cursors
 
@@ -55,6 +54,9 @@ struct Bm25Args {
 };
 
 // Stream the postings of one term that fall below d1 into the warp's accumulator.
+// U chunks of 32 postings are loaded per pass (all loads independent) plus one "peek" posting
+// right behind them, so a pass that consumes everything it loaded still learns the next
+// document without another round trip to memory.
 template <int U>
 __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc,
                                             const uint16_t* __restrict__ post_tf, int64_t& pos, const int64_t end,
@@ -70,6 +72,9 @@ __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc
       doc[u] = in ? __ldg(post_doc + idx) : INT_MAX;
       tf[u] = in ? static_cast<unsigned>(__ldg(post_tf + idx)) : 0u;
     }
+    const int64_t peek_idx = pos + U * 32;
+    int peek = INT_MAX;
+    if (lane == 0 && peek_idx < end) peek = __ldg(post_doc + peek_idx);
     int taken = 0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -89,6 +94,11 @@ __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc
       for (int u = 0; u < U; ++u)
         if (u == (taken >> 5)) cand = doc[u];
       next_doc = __shfl_sync(0xffffffffu, cand, taken & 31);
+      return;
+    }
+    peek = __shfl_sync(0xffffffffu, peek, 0);
+    if (peek >= d1) {
+      next_doc = peek;
       return;
     }
     __syncwarp();
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
           s_nxt[ntv] = nd;
           // expected postings of this term per 256-document range
           const double per_range = static_cast<double>(te[j] - ts[j]) * BM_RANGE / static_cast<double>(a.n_docs);
-          s_dense[ntv] = per_range >= BM_DENSE_POSTINGS ? 1 : 0;
+          s_dense[ntv] = per_range < 24.0 ? 0 : (per_range < 56.0 ? 1 : (per_range < 120.0 ? 2 : 3));
         }
         ++ntv;
       }
@@ -233,10 +243,12 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         const int64_t end = s_end[ti];
         const float w = s_wgt[ti];
         int next_doc;
-        if (s_dense[ti])
-          stream_term<4>(a.post_doc, a.post_tf, pos, end, d0, d1, w, accw, nrmw, lane, next_doc);
-        else
-          stream_term<1>(a.post_doc, a.post_tf, pos, end, d0, d1, w, accw, nrmw, lane, next_doc);
+        switch (s_dense[ti]) {  // chunks per pass sized to the term's density (warp-uniform)
+          case 0: stream_term<1>(a.post_doc, a.post_tf, pos, end, d0, d1, w, accw, nrmw, lane, next_doc); break;
+          case 1: stream_term<2>(a.post_doc, a.post_tf, pos, end, d0, d1, w, accw, nrmw, lane, next_doc); break;
+          case 2: stream_term<4>(a.post_doc, a.post_tf, pos, end, d0, d1, w, accw, nrmw, lane, next_doc); break;
+          default: stream_term<8>(a.post_doc, a.post_tf, pos, end, d0, d1, w, accw, nrmw, lane, next_doc); break;
+        }
         if (lane == 0) {
           s_pos[ti] = pos;
           s_nxt[ti] = next_doc;

@@ -12,7 +12,8 @@
 //   warps 2..5  epilogue: tcgen05.ld of the accumulator; THREAD r OWNS QUERY r of the
 //               slab for the whole kernel, so its admission threshold is a register and
 //               the common case is "32 scores, one max, one compare".  Survivors are
-//               inserted into the thread's private sorted list in shared memory.
+//               appended to the thread's private list in shared memory; a full list is
+//               compacted to its best k by the whole warp (shuffle bitonic sort).
 //   The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the
 //   MMAs of tile i+1.
 //
@@ -151,24 +152,80 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-__device__ __forceinline__ void list_insert(uint64_t* list, int k, int& n, uint64_t key, uint64_t& thr_key,
-                                            float& thr_score) {
-  int j = n < k ? n : k - 1;
-  while (j > 0) {
-    const uint64_t prev = list[(j - 1) * MM_BM];
-    if (prev >= key) break;
-    list[j * MM_BM] = prev;
-    --j;
-  }
-  list[j * MM_BM] = key;
-  if (n < k) ++n;
-  if (n == k) {
-    thr_key = list[(k - 1) * MM_BM];
-    thr_score = key_score(thr_key);
+// Descending bitonic sort of 32*KPL keys held striped over a warp (element e = r*32 + lane).
+template <int KPL>
+__device__ __forceinline__ void warp_sort_desc(uint64_t (&v)[KPL], const int lane) {
+  constexpr int N = 32 * KPL;
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int j = size >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int jr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+          const int r2 = r ^ jr;
+          if (r2 > r) {
+            const bool desc = (((r * 32 + lane) & size) == 0);
+            const uint64_t x = v[r], y = v[r2];
+            const bool sw = (x < y) == desc;
+            v[r] = sw ? y : x;
+            v[r2] = sw ? x : y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < KPL; ++r) {
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, v[r], j);
+          const bool desc = (((r * 32 + lane) & size) == 0);
+          const bool take_max = (((lane & j) == 0) == desc);
+          const uint64_t mx = v[r] > other ? v[r] : other;
+          const uint64_t mn = v[r] > other ? other : v[r];
+          v[r] = take_max ? mx : mn;
+        }
+      }
+    }
   }
 }
 
-template <int BN, bool A_IN_TMEM>
+// Per-thread candidate list: LIST_CAP = 32*KPL slots, the best k sorted in front after a
+// compaction, appended survivors behind them.  When a lane's list is full the WHOLE WARP sorts
+// it (KPL keys per lane, shuffles only), keeps the best k and tightens that lane's threshold:
+// an append is one shared-memory store, a compaction ~20 shuffle stages once per (cap - k) appends.
+template <int KPL>
+__device__ __forceinline__ void compact_lists(uint64_t* warp_lists, unsigned lanes, const int lane, const int k,
+                                              int& cnt, uint64_t& thr_key, float& thr_score) {
+  constexpr int CAP = 32 * KPL;
+  constexpr int STRIDE = CAP + 1;
+  __syncwarp();
+  while (lanes) {
+    const int src = __ffs(lanes) - 1;
+    lanes &= lanes - 1;
+    const int n_src = __shfl_sync(0xffffffffu, cnt, src);
+    uint64_t* list = warp_lists + src * STRIDE;
+    uint64_t v[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) v[r] = (r * 32 + lane) < n_src ? list[r * 32 + lane] : 0ull;
+    warp_sort_desc<KPL>(v, lane);
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) list[r * 32 + lane] = v[r];
+    uint64_t kth = 0ull;
+#pragma unroll
+    for (int r = 0; r < KPL; ++r)
+      if (r == ((k - 1) >> 5)) kth = v[r];
+    kth = __shfl_sync(0xffffffffu, kth, (k - 1) & 31);
+    if (lane == src) {
+      cnt = n_src < k ? n_src : k;
+      if (n_src >= k) {
+        thr_key = kth;
+        thr_score = key_score(kth);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int BN, bool A_IN_TMEM, int KPL>
 __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                   const __grid_constant__ CUtensorMap tmap_e,
                                                                   const MmaArgs a) {
@@ -293,7 +350,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
     const int tslot = quad * 32 + lane;  // TMEM lane == query row inside the slab
     const int query = slab * MM_BM + tslot;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    uint64_t* my_list = lists + tslot;
+    constexpr int LIST_CAP = 32 * KPL;
+    constexpr int LIST_STRIDE = LIST_CAP + 1;
+    uint64_t* warp_lists = lists + static_cast<size_t>(quad) * 32 * LIST_STRIDE;
+    uint64_t* my_list = warp_lists + lane * LIST_STRIDE;
 
     if (A_IN_TMEM) {
       // store the thread's query row (packed bf16 pairs, K ascending) into its TMEM lane
@@ -316,7 +376,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
       mbar_arrive(smem_u32(&bar_a_ready));
     }
 
-    int n = 0;
+    int cnt = 0;
     uint64_t thr_key = 0ull;
     float thr_score = -INFINITY;
     uint32_t buf = 0, acc_phase = 0;
@@ -327,20 +387,23 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
+        __syncwarp();
         tc_ld32(tmem_base + lane_addr + acc_col0 + buf * BN + c * 32, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float m = __uint_as_float(v[0]);
 #pragma unroll
         for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-        if (m >= thr_score) {
+        if (__any_sync(0xffffffffu, m >= thr_score)) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int64_t row = row0 + c * 32 + i;
             const float s = __uint_as_float(v[i]);
             if (s >= thr_score && row < a.n_rows) {
               const uint64_t key = make_key(s, static_cast<int32_t>(a.id_base + row));
-              if (key > thr_key) list_insert(my_list, a.k, n, key, thr_key, thr_score);
+              if (key > thr_key) my_list[cnt++] = key;
             }
+            const unsigned full = __ballot_sync(0xffffffffu, cnt == LIST_CAP);
+            if (full) compact_lists<KPL>(warp_lists, full, lane, a.k, cnt, thr_key, thr_score);
           }
         }
       }
@@ -350,9 +413,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
       buf ^= 1;
       if (buf == 0) acc_phase ^= 1;
     }
+    compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, cnt, thr_key, thr_score);
     if (query < a.n_queries) {
       uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.n_groups + group) * a.k;
-      for (int j = 0; j < a.k; ++j) dst[j] = j < n ? my_list[j * MM_BM] : 0ull;
+      for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? my_list[j] : 0ull;
     }
   }
 
@@ -394,7 +458,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int dim, in
   return RAGB_OK;
 }
 
-template <int BN, bool A_IN_TMEM>
+template <int BN, bool A_IN_TMEM, int KPL>
 static int launch_mma(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
                       int64_t id_base, uint64_t* part, int* n_groups_out, cudaStream_t stream) {
   constexpr int STAGE_BYTES = (A_IN_TMEM ? 0 : MM_A_STAGE_BYTES) + BN * MM_BK * 2;
@@ -421,15 +485,15 @@ static int launch_mma(const void* passages, int64_t n_rows, int dim, const void*
   a.tiles_per_group = (a.n_tiles + a.n_groups - 1) / a.n_groups;
   a.n_groups = (a.n_tiles + a.tiles_per_group - 1) / a.tiles_per_group;
   a.part_keys = part;
-  const size_t list_bytes = static_cast<size_t>(k) * MM_BM * sizeof(uint64_t);
+  const size_t list_bytes = static_cast<size_t>(32 * KPL + 1) * MM_BM * sizeof(uint64_t);
   int stages = static_cast<int>((MM_MAX_SMEM - 1024 - 256 - list_bytes) / STAGE_BYTES);
   if (stages > MM_MAX_STAGES) stages = MM_MAX_STAGES;
   RAGB_REQUIRE(stages >= 2, RAGB_ELIMIT, "ragb_dense_mma_topk: k=%d leaves no room for a 2-stage pipeline", k);
   a.n_stages = stages;
   const size_t smem = 1024 + static_cast<size_t>(stages) * STAGE_BYTES + list_bytes;
-  RAGB_CUDA(cudaFuncSetAttribute(dense_mma_kernel<BN, A_IN_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  RAGB_CUDA(cudaFuncSetAttribute(dense_mma_kernel<BN, A_IN_TMEM, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-  dense_mma_kernel<BN, A_IN_TMEM><<<a.n_slabs * a.n_groups, MM_THREADS, smem, stream>>>(map_q, map_e, a);
+  dense_mma_kernel<BN, A_IN_TMEM, KPL><<<a.n_slabs * a.n_groups, MM_THREADS, smem, stream>>>(map_q, map_e, a);
   RAGB_AFTER_LAUNCH(1);
   *n_groups_out = a.n_groups;
   return RAGB_OK;
@@ -458,7 +522,7 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
   RAGB_REQUIRE(n_rows > 0 && n_queries > 0, RAGB_EINVAL, "ragb_dense_mma_topk: empty shape");
   RAGB_REQUIRE(dim >= MM_BK && dim % MM_BK == 0, RAGB_EINVAL, "ragb_dense_mma_topk: dim=%d must be a multiple of %d", dim,
                MM_BK);
-  RAGB_REQUIRE(k > 0 && k <= 128, RAGB_ELIMIT, "ragb_dense_mma_topk: k=%d outside [1,128]", k);
+  RAGB_REQUIRE(k > 0 && k <= 100, RAGB_ELIMIT, "ragb_dense_mma_topk: k=%d outside [1,100]", k);
   RAGB_REQUIRE(variant == 0 || variant == 1, RAGB_EINVAL, "ragb_dense_mma_topk: variant must be 0 or 1");
   RAGB_REQUIRE(variant == 0 || dim <= 768, RAGB_ELIMIT, "ragb_dense_mma_topk: variant 1 keeps the query slab in TMEM and needs dim <= 768");
   RAGB_REQUIRE(id_base >= 0 && id_base + n_rows < (1ll << 31), RAGB_ELIMIT, "ragb_dense_mma_topk: ids must fit int32");
@@ -467,10 +531,18 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
   uint64_t* part = static_cast<uint64_t*>(workspace);
   int n_groups = 0;
   int rc;
-  if (variant == 0)
-    rc = launch_mma<128, false>(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, &n_groups, stream);
-  else
-    rc = launch_mma<64, true>(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, &n_groups, stream);
+  // list capacity per query thread: 32 (k <= 16), 64 (k <= 50) or 128 (k <= 100) slots
+#define RAGB_MMA_ARGS passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, &n_groups, stream
+  if (variant == 0) {
+    if (k <= 16) rc = launch_mma<128, false, 1>(RAGB_MMA_ARGS);
+    else if (k <= 50) rc = launch_mma<128, false, 2>(RAGB_MMA_ARGS);
+    else rc = launch_mma<128, false, 4>(RAGB_MMA_ARGS);
+  } else {
+    if (k <= 16) rc = launch_mma<64, true, 1>(RAGB_MMA_ARGS);
+    else if (k <= 50) rc = launch_mma<64, true, 2>(RAGB_MMA_ARGS);
+    else rc = launch_mma<64, true, 4>(RAGB_MMA_ARGS);
+  }
+#undef RAGB_MMA_ARGS
   if (rc != RAGB_OK) return rc;
   return launch_merge_keys(part, n_queries, n_groups, k, k, out_score, out_id, stream);
 }

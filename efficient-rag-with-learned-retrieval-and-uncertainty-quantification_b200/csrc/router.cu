@@ -4,9 +4,8 @@
 // (rag_uq/router.py:100-202) and T stochastic passes of the nn.Dropout at router.py:78,
 // aggregated with the arithmetic of MCDropoutConfidence (rag_uq/confidence.py:195-202,
 // 258-264).  The gate is Linear(3,H) -> ReLU -> Dropout -> Linear(H,1) -> Sigmoid on the
-// features [bn, dn, dn - bn]; the third feature is folded into the first-layer weights
-// on the fly is NOT done here: the arithmetic keeps the reference's three products so fp32
-// results stay within 1e-5 of torch.
+// features [bn, dn, dn - bn]; the arithmetic keeps the reference's three products per hidden
+// unit (no weight folding) so fp32 results stay within 1e-5 of torch.
 #include <cmath>
 
 #include "common.cuh"
@@ -65,8 +64,7 @@ __global__ void stats_final_kernel(const double* __restrict__ partial, int n_par
   const double nn = static_cast<double>(n);
   for (int c = 0; c < 2; ++c) {
     const double mean = t[2 * c] / nn;
-    double var = (t[2 * c + 1] - nn * mean * mean) / (nn - 1.0);  // n == 1 -> NaN like torch
-    if (var < 0.0 && var > -1e-300) var = 0.0;
+    double var = (t[2 * c + 1] - nn * mean * mean) / (nn - 1.0);  // n == 1 -> 0/0 = NaN like torch
     if (n > 1 && var < 0.0) var = 0.0;
     stats_out[2 * c] = static_cast<float>(mean);
     stats_out[2 * c + 1] = static_cast<float>(sqrt(var));
@@ -138,7 +136,7 @@ __global__ void __launch_bounds__(RT_THREADS) router_forward_kernel(const float*
     float z = b2;
     for (int j = 0; j < H; ++j) {
       float h = fmaf(s_w1[3 * j + 2], df, fmaf(s_w1[3 * j + 1], dn, fmaf(s_w1[3 * j], bn, s_b1[j])));
-      h = fmaxf(h, 0.0f);
+      h = h < 0.0f ? 0.0f : h;  // ReLU that lets NaN through like torch.relu
       z = fmaf(s_w2[j], h, z);
     }
     const float g = sigmoidf_exact(z);
@@ -229,7 +227,7 @@ __global__ void __launch_bounds__(RT_THREADS) router_mc_kernel(const McArgs a) {
         const int j = u + i;
         const bool keep = uniform_from_bits(rb[i]) < a.keep_prob;
         float h = fmaf(s_w1[3 * j + 2], df, fmaf(s_w1[3 * j + 1], dn, fmaf(s_w1[3 * j], bn, s_b1[j])));
-        h = fmaxf(h, 0.0f);
+        h = h < 0.0f ? 0.0f : h;
         h = keep ? h * a.scale : 0.0f;
         z = fmaf(s_w2[j], h, z);
         if (a.mask_dump) a.mask_dump[(static_cast<int64_t>(t) * a.n_queries * P + cand) * H + j] = keep ? 1 : 0;
