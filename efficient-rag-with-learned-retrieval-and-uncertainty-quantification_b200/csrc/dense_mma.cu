@@ -192,16 +192,24 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t (&v)[KPL], const int lan
 // compaction, appended survivors behind them.  When a lane's list is full the WHOLE WARP sorts
 // it (KPL keys per lane, shuffles only), keeps the best k and tightens that lane's threshold:
 // an append is one shared-memory store, a compaction ~20 shuffle stages once per (cap - k) appends.
+struct ListState {
+  int cnt;
+  float thr_score;
+  uint64_t thr_key;
+};
+
+// Deliberately NOT inlined: it is called from inside the 32-way unrolled admission loop and
+// inlining it there blows the instruction cache (measured: stall_no_inst dominated the kernel).
 template <int KPL>
-__device__ __forceinline__ void compact_lists(uint64_t* warp_lists, unsigned lanes, const int lane, const int k,
-                                              int& cnt, uint64_t& thr_key, float& thr_score) {
+__device__ __noinline__ ListState compact_lists(uint64_t* warp_lists, unsigned lanes, const int lane, const int k,
+                                                ListState st) {
   constexpr int CAP = 32 * KPL;
   constexpr int STRIDE = CAP + 1;
   __syncwarp();
   while (lanes) {
     const int src = __ffs(lanes) - 1;
     lanes &= lanes - 1;
-    const int n_src = __shfl_sync(0xffffffffu, cnt, src);
+    const int n_src = __shfl_sync(0xffffffffu, st.cnt, src);
     uint64_t* list = warp_lists + src * STRIDE;
     uint64_t v[KPL];
 #pragma unroll
@@ -215,14 +223,15 @@ __device__ __forceinline__ void compact_lists(uint64_t* warp_lists, unsigned lan
       if (r == ((k - 1) >> 5)) kth = v[r];
     kth = __shfl_sync(0xffffffffu, kth, (k - 1) & 31);
     if (lane == src) {
-      cnt = n_src < k ? n_src : k;
+      st.cnt = n_src < k ? n_src : k;
       if (n_src >= k) {
-        thr_key = kth;
-        thr_score = key_score(kth);
+        st.thr_key = kth;
+        st.thr_score = key_score(kth);
       }
     }
   }
   __syncwarp();
+  return st;
 }
 
 template <int BN, bool A_IN_TMEM, int KPL>
@@ -376,14 +385,13 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
       mbar_arrive(smem_u32(&bar_a_ready));
     }
 
-    int cnt = 0;
-    uint64_t thr_key = 0ull;
-    float thr_score = -INFINITY;
+    ListState st{0, -INFINITY, 0ull};
     uint32_t buf = 0, acc_phase = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_phase);
       tc_fence_after();
       const int64_t row0 = static_cast<int64_t>(tile) * BN;
+      const int valid = static_cast<int>(min(static_cast<int64_t>(BN), a.n_rows - row0));  // rows of this tile that exist
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
@@ -393,17 +401,18 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
         float m = __uint_as_float(v[0]);
 #pragma unroll
         for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-        if (__any_sync(0xffffffffu, m >= thr_score)) {
+        if (__any_sync(0xffffffffu, m >= st.thr_score)) {
+          const int32_t id0 = static_cast<int32_t>(a.id_base + row0) + c * 32;
+          const int lim = valid - c * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int64_t row = row0 + c * 32 + i;
             const float s = __uint_as_float(v[i]);
-            if (s >= thr_score && row < a.n_rows) {
-              const uint64_t key = make_key(s, static_cast<int32_t>(a.id_base + row));
-              if (key > thr_key) my_list[cnt++] = key;
+            if (s >= st.thr_score && i < lim) {
+              const uint64_t key = make_key(s, id0 + i);
+              if (key > st.thr_key) my_list[st.cnt++] = key;
             }
-            const unsigned full = __ballot_sync(0xffffffffu, cnt == LIST_CAP);
-            if (full) compact_lists<KPL>(warp_lists, full, lane, a.k, cnt, thr_key, thr_score);
+            const unsigned full = __ballot_sync(0xffffffffu, st.cnt == LIST_CAP);
+            if (full) st = compact_lists<KPL>(warp_lists, full, lane, a.k, st);
           }
         }
       }
@@ -413,7 +422,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
       buf ^= 1;
       if (buf == 0) acc_phase ^= 1;
     }
-    compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, cnt, thr_key, thr_score);
+    st = compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, st);
+    const int cnt = st.cnt;
     if (query < a.n_queries) {
       uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.n_groups + group) * a.k;
       for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? my_list[j] : 0ull;

@@ -48,11 +48,12 @@ def gather_candidates(score: Tensor, ids: Tensor, group=None) -> Tuple[Tensor, T
     if world == 1:
         return score.unsqueeze(1), ids.unsqueeze(1)
     b, k = score.shape
-    all_s = torch.empty((world, b, k), dtype=score.dtype, device=score.device)
-    all_i = torch.empty((world, b, k), dtype=ids.dtype, device=ids.device)
+    all_s = torch.empty((world * b, k), dtype=score.dtype, device=score.device)   # rank-major concatenation
+    all_i = torch.empty((world * b, k), dtype=ids.dtype, device=ids.device)
     dist.all_gather_into_tensor(all_s, score.contiguous(), group=group)
     dist.all_gather_into_tensor(all_i, ids.contiguous(), group=group)
-    return all_s.permute(1, 0, 2).contiguous(), all_i.permute(1, 0, 2).contiguous()
+    return (all_s.view(world, b, k).permute(1, 0, 2).contiguous(),
+            all_i.view(world, b, k).permute(1, 0, 2).contiguous())
 
 
 class HybridEngine:

@@ -1,0 +1,214 @@
+"""Host-side checks that need no GPU: the C ABI exports what include/ragb200.h declares, the
+ops refuse to run anywhere but on CUDA, generators are deterministic, host logic of the
+drop-in classes behaves like the reference's."""
+import ctypes
+import json
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def rq(lib_built):
+    import rag_uq_b200
+    return rag_uq_b200
+
+
+def declared_functions():
+    text = (ROOT / "include" / "ragb200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ragb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(rq):
+    names = declared_functions()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(str(rq._lib.LIB_PATH))
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/ragb200.h but not exported"
+    assert set(names) == set(rq._lib.SIGNATURES), "ctypes signature table and header disagree"
+    assert lib.ragb_abi_version() == 1
+
+
+def test_library_is_sm100a_with_blackwell_instructions(rq):
+    """The shipped code object holds tcgen05 / TMA SASS and nothing for other architectures."""
+    out = subprocess.run(["cuobjdump", "-lelf", str(rq._lib.LIB_PATH)], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", str(rq._lib.LIB_PATH)], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_no_cpu_fallback(rq):
+    with pytest.raises(NotImplementedError):
+        rq.ops.topk_rows(torch.zeros(2, 8), 2)
+    with pytest.raises(NotImplementedError):
+        rq.ops.dense_gemv_topk(torch.zeros(8, 64, dtype=torch.bfloat16), torch.zeros(1, 64, dtype=torch.bfloat16), 1, 0)
+    router = rq.RetrievalRouter()
+    with pytest.raises(NotImplementedError):
+        router(torch.randn(2, 5), torch.randn(2, 5))
+    with pytest.raises(NotImplementedError):
+        rq.HybridEngine(None, torch.zeros(4, 64, dtype=torch.bfloat16))
+    if not torch.cuda.is_available():
+        # the C ABI itself refuses when there is no sm_100 device
+        rc = rq._lib.lib.ragb_topk_merge(None, None, 1, 1, 1, 1, None, None, None)
+        assert rc in (rq._lib.RAGB_ECUDA, rq._lib.RAGB_EARCH)
+        assert rq._lib.last_error()
+        index = rq.BM25Index()
+        index.add_documents([rq.Document(id="a", text="x y z")])
+        with pytest.raises(RuntimeError):
+            index.search("x")
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = ROOT / "efficient-rag-with-learned-retrieval-and-uncertainty-quantification_b200"
+    for path in list(pkg.glob("*.py")) + list(pkg.glob("csrc/*")) + [ROOT / "rag_uq_b200" / "__init__.py"]:
+        text = path.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
+
+
+def test_router_state_dict_is_reference_compatible(rq, golden_dir):
+    gold = np.load(golden_dir / "router_golden.npz")
+    state = {k[len("h64/state/"):]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("h64/state/")}
+    router = rq.RetrievalRouter()
+    assert set(router.state_dict()) == set(state)
+    router.load_state_dict(state)                       # strict: same keys, same shapes
+    assert router.stats_initialized is False            # plain attribute, not in the checkpoint
+    assert router._count_params() == 321
+    assert rq.RetrievalRouter(rq.RouterConfig(hidden_dim=32))._count_params() == 161
+    with pytest.raises(ValueError):
+        rq.RetrievalRouter(rq.RouterConfig(num_layers=3))
+    with pytest.raises(ValueError):
+        rq.RetrievalRouter(rq.RouterConfig(use_batch_norm=True))
+
+
+def test_synth_is_deterministic_and_shardable(rq):
+    from rag_uq_b200 import synth
+    a = synth.passage_embeddings(100, 228, 64, "cpu")
+    b = synth.passage_embeddings(0, 300, 64, "cpu")[100:228]
+    assert torch.equal(a, b)
+    cdf = synth.zipf_cdf(synth.vocab_size(1000), "cpu")
+    off1, tok1 = synth.doc_tokens(10, 60, cdf)
+    off2, tok2 = synth.doc_tokens(0, 60, cdf)
+    assert torch.equal(tok1, tok2[int(off2[10]):])
+    lens = (off2[1:] - off2[:-1])
+    assert 20 <= int(lens.min()) and int(lens.max()) <= 300
+    q1 = synth.make_queries(5, 1000, 64, cdf, "cpu")
+    q2 = synth.make_queries(5, 1000, 64, cdf, "cpu")
+    assert torch.equal(q1.q_terms, q2.q_terms) and torch.equal(q1.q_emb, q2.q_emb)
+    assert q1.q_off.tolist() == [0, 8, 16, 24, 32, 40]
+    # the query's tokens really come from its source passage
+    off, tok = synth.doc_tokens(0, 1000, cdf)
+    for i in range(5):
+        src = int(q1.source_rows[i])
+        doc = set(tok[int(off[src]):int(off[src + 1])].tolist())
+        assert all(t in doc or t >= cdf.shape[0] for t in q1.q_terms[8 * i:8 * i + 8].tolist())
+
+
+def test_shard_rows_partition():
+    import rag_uq_b200 as rq
+    for n, world in [(10, 3), (10_000_000, 8), (7, 8), (1, 1)]:
+        parts = [rq.shard_rows(n, world, r) for r in range(world)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        sizes = [hi - lo for lo, hi in parts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_streaming_index_checkpoint_and_resume(rq, tmp_path):
+    """StreamingIndex keeps the reference's checkpoint semantics (streaming_index.py:593-679)."""
+
+    class FakeRetriever:
+        def __init__(self):
+            self.batches, self.documents = [], {}
+
+        def add_documents(self, docs):
+            self.batches.append([d.id for d in docs])
+            self.documents.update({d.id: d for d in docs})
+            return {}
+
+        def __len__(self):
+            return len(self.documents)
+
+    corpus = tmp_path / "corpus.jsonl"
+    lines = [json.dumps({"id": f"d{i}", "text": f"text {i}", "title": f"t{i}"}) for i in range(7)]
+    lines.insert(3, "{not json")                         # skipped with a warning, still counts as an offset
+    lines.insert(5, json.dumps({"id": "no-text"}))       # KeyError -> skipped
+    corpus.write_text("\n".join(lines) + "\n")
+    ckpt = tmp_path / "state" / "ckpt.json"
+
+    fake = FakeRetriever()
+    index = rq.StreamingIndex(fake, checkpoint_path=str(ckpt), batch_size=3)
+    assert index.get_progress() == {"last_offset": 0, "total_indexed": 0, "files_completed": [], "retriever_size": 0}
+    gen = index.stream_from_jsonl(str(corpus))
+    assert next(gen) == 3
+    saved = json.loads(ckpt.read_text())
+    assert saved["last_offset"] == 3 and saved["total_indexed"] == 3      # committed right after the third line
+    # crash here; a new process resumes from the checkpoint and does not re-add the first batch
+    fake2 = FakeRetriever()
+    index2 = rq.StreamingIndex(fake2, checkpoint_path=str(ckpt), batch_size=3)
+    assert list(index2.stream_from_jsonl(str(corpus))) == [3, 1]
+    assert fake2.batches == [["d3", "d4", "d5"], ["d6"]]
+    final = json.loads(ckpt.read_text())
+    assert final == {"last_offset": 9, "total_indexed": 7, "files_completed": [str(corpus)]}
+    with pytest.raises(FileNotFoundError):
+        list(index2.stream_from_jsonl(str(tmp_path / "missing.jsonl")))
+    # resume=False starts over
+    fake3 = FakeRetriever()
+    index3 = rq.StreamingIndex(fake3, checkpoint_path=str(tmp_path / "other.json"), batch_size=100)
+    assert list(index3.stream_from_jsonl(str(corpus), resume=False)) == [7]
+
+
+def test_bm25_index_host_state_and_pickle_schema(rq, tmp_path):
+    path = tmp_path / "idx" / "bm25.pkl"
+    index = rq.BM25Index(persist_path=str(path), k1=1.2, b=0.5)
+    docs = [rq.Document(id="a", text="The Sky  is BLUE"), rq.Document(id="b", text="the sun", title="Sun", metadata={"x": 1})]
+    assert index.add_documents(docs) == 2
+    assert index.add_documents(docs) == 0                           # ids already present (:134)
+    assert index.tokenized_corpus[0] == ["the", "sky", "is", "blue"] and len(index) == 2
+    assert index.get_document("b").title == "Sun" and index.get_document("zz") is None
+    import pickle
+    payload = pickle.loads(path.read_bytes())
+    assert set(payload) == {"documents", "doc_ids", "tokenized_corpus", "k1", "b"}
+    assert payload["documents"]["b"] == {"id": "b", "text": "the sun", "title": "Sun", "metadata": {"x": 1}}
+    again = rq.BM25Index(persist_path=str(path))
+    assert again.doc_ids == ["a", "b"] and again.k1 == 1.2 and again.b == 0.5 and again.vocab == index.vocab
+    q_rows = [[again.vocab.get(t, -1) for t in again._tokenize(q)] for q in ["the moon", ""]]
+    assert q_rows == [[again.vocab["the"], -1], []]
+    assert rq.BM25Index().search("anything") == []                   # empty index -> [] (:165-166)
+    d = rq.Document.from_dict({"id": "q", "text": "t"})
+    assert d.title is None and d.to_dict() == {"id": "q", "text": "t", "title": "", "metadata": {}}
+
+
+def test_confidence_host_math(rq):
+    from rag_uq_b200.confidence import embedding_variance, lexical_diversity
+    emb = np.array([[0.0, 0.0], [2.0, 0.0], [0.0, 2.0], [2.0, 2.0]])
+    var, centroid, dist = embedding_variance(emb)
+    assert np.allclose(centroid, [1, 1]) and np.allclose(dist, np.sqrt(2)) and var == pytest.approx(0.0)
+    assert lexical_diversity(["a b", "a c"]) == 0.75 and lexical_diversity([]) == 1.0
+
+    class LLM:
+        def __init__(self):
+            self.n = 0
+
+        def generate(self, **kw):
+            self.n += 1
+            return {"response": ["Paris", "Paris", "London", ""][self.n % 4]}
+
+    class Enc:
+        def encode(self, texts):
+            return np.array([[1.0, 0.0] if t == "Paris" else [0.0, 1.0] for t in texts])
+
+    res = rq.MCDropoutConfidence(LLM(), n_samples=8, encoder=Enc()).get_confidence_interval("p", "c", "q")
+    assert res.consensus_answer == "Paris" and 0.0 <= res.confidence <= 1.0
+    assert res.uncertainty_score == pytest.approx(min(1.0, res.embedding_variance / 2))
+    assert res.metadata["n_samples"] == 6
