@@ -11,15 +11,22 @@
 //
 // Kernel shape.  grid = (queries, stripes); a block of 8 warps owns one stripe of
 // consecutive documents for one query, each WARP owns a contiguous eighth of it and walks
-// it in ranges of 256 documents.  Per range the warp keeps a 256-float accumulator in
-// shared memory and streams, term after term, the postings that fall in the range:
-// posting lists are sorted by document, so every warp simply continues reading where it
-// stopped (one cursor per term), 128-byte coalesced, 1 to 8 independent 32-posting chunks in
-// flight per pass depending on the list's density.  Within one 32-posting chunk all documents are distinct, so
-// the accumulation is a plain shared-memory read-modify-write: no atomics anywhere.
-// Terms whose next posting lies beyond the range are skipped without touching memory.
-// The block-wide running top-k (topk.cuh) then filters the 8x256 scores: one barrier per
-// range in steady state.
+// it in ranges of 256 documents (8 per lane).  Two ways a term reaches the accumulator:
+//  * the handful of terms that occur in more than 1/8 of all documents (stop words: they carry
+//    >90% of all postings) are ALSO stored as a dense row of uint8 term frequencies; a lane
+//    loads its 8 bytes with one 64-bit load per term and accumulates in registers - no document
+//    ids, no cursor, no compare, ~12x fewer instructions per posting than list streaming;
+//  * every other term streams its posting list: lists are sorted by document, so a warp
+//    continues reading where it stopped (one cursor per term, placed once by a 32-ary search),
+//    128-byte coalesced, 1 to 8 independent 32-posting chunks per pass sized to the list's
+//    density, into a 256-float shared-memory accumulator.  All documents inside one chunk are
+//    distinct, so the update is a plain read-modify-write: no atomics anywhere.  Terms whose
+//    next posting lies beyond the range are skipped with one ballot.
+// Which terms use the table is decided from GLOBAL document frequencies, so every shard makes
+// the same choice and the fp32 accumulation order (table terms in query order, then list terms
+// in query order) does not depend on how the corpus is sharded.
+// The block-wide running top-k (topk.cuh) then filters the 8x256 scores: one barrier per range
+// in steady state.
 #include <climits>
 
 #include "common.cuh"
@@ -31,6 +38,7 @@ constexpr int BM_THREADS = 256;
 constexpr int BM_WARPS = BM_THREADS / 32;
 constexpr int BM_RANGE = 256;          // documents per warp range
 constexpr int BM_MAX_TERMS = 64;
+constexpr int BM_MAX_DENSE = 64;  // rows of the dense tf table
 constexpr int BM_SEARCH = 4;  // posting lists searched concurrently while placing the cursors
 
 struct Bm25Args {
@@ -51,6 +59,10 @@ struct Bm25Args {
   int capacity;
   uint64_t* part_keys;  // [queries, stripes, k]            (top-k mode)
   float* out_scores;    // [queries, n_docs]                (dense mode)
+  const uint8_t* dense_tf;   // [n_dense, dense_stride] tf of the most frequent terms, 0 = absent
+  const int32_t* dense_terms;  // [n_dense] term id of each row
+  int64_t dense_stride;      // multiple of BM_RANGE, >= n_docs
+  int n_dense;
 };
 
 // Stream the postings of one term that fall below d1 into the warp's accumulator.
@@ -122,15 +134,22 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   sp += sizeof(float) * BM_WARPS * BM_RANGE;
   float* nrmw = reinterpret_cast<float*>(sp) + warp * BM_RANGE;
   sp += sizeof(float) * BM_WARPS * BM_RANGE;
-  float* s_wgt = reinterpret_cast<float*>(sp) + warp * mt;
+  float* s_wgt = reinterpret_cast<float*>(sp) + warp * mt;    // sparse term weights
   sp += sizeof(float) * BM_WARPS * mt;
-  int* s_nxt = reinterpret_cast<int*>(sp) + warp * mt;
+  float* s_dwgt = reinterpret_cast<float*>(sp) + warp * mt;   // dense-table term weights
+  sp += sizeof(float) * BM_WARPS * mt;
+  int* s_nxt = reinterpret_cast<int*>(sp) + warp * mt;        // next document of each sparse term
   sp += sizeof(int) * BM_WARPS * mt;
-  unsigned char* s_dense = sp + warp * mt;
+  int* s_tmp = reinterpret_cast<int*>(sp) + warp * mt;        // term ids while the cursors are placed
+  sp += sizeof(int) * BM_WARPS * mt;
+  unsigned char* s_dense = sp + warp * mt;                    // chunks per pass class of each sparse term
+  sp += BM_WARPS * mt;
+  unsigned char* s_dslot = sp + warp * mt;                    // dense-table row of each dense term
 
   __shared__ int s_count;
   __shared__ uint64_t s_threshold;
   __shared__ int s_pending[3];
+  __shared__ int s_dterms[BM_MAX_DENSE];
 
   const int q = blockIdx.x;
   const int64_t stripe_begin = static_cast<int64_t>(blockIdx.y) * a.stripe_docs;
@@ -140,33 +159,59 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   const int64_t w_end = min(stripe_end, w_begin + sub_docs);
   const int n_iters = static_cast<int>(sub_docs / BM_RANGE);
 
+  for (int i = tid; i < a.n_dense; i += BM_THREADS) s_dterms[i] = a.dense_terms[i];
   BlockTopK<BM_THREADS> tk;
   if (!DENSE_OUT) {
     if (tid < 3) s_pending[tid] = 0;
     tk.init(s_keys, &s_count, &s_threshold, a.k, a.capacity, positive_floor_key());
+  } else {
+    __syncthreads();
   }
 
-  // ---- per-warp cursors: lower_bound(post_doc[term], w_begin) by a 32-ary search, 4 terms at a time
+  // ---- split the query's terms: rows of the dense tf table vs posting lists -------------------
   const int qb = a.q_off[q];
   const int nt = min(a.q_off[q + 1] - qb, mt);
-  int ntv = 0;  // valid terms kept (warp-uniform)
-  for (int g = 0; g < nt; g += BM_SEARCH) {
+  int nd = 0, ns = 0;  // dense / sparse term counts (warp-uniform)
+  for (int base = 0; base < nt; base += 32) {
+    const int ti = base + lane;
+    int t = -1, slot = -1;
+    float w = 0.0f;
+    if (ti < nt) {
+      t = a.q_terms[qb + ti];
+      if (t >= 0 && t < a.vocab) {
+        w = a.idf[t] * a.k1p1;
+        for (int e = 0; e < a.n_dense; ++e)
+          if (s_dterms[e] == t) slot = e;
+      }
+    }
+    const bool live = w != 0.0f;
+    const unsigned md = __ballot_sync(0xffffffffu, live && slot >= 0);
+    const unsigned ms = __ballot_sync(0xffffffffu, live && slot < 0);
+    if (live && slot >= 0) {
+      const int o = nd + __popc(md & ((1u << lane) - 1));
+      s_dslot[o] = static_cast<unsigned char>(slot);
+      s_dwgt[o] = w;
+    }
+    if (live && slot < 0) s_tmp[ns + __popc(ms & ((1u << lane) - 1))] = t;
+    nd += __popc(md);
+    ns += __popc(ms);
+  }
+  __syncwarp();
+
+  // ---- per-warp cursors: lower_bound(post_doc[term], w_begin) by a 32-ary search, 4 terms at a time
+  int ntv = 0;  // sparse terms with a non-empty posting list (warp-uniform)
+  for (int g = 0; g < ns; g += BM_SEARCH) {
     int64_t lo[BM_SEARCH], hi[BM_SEARCH], te[BM_SEARCH], ts[BM_SEARCH];
     float wg[BM_SEARCH];
 #pragma unroll
     for (int j = 0; j < BM_SEARCH; ++j) {
       lo[j] = hi[j] = te[j] = ts[j] = 0;
       wg[j] = 0.0f;
-      if (g + j < nt) {
-        const int t = a.q_terms[qb + g + j];
-        if (t >= 0 && t < a.vocab) {
-          const float w = a.idf[t] * a.k1p1;
-          if (w != 0.0f) {
-            lo[j] = ts[j] = a.term_off[t];
-            hi[j] = te[j] = a.term_off[t + 1];
-            wg[j] = w;
-          }
-        }
+      if (g + j < ns) {
+        const int t = s_tmp[g + j];
+        lo[j] = ts[j] = a.term_off[t];
+        hi[j] = te[j] = a.term_off[t + 1];
+        if (hi[j] > lo[j]) wg[j] = a.idf[t] * a.k1p1;
       }
     }
     const int target = static_cast<int>(w_begin);
@@ -201,19 +246,20 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         }
       }
     }
+    __syncwarp();  // s_tmp[g..g+3] has been read by every lane before slots below are written
 #pragma unroll
     for (int j = 0; j < BM_SEARCH; ++j) {
       if (wg[j] != 0.0f) {  // warp-uniform
         const int64_t idx = lo[j] + lane;
         const bool below = idx < hi[j] && __ldg(a.post_doc + idx) < target;
         const int64_t cur = lo[j] + __popc(__ballot_sync(0xffffffffu, below));
-        int nd = INT_MAX;
-        if (cur < te[j]) nd = __ldg(a.post_doc + cur);
+        int nx = INT_MAX;
+        if (cur < te[j]) nx = __ldg(a.post_doc + cur);
         if (lane == 0) {
           s_pos[ntv] = cur;
           s_end[ntv] = te[j];
           s_wgt[ntv] = wg[j];
-          s_nxt[ntv] = nd;
+          s_nxt[ntv] = nx;
           // expected postings of this term per 256-document range
           const double per_range = static_cast<double>(te[j] - ts[j]) * BM_RANGE / static_cast<double>(a.n_docs);
           s_dense[ntv] = per_range < 24.0 ? 0 : (per_range < 56.0 ? 1 : (per_range < 120.0 ? 2 : 3));
@@ -225,20 +271,77 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   __syncwarp();
 
   int local_count = 0;  // replica of tk.count, identical in every thread
+  const int j0 = lane * 8;  // the 8 documents of the range this lane owns outside the posting phase
   for (int it = 0; it < n_iters; ++it) {
     const int64_t d0l = w_begin + static_cast<int64_t>(it) * BM_RANGE;
     const int d0 = static_cast<int>(d0l < w_end ? d0l : w_end);
     const int d1 = static_cast<int>(min(w_end, d0l + BM_RANGE));
     const int cnt = d1 > d0 ? d1 - d0 : 0;
+    float ac[8], nr[8];
 #pragma unroll
-    for (int j = lane; j < BM_RANGE; j += 32) {
-      accw[j] = 0.0f;
-      nrmw[j] = j < cnt ? __ldg(a.norm + d0 + j) : 1.0f;
+    for (int j = 0; j < 8; ++j) ac[j] = 0.0f;
+    if (cnt == BM_RANGE) {
+      const float4 n0 = __ldg(reinterpret_cast<const float4*>(a.norm + d0 + j0));
+      const float4 n1 = __ldg(reinterpret_cast<const float4*>(a.norm + d0 + j0 + 4));
+      nr[0] = n0.x; nr[1] = n0.y; nr[2] = n0.z; nr[3] = n0.w;
+      nr[4] = n1.x; nr[5] = n1.y; nr[6] = n1.z; nr[7] = n1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) nr[j] = (j0 + j) < cnt ? __ldg(a.norm + d0 + j0 + j) : 1.0f;
     }
-    __syncwarp();
+    // ---- dense-table terms: 8 tf bytes per lane per term, accumulators stay in registers
     if (cnt > 0) {
+      for (int i0 = 0; i0 < nd; i0 += 4) {
+        uint2 tf8[4];
+        float w4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          tf8[u] = make_uint2(0u, 0u);
+          w4[u] = 0.0f;
+          if (i0 + u < nd) {
+            w4[u] = s_dwgt[i0 + u];
+            tf8[u] = __ldg(reinterpret_cast<const uint2*>(a.dense_tf + static_cast<int64_t>(s_dslot[i0 + u]) * a.dense_stride + d0 + j0));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const unsigned word = j < 4 ? tf8[u].x : tf8[u].y;
+            const unsigned tfb = (word >> (8 * (j & 3))) & 0xffu;
+            const float f = __uint_as_float(0x4B000000u | tfb) - 8388608.0f;  // exact small-int -> float
+            ac[j] = fmaf(w4[u], __fdividef(f, f + nr[j]), ac[j]);
+          }
+        }
+      }
+    }
+    // ---- posting-list terms: shared-memory accumulator, only when some list reaches into the range
+    unsigned active = 0;  // terms ti < 32 with a posting in the range; longer queries fall back to a scan
+    bool any_sparse = false;
+    if (cnt > 0 && ntv > 0) {
+      if (ntv <= 32) {
+        active = __ballot_sync(0xffffffffu, lane < ntv && s_nxt[lane] < d1);
+        any_sparse = active != 0;
+      } else {
+        any_sparse = true;
+      }
+    }
+    if (any_sparse || DENSE_OUT) {
+      *reinterpret_cast<float4*>(accw + j0) = make_float4(ac[0], ac[1], ac[2], ac[3]);
+      *reinterpret_cast<float4*>(accw + j0 + 4) = make_float4(ac[4], ac[5], ac[6], ac[7]);
+    }
+    if (any_sparse) {
+      *reinterpret_cast<float4*>(nrmw + j0) = make_float4(nr[0], nr[1], nr[2], nr[3]);
+      *reinterpret_cast<float4*>(nrmw + j0 + 4) = make_float4(nr[4], nr[5], nr[6], nr[7]);
+      __syncwarp();
       for (int ti = 0; ti < ntv; ++ti) {
-        if (s_nxt[ti] >= d1) continue;  // nothing of this term in the range
+        if (ntv <= 32) {
+          if (active == 0) break;
+          ti = __ffs(active) - 1;
+          active &= active - 1;
+        } else if (s_nxt[ti] >= d1) {
+          continue;
+        }
         int64_t pos = s_pos[ti];
         const int64_t end = s_end[ti];
         const float w = s_wgt[ti];
@@ -255,21 +358,25 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         }
         __syncwarp();
       }
+      const float4 r0 = *reinterpret_cast<const float4*>(accw + j0);
+      const float4 r1 = *reinterpret_cast<const float4*>(accw + j0 + 4);
+      ac[0] = r0.x; ac[1] = r0.y; ac[2] = r0.z; ac[3] = r0.w;
+      ac[4] = r1.x; ac[5] = r1.y; ac[6] = r1.z; ac[7] = r1.w;
     }
     if (DENSE_OUT) {
+      __syncwarp();
       float* dst = a.out_scores + static_cast<int64_t>(q) * a.n_docs + d0;
       for (int j = lane; j < cnt; j += 32) dst[j] = accw[j];
       __syncwarp();
     } else {
       // ---- block-wide selection: count what beats the threshold, one barrier, then append
       const uint64_t thr = s_threshold;
-      const int32_t gid0 = static_cast<int32_t>(a.id_base + d0);
+      const float thr_score = key_score(thr);
+      const int32_t gid0 = static_cast<int32_t>(a.id_base + d0) + j0;
       unsigned mask = 0;
 #pragma unroll
-      for (int u = 0; u < BM_RANGE / 32; ++u) {
-        const int j = u * 32 + lane;
-        if (j < cnt && make_key(accw[j], gid0 + j) > thr) mask |= 1u << u;
-      }
+      for (int j = 0; j < 8; ++j)
+        if (ac[j] >= thr_score && (j0 + j) < cnt && make_key(ac[j], gid0 + j) > thr) mask |= 1u << j;
       int mine = __popc(mask);
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, s);
@@ -279,22 +386,25 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
       if (tid == 0) s_pending[(it + 2) % 3] = 0;
       if (local_count + pending <= tk.room()) {
 #pragma unroll
-        for (int u = 0; u < BM_RANGE / 32; ++u)
-          if (mask & (1u << u)) {
-            const int j = u * 32 + lane;
+        for (int j = 0; j < 8; ++j)
+          if (mask & (1u << j)) {
             const int slot = atomicAdd(&s_count, 1);
-            s_keys[a.k + slot] = make_key(accw[j], gid0 + j);
+            s_keys[a.k + slot] = make_key(ac[j], gid0 + j);
           }
         local_count += pending;
       } else {
-        // slow path (first ranges, adversarial data): 64 documents per warp at a time
-        for (int ph = 0; ph < BM_RANGE / 64; ++ph) {
+        // slow path (first ranges, adversarial data): 2 documents per lane at a time
+        for (int ph = 0; ph < 4; ++ph) {
           tk.reserve(BM_WARPS * 64);
           const uint64_t t2 = s_threshold;
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int j = ph * 64 + u * 32 + lane;
-            if (j < cnt) tk.offer(make_key(accw[j], gid0 + j), t2);
+            const int j = ph * 2 + u;
+            float v = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              if (jj == j) v = ac[jj];
+            if ((j0 + j) < cnt) tk.offer(make_key(v, gid0 + j), t2);
           }
         }
         __syncthreads();
@@ -399,19 +509,29 @@ static size_t bm25_smem_bytes(int max_terms, int capacity, bool dense_out) {
   b += 2 * sizeof(int64_t) * BM_WARPS * max_terms;
   if (!dense_out) b += sizeof(uint64_t) * capacity;
   b += 2 * sizeof(float) * BM_WARPS * BM_RANGE;
-  b += (sizeof(float) + sizeof(int) + 1) * BM_WARPS * max_terms;
+  b += (2 * sizeof(float) + 2 * sizeof(int) + 2) * BM_WARPS * max_terms;
   return (b + 15) & ~static_cast<size_t>(15);
 }
 
 static int bm25_common_checks(const char* who, const int64_t* term_off, const int32_t* post_doc,
                               const uint16_t* post_tf, const float* norm, const float* idf, int64_t vocab,
                               const int32_t* q_terms, const int32_t* q_off, int32_t n_queries, int64_t n_docs,
-                              int32_t max_terms) {
+                              int32_t max_terms, const uint8_t* dense_tf, int64_t dense_stride,
+                              const int32_t* dense_terms, int32_t n_dense) {
   RAGB_REQUIRE(term_off && post_doc && post_tf && norm && idf && q_terms && q_off, RAGB_EINVAL, "%s: null pointer", who);
   RAGB_REQUIRE(vocab > 0 && n_queries > 0 && n_docs > 0, RAGB_EINVAL, "%s: empty shape", who);
   RAGB_REQUIRE(n_docs < (1ll << 31) - BM_RANGE, RAGB_ELIMIT, "%s: n_docs per shard must fit int32", who);
   RAGB_REQUIRE(max_terms >= 1 && max_terms <= BM_MAX_TERMS, RAGB_ELIMIT,
                "%s: max_query_terms=%d outside [1,%d]", who, max_terms, BM_MAX_TERMS);
+  RAGB_REQUIRE(n_dense >= 0 && n_dense <= BM_MAX_DENSE, RAGB_ELIMIT, "%s: n_dense=%d outside [0,%d]", who, n_dense,
+               BM_MAX_DENSE);
+  if (n_dense > 0) {
+    RAGB_REQUIRE(dense_tf && dense_terms, RAGB_EINVAL, "%s: dense table pointers missing", who);
+    RAGB_REQUIRE(dense_stride >= n_docs && dense_stride % BM_RANGE == 0, RAGB_EINVAL,
+                 "%s: dense_stride must be a multiple of %d covering n_docs", who, BM_RANGE);
+    RAGB_REQUIRE((reinterpret_cast<uintptr_t>(dense_tf) & 15) == 0, RAGB_EINVAL, "%s: dense table must be 16-byte aligned", who);
+  }
+  RAGB_REQUIRE((reinterpret_cast<uintptr_t>(norm) & 15) == 0, RAGB_EINVAL, "%s: norm must be 16-byte aligned", who);
   return RAGB_OK;
 }
 
@@ -460,14 +580,15 @@ size_t ragb_bm25_topk_workspace_bytes(int32_t n_queries, int64_t n_docs, int32_t
 }
 
 int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
-                         const float* idf, int64_t vocab, double k1, const int32_t* q_terms, const int32_t* q_off,
+                         const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
+                         const int32_t* dense_terms, int32_t n_dense, const int32_t* q_terms, const int32_t* q_off,
                          int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          float* out_score, int32_t* out_id, void* workspace, size_t workspace_bytes,
                          ragb_stream_t stream_) {
   RAGB_ENTRY();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = bm25_common_checks("ragb_bm25_score_topk", term_off, post_doc, post_tf, norm, idf, vocab, q_terms, q_off,
-                              n_queries, n_docs, max_query_terms);
+                              n_queries, n_docs, max_query_terms, dense_tf, dense_stride, dense_terms, n_dense);
   if (rc != RAGB_OK) return rc;
   RAGB_REQUIRE(out_score && out_id && workspace, RAGB_EINVAL, "ragb_bm25_score_topk: null pointer");
   RAGB_REQUIRE(k > 0 && k <= RAGB_MAX_TOPK, RAGB_ELIMIT, "ragb_bm25_score_topk: k=%d outside [1,%d]", k, RAGB_MAX_TOPK);
@@ -487,6 +608,10 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   a.id_base = id_base;
   a.k1p1 = static_cast<float>(k1 + 1.0);
   a.max_terms = max_query_terms;
+  a.dense_tf = dense_tf;
+  a.dense_terms = dense_terms;
+  a.dense_stride = dense_stride;
+  a.n_dense = n_dense;
   a.k = k;
   a.capacity = topk_capacity(k);
   a.part_keys = static_cast<uint64_t*>(workspace);
@@ -500,13 +625,14 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
 }
 
 int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
-                     const float* idf, int64_t vocab, double k1, const int32_t* q_terms, const int32_t* q_off,
+                     const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
+                     const int32_t* dense_terms, int32_t n_dense, const int32_t* q_terms, const int32_t* q_off,
                      int32_t n_queries, int32_t max_query_terms, int64_t n_docs, float* out_scores,
                      ragb_stream_t stream_) {
   RAGB_ENTRY();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = bm25_common_checks("ragb_bm25_scores", term_off, post_doc, post_tf, norm, idf, vocab, q_terms, q_off,
-                              n_queries, n_docs, max_query_terms);
+                              n_queries, n_docs, max_query_terms, dense_tf, dense_stride, dense_terms, n_dense);
   if (rc != RAGB_OK) return rc;
   RAGB_REQUIRE(out_scores, RAGB_EINVAL, "ragb_bm25_scores: null pointer");
   Bm25Args a{};
@@ -522,6 +648,10 @@ int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uin
   a.id_base = 0;
   a.k1p1 = static_cast<float>(k1 + 1.0);
   a.max_terms = max_query_terms;
+  a.dense_tf = dense_tf;
+  a.dense_terms = dense_terms;
+  a.dense_stride = dense_stride;
+  a.n_dense = n_dense;
   a.k = 1;
   a.capacity = 0;
   const int stripes = bm25_stripes(n_queries, n_docs, &a.stripe_docs);

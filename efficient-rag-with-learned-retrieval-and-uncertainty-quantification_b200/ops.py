@@ -72,6 +72,17 @@ def _(doc_len, avgdl, k1, b):
     return doc_len.new_empty(doc_len.shape, dtype=torch.float32)
 
 
+def _dense_table(dense_tf: Tensor, dense_terms: Tensor, n_docs: int):
+    """(ptr, stride, terms ptr, rows) of the optional dense tf table; an empty tensor disables it."""
+    if dense_tf.numel() == 0 or dense_terms.numel() == 0:
+        return None, 0, None, 0
+    dense_tf = _need(dense_tf, torch.uint8, "dense_tf")
+    dense_terms = _need(dense_terms, torch.int32, "dense_terms")
+    if dense_tf.dim() != 2 or dense_tf.shape[0] != dense_terms.shape[0] or dense_tf.shape[1] < n_docs:
+        raise ValueError("dense_tf must be [n_dense, stride >= n_docs] with one row per entry of dense_terms")
+    return dense_tf.data_ptr(), dense_tf.shape[1], dense_terms.data_ptr(), dense_terms.shape[0]
+
+
 def _bm25_args(term_off, post_doc, post_tf, norm, idf, q_terms, q_off):
     term_off = _need(term_off, torch.int64, "term_off")
     post_doc = _need(post_doc, torch.int32, "post_doc")
@@ -87,43 +98,47 @@ def _bm25_args(term_off, post_doc, post_tf, norm, idf, q_terms, q_off):
 
 @torch.library.custom_op(f"{NS}::bm25_score_topk", mutates_args=(), device_types="cuda")
 def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
-                    q_terms: Tensor, q_off: Tensor, max_query_terms: int, id_base: int,
-                    k: int) -> Tuple[Tensor, Tensor]:
+                    dense_tf: Tensor, dense_terms: Tensor, q_terms: Tensor, q_off: Tensor, max_query_terms: int,
+                    id_base: int, k: int) -> Tuple[Tensor, Tensor]:
     term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
                                                                         q_terms, q_off)
     n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
     score = torch.empty((n_q, k), dtype=torch.float32, device=dev)
     ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
     ws = _workspace(lib.ragb_bm25_topk_workspace_bytes(n_q, n_docs, k), dev)
+    dt, stride, dterms, n_dense = _dense_table(dense_tf, dense_terms, n_docs)
     with torch.cuda.device(dev):
         check(lib.ragb_bm25_score_topk(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf),
-                                       idf.shape[0], k1, _ptr(q_terms), _ptr(q_off), n_q, max_query_terms, n_docs,
-                                       id_base, k, _ptr(score), _ptr(ids), _ptr(ws), ws.numel(), _stream()))
+                                       idf.shape[0], k1, dt, stride, dterms, n_dense, _ptr(q_terms), _ptr(q_off), n_q,
+                                       max_query_terms, n_docs, id_base, k, _ptr(score), _ptr(ids), _ptr(ws),
+                                       ws.numel(), _stream()))
     return score, ids
 
 
 @bm25_score_topk.register_fake
-def _(term_off, post_doc, post_tf, norm, idf, k1, q_terms, q_off, max_query_terms, id_base, k):
+def _(term_off, post_doc, post_tf, norm, idf, k1, dense_tf, dense_terms, q_terms, q_off, max_query_terms, id_base, k):
     n_q = q_off.shape[0] - 1
     return norm.new_empty((n_q, k)), norm.new_empty((n_q, k), dtype=torch.int32)
 
 
 @torch.library.custom_op(f"{NS}::bm25_scores", mutates_args=(), device_types="cuda")
 def bm25_scores(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
-                q_terms: Tensor, q_off: Tensor, max_query_terms: int) -> Tensor:
+                dense_tf: Tensor, dense_terms: Tensor, q_terms: Tensor, q_off: Tensor,
+                max_query_terms: int) -> Tensor:
     term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
                                                                         q_terms, q_off)
     n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
     out = torch.empty((n_q, n_docs), dtype=torch.float32, device=dev)
+    dt, stride, dterms, n_dense = _dense_table(dense_tf, dense_terms, n_docs)
     with torch.cuda.device(dev):
         check(lib.ragb_bm25_scores(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf),
-                                   idf.shape[0], k1, _ptr(q_terms), _ptr(q_off), n_q, max_query_terms, n_docs,
-                                   _ptr(out), _stream()))
+                                   idf.shape[0], k1, dt, stride, dterms, n_dense, _ptr(q_terms), _ptr(q_off), n_q,
+                                   max_query_terms, n_docs, _ptr(out), _stream()))
     return out
 
 
 @bm25_scores.register_fake
-def _(term_off, post_doc, post_tf, norm, idf, k1, q_terms, q_off, max_query_terms):
+def _(term_off, post_doc, post_tf, norm, idf, k1, dense_tf, dense_terms, q_terms, q_off, max_query_terms):
     return norm.new_empty((q_off.shape[0] - 1, norm.shape[0]))
 
 

@@ -22,9 +22,12 @@ from dataclasses import dataclass
 from typing import List, Optional
 
 import torch
+import torch.distributed as dist
 from torch import Tensor
 
 from . import ops
+
+MAX_DENSE_TERMS = 64
 
 
 @dataclass
@@ -44,13 +47,16 @@ class SparseShard:
     norm: Optional[Tensor] = None
     corpus_size: int = 0
     avgdl: float = 0.0
+    dense_tf: Optional[Tensor] = None      # uint8 [n_dense, stride]: tf rows of the most frequent terms
+    dense_terms: Optional[Tensor] = None   # int32 [n_dense]
+    use_dense_table: bool = True
 
     @property
     def nnz(self) -> int:
         return int(self.post_doc.shape[0])
 
     def finalize(self, df_global: Optional[Tensor] = None, corpus_size: Optional[int] = None,
-                 total_len: Optional[int] = None) -> "SparseShard":
+                 total_len: Optional[int] = None, group=None) -> "SparseShard":
         """(Re)compute idf[V] and norm[N] from GLOBAL statistics (defaults: this shard alone)."""
         df_global = self.df if df_global is None else df_global
         self.corpus_size = self.n_docs if corpus_size is None else int(corpus_size)
@@ -58,15 +64,50 @@ class SparseShard:
         self.avgdl = total / self.corpus_size
         self.idf = ops.bm25_build_idf(df_global.to(torch.int32), self.corpus_size, self.epsilon)
         self.norm = ops.bm25_build_norm(self.doc_len, self.avgdl, self.k1, self.b)
+        self._build_dense_table(df_global, group)
         return self
+
+    def _build_dense_table(self, df_global: Tensor, group=None) -> None:
+        """Dense uint8 tf rows for the terms present in >= 1/8 of ALL documents (at most 64).
+
+        The choice uses global document frequencies and a cross-shard agreement on "every tf fits
+        a byte", so all shards pick the same terms and accumulate in the same order.
+        """
+        dev = self.post_doc.device
+        empty_u8 = torch.empty(0, dtype=torch.uint8, device=dev)
+        self.dense_tf, self.dense_terms = empty_u8, torch.empty(0, dtype=torch.int32, device=dev)
+        if not self.use_dense_table or self.n_docs == 0:
+            return
+        cand = torch.nonzero(df_global.to(torch.int64) * 8 >= self.corpus_size).flatten()
+        if cand.numel() == 0:
+            return
+        if cand.numel() > MAX_DENSE_TERMS:
+            top = torch.topk(df_global[cand].to(torch.int64), MAX_DENSE_TERMS).indices
+            cand = cand[top].sort().values
+        lo, hi = self.term_off[cand].tolist(), self.term_off[cand + 1].tolist()
+        fits = torch.ones(cand.numel(), dtype=torch.int32, device=dev)
+        for i, (a, b) in enumerate(zip(lo, hi)):
+            if b > a and int((self.post_tf[a:b].to(torch.int32) & 0xFFFF).max()) > 255:
+                fits[i] = 0
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=group)
+        cand = cand[fits.bool()]
+        if cand.numel() == 0:
+            return
+        stride = (self.n_docs + 255) // 256 * 256
+        table = torch.zeros((cand.numel(), stride), dtype=torch.uint8, device=dev)
+        for i, t in enumerate(cand.tolist()):
+            a, b = int(self.term_off[t]), int(self.term_off[t + 1])
+            table[i, self.post_doc[a:b].to(torch.int64)] = self.post_tf[a:b].to(torch.uint8)
+        self.dense_tf, self.dense_terms = table, cand.to(torch.int32)
 
     def score_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int):
         return ops.bm25_score_topk(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1,
-                                   q_terms, q_off, max_terms, self.id_base, k)
+                                   self.dense_tf, self.dense_terms, q_terms, q_off, max_terms, self.id_base, k)
 
     def scores(self, q_terms: Tensor, q_off: Tensor, max_terms: int) -> Tensor:
-        return ops.bm25_scores(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1, q_terms,
-                               q_off, max_terms)
+        return ops.bm25_scores(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1,
+                               self.dense_tf, self.dense_terms, q_terms, q_off, max_terms)
 
 
 def _segment(doc_off: Tensor, doc_tok: Tensor, vocab: int):

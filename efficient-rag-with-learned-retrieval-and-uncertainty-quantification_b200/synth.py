@@ -164,5 +164,5 @@ def build_synthetic_engine(n_passages: int, dim: int, device, rank: int = 0, wor
                 yield doc_tokens(b0, min(hi, b0 + block_docs), cdf)
         sparse = build_shard_blocked(blocks(), hi - lo, vocab, device, id_base=lo)
         df, n_all, len_all = global_bm25_statistics(sparse.df, hi - lo, int(sparse.doc_len.sum()), group)
-        sparse.finalize(df, n_all, len_all)
+        sparse.finalize(df, n_all, len_all, group)
     return HybridEngine(sparse, passages, id_base=lo, group=group, mma_variant=mma_variant), cdf

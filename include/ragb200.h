@@ -65,6 +65,11 @@ int ragb_bm25_build_norm(const int32_t* doc_len, int64_t n_docs, double avgdl, d
  * post_doc/post_tf[term_off[t] .. term_off[t+1]) with post_doc ascending local rows.
  * Queries are ragged lists of term ids q_terms[q_off[i] .. q_off[i+1]); every OCCURRENCE
  * contributes; ids outside [0, vocab) are out-of-vocabulary and contribute 0.
+ * Optional dense tf table: dense_tf[r * dense_stride + d] (uint8, 0 = term absent) holds the
+ * term frequencies of term dense_terms[r] for r < n_dense <= 64 (terms so frequent that a
+ * byte per document beats a posting list; every tf of such a term must be <= 255, and the
+ * choice must be the same on every shard).  Their posting lists stay in the CSR but are not
+ * read.  dense_stride is a multiple of 256, >= n_docs; n_dense = 0 disables the table.
  * max_query_terms (<= RAGB_MAX_QUERY_TERMS) is the caller's bound on the longest query;
  * it sizes the per-warp cursor table and longer queries are cut to it.
  * score = sum idf[t] * tf * (k1 + 1) / (tf + norm[d]).   Only score > 0 is returned
@@ -72,6 +77,8 @@ int ragb_bm25_build_norm(const int32_t* doc_len, int64_t n_docs, double avgdl, d
 size_t ragb_bm25_topk_workspace_bytes(int32_t n_queries, int64_t n_docs, int32_t k);
 int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf,
                          const float* norm, const float* idf, int64_t vocab, double k1,
+                         const uint8_t* dense_tf, int64_t dense_stride,
+                         const int32_t* dense_terms, int32_t n_dense,
                          const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
                          int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          float* out_score, int32_t* out_id,
@@ -79,6 +86,8 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
 /* Same arithmetic, full score vectors out_scores[n_queries, n_docs] (get_scores itself). */
 int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf,
                      const float* norm, const float* idf, int64_t vocab, double k1,
+                     const uint8_t* dense_tf, int64_t dense_stride,
+                     const int32_t* dense_terms, int32_t n_dense,
                      const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
                      int32_t max_query_terms, int64_t n_docs, float* out_scores, ragb_stream_t stream);
 

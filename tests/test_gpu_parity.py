@@ -119,11 +119,22 @@ def test_bm25_csr_build_is_bit_exact(rq, dev):
         assert torch.equal(getattr(blocked, name), getattr(shard, name)), name
 
 
+@pytest.mark.parametrize("table", [True, False])
 @pytest.mark.parametrize("n,n_q", [(10_000, 64), (2500, 3), (300, 5)])
-def test_bm25_scores_and_topk(rq, dev, n, n_q):
+def test_bm25_scores_and_topk(rq, dev, n, n_q, table):
+    """table=True: frequent terms come from the dense tf table; False: every term streams its postings."""
     from rag_uq_b200 import synth
     vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
-    shard = rq.build_shard(doc_off, doc_tok, vocab).finalize()
+    shard = rq.build_shard(doc_off, doc_tok, vocab)
+    shard.use_dense_table = table
+    shard.finalize()
+    assert (shard.dense_terms.numel() > 0) == table
+    if table:   # the table is the postings of those terms, byte for byte
+        t = int(shard.dense_terms[0])
+        a, b = int(shard.term_off[t]), int(shard.term_off[t + 1])
+        row = shard.dense_tf[0]
+        assert int((row != 0).sum()) == b - a
+        assert torch.equal(row[shard.post_doc[a:b].long()].to(torch.int16), shard.post_tf[a:b])
     qb = synth.make_queries(n_q, n, 64, cdf, dev)
     ref = bm25_okapi.OkapiCsr(doc_off.cpu().numpy(), doc_tok.cpu().numpy(), vocab)
     full = shard.scores(qb.q_terms, qb.q_off, qb.max_terms).cpu().numpy()
