@@ -12,8 +12,8 @@
 // Kernel shape.  grid = (queries, stripes); a block of 8 warps owns one stripe of
 // consecutive documents for one query, each WARP owns a contiguous eighth of it and walks
 // it in ranges of 256 documents (8 per lane).  Two ways a term reaches the accumulator:
-//  * the handful of terms that occur in more than 1/8 of all documents (stop words: they carry
-//    >90% of all postings) are ALSO stored as a dense row of uint8 term frequencies; a lane
+//  * the terms that occur in more than 1/64 of all documents (a few hundred; they carry >95% of
+//    all postings) are ALSO stored as a dense row of uint8 term frequencies; a lane
 //    loads its 8 bytes with one 64-bit load per term and accumulates in registers - no document
 //    ids, no cursor, no compare, ~12x fewer instructions per posting than list streaming;
 //  * every other term streams its posting list: lists are sorted by document, so a warp
@@ -38,7 +38,7 @@ constexpr int BM_THREADS = 256;
 constexpr int BM_WARPS = BM_THREADS / 32;
 constexpr int BM_RANGE = 256;          // documents per warp range
 constexpr int BM_MAX_TERMS = 64;
-constexpr int BM_MAX_DENSE = 64;  // rows of the dense tf table
+constexpr int BM_MAX_DENSE = 1024;  // rows of the dense tf table (term ids sorted ascending)
 constexpr int BM_SEARCH = 4;  // posting lists searched concurrently while placing the cursors
 
 struct Bm25Args {
@@ -64,6 +64,15 @@ struct Bm25Args {
   int64_t dense_stride;      // multiple of BM_RANGE, >= n_docs
   int n_dense;
 };
+
+// 1/x for x in the normal range (here x = tf + norm in [0.3, 7e4]): one MUFU.RCP, none of the
+// range-scaling __fdividef wraps around it.  Both accumulation paths use this same expression, so
+// a term scores identically whether it is read from the dense table or from its posting list.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // Stream the postings of one term that fall below d1 into the warp's accumulator.
 // U chunks of 32 postings are loaded per pass (all loads independent) plus one "peek" posting
@@ -94,7 +103,7 @@ __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc
       if (take) {
         const float f = static_cast<float>(tf[u]);
         const int o = doc[u] - d0;
-        accw[o] += weight * __fdividef(f, f + nrmw[o]);
+        accw[o] += weight * (f * fast_rcp(f + nrmw[o]));
       }
       taken += __popc(__ballot_sync(0xffffffffu, take));
     }
@@ -142,9 +151,9 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   sp += sizeof(int) * BM_WARPS * mt;
   int* s_tmp = reinterpret_cast<int*>(sp) + warp * mt;        // term ids while the cursors are placed
   sp += sizeof(int) * BM_WARPS * mt;
+  unsigned short* s_dslot = reinterpret_cast<unsigned short*>(sp) + warp * mt;  // dense-table row of each dense term
+  sp += sizeof(unsigned short) * BM_WARPS * mt;
   unsigned char* s_dense = sp + warp * mt;                    // chunks per pass class of each sparse term
-  sp += BM_WARPS * mt;
-  unsigned char* s_dslot = sp + warp * mt;                    // dense-table row of each dense term
 
   __shared__ int s_count;
   __shared__ uint64_t s_threshold;
@@ -180,8 +189,12 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
       t = a.q_terms[qb + ti];
       if (t >= 0 && t < a.vocab) {
         w = a.idf[t] * a.k1p1;
-        for (int e = 0; e < a.n_dense; ++e)
-          if (s_dterms[e] == t) slot = e;
+        int lo_e = 0, hi_e = a.n_dense;  // lower_bound in the sorted table directory
+        while (lo_e < hi_e) {
+          const int mid = (lo_e + hi_e) >> 1;
+          if (s_dterms[mid] < t) lo_e = mid + 1; else hi_e = mid;
+        }
+        if (lo_e < a.n_dense && s_dterms[lo_e] == t) slot = lo_e;
       }
     }
     const bool live = w != 0.0f;
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
     const unsigned ms = __ballot_sync(0xffffffffu, live && slot < 0);
     if (live && slot >= 0) {
       const int o = nd + __popc(md & ((1u << lane) - 1));
-      s_dslot[o] = static_cast<unsigned char>(slot);
+      s_dslot[o] = static_cast<unsigned short>(slot);
       s_dwgt[o] = w;
     }
     if (live && slot < 0) s_tmp[ns + __popc(ms & ((1u << lane) - 1))] = t;
@@ -305,12 +318,14 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
+          if (i0 + u < nd) {  // warp-uniform
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const unsigned word = j < 4 ? tf8[u].x : tf8[u].y;
-            const unsigned tfb = (word >> (8 * (j & 3))) & 0xffu;
-            const float f = __uint_as_float(0x4B000000u | tfb) - 8388608.0f;  // exact small-int -> float
-            ac[j] = fmaf(w4[u], __fdividef(f, f + nr[j]), ac[j]);
+            for (int j = 0; j < 8; ++j) {
+              const unsigned word = j < 4 ? tf8[u].x : tf8[u].y;
+              const unsigned tfb = (word >> (8 * (j & 3))) & 0xffu;
+              const float f = __uint_as_float(0x4B000000u | tfb) - 8388608.0f;  // exact small-int -> float
+              ac[j] = fmaf(w4[u], f * fast_rcp(f + nr[j]), ac[j]);
+            }
           }
         }
       }
@@ -509,7 +524,7 @@ static size_t bm25_smem_bytes(int max_terms, int capacity, bool dense_out) {
   b += 2 * sizeof(int64_t) * BM_WARPS * max_terms;
   if (!dense_out) b += sizeof(uint64_t) * capacity;
   b += 2 * sizeof(float) * BM_WARPS * BM_RANGE;
-  b += (2 * sizeof(float) + 2 * sizeof(int) + 2) * BM_WARPS * max_terms;
+  b += (2 * sizeof(float) + 2 * sizeof(int) + 3) * BM_WARPS * max_terms;
   return (b + 15) & ~static_cast<size_t>(15);
 }
 

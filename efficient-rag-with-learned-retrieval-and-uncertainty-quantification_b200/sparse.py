@@ -27,7 +27,9 @@ from torch import Tensor
 
 from . import ops
 
-MAX_DENSE_TERMS = 64
+MAX_DENSE_TERMS = 1024          # rows the kernel's table directory can hold
+DENSE_MIN_FRACTION = 64         # a term gets a row when df >= N / 64 ...
+DENSE_TABLE_BYTES = 8 << 30     # ... while the table stays under this many bytes per shard
 
 
 @dataclass
@@ -68,7 +70,7 @@ class SparseShard:
         return self
 
     def _build_dense_table(self, df_global: Tensor, group=None) -> None:
-        """Dense uint8 tf rows for the terms present in >= 1/8 of ALL documents (at most 64).
+        """Dense uint8 tf rows for the terms present in >= 1/64 of ALL documents (capped by memory).
 
         The choice uses global document frequencies and a cross-shard agreement on "every tf fits
         a byte", so all shards pick the same terms and accumulate in the same order.
@@ -78,11 +80,15 @@ class SparseShard:
         self.dense_tf, self.dense_terms = empty_u8, torch.empty(0, dtype=torch.int32, device=dev)
         if not self.use_dense_table or self.n_docs == 0:
             return
-        cand = torch.nonzero(df_global.to(torch.int64) * 8 >= self.corpus_size).flatten()
+        cand = torch.nonzero(df_global.to(torch.int64) * DENSE_MIN_FRACTION >= self.corpus_size).flatten()
         if cand.numel() == 0:
             return
-        if cand.numel() > MAX_DENSE_TERMS:
-            top = torch.topk(df_global[cand].to(torch.int64), MAX_DENSE_TERMS).indices
+        stride = (self.n_docs + 255) // 256 * 256
+        # the row budget depends only on global quantities, so every shard keeps the same terms
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rows_max = max(1, min(MAX_DENSE_TERMS, DENSE_TABLE_BYTES // max(256, -(-self.corpus_size // world))))
+        if cand.numel() > rows_max:
+            top = torch.topk(df_global[cand].to(torch.int64), rows_max).indices
             cand = cand[top].sort().values
         lo, hi = self.term_off[cand].tolist(), self.term_off[cand + 1].tolist()
         fits = torch.ones(cand.numel(), dtype=torch.int32, device=dev)
@@ -94,7 +100,6 @@ class SparseShard:
         cand = cand[fits.bool()]
         if cand.numel() == 0:
             return
-        stride = (self.n_docs + 255) // 256 * 256
         table = torch.zeros((cand.numel(), stride), dtype=torch.uint8, device=dev)
         for i, t in enumerate(cand.tolist()):
             a, b = int(self.term_off[t]), int(self.term_off[t + 1])

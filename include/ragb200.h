@@ -66,7 +66,7 @@ int ragb_bm25_build_norm(const int32_t* doc_len, int64_t n_docs, double avgdl, d
  * Queries are ragged lists of term ids q_terms[q_off[i] .. q_off[i+1]); every OCCURRENCE
  * contributes; ids outside [0, vocab) are out-of-vocabulary and contribute 0.
  * Optional dense tf table: dense_tf[r * dense_stride + d] (uint8, 0 = term absent) holds the
- * term frequencies of term dense_terms[r] for r < n_dense <= 64 (terms so frequent that a
+ * term frequencies of term dense_terms[r] (sorted ascending) for r < n_dense <= 1024 (terms so frequent that a
  * byte per document beats a posting list; every tf of such a term must be <= 255, and the
  * choice must be the same on every shard).  Their posting lists stay in the CSR but are not
  * read.  dense_stride is a multiple of 256, >= n_docs; n_dense = 0 disables the table.
