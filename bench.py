@@ -44,6 +44,9 @@ def parse_args():
     p.add_argument("--variant", type=int, default=int(os.environ.get("RAGB_MMA_VARIANT", "0")))
     p.add_argument("--cpu-sample-docs", type=int, default=20_000)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--workload", default="c3", choices=["c3", "c2"],
+                   help="c3 (default, headline): 10M passages, batch 1024, tcgen05 dense.  c2: BASELINE.json configs[1], "
+                        "1M passages, batch-1 GEMV + BM25 (sets --passages 1000000 --batch 1 unless given)")
     return p.parse_args()
 
 
@@ -314,6 +317,8 @@ def run_ours(args):
         bm25_avg = sum(bm25_ms) / len(bm25_ms)
         flops = 2.0 * args.batch * n_local * DIM
         achieved = flops / (dense_avg / 1000.0) / 1e12
+        gemv = args.batch <= 8
+        dense_bytes = n_local * DIM * 2.0 * (-(-args.batch // 4) if gemv else 1)   # GEMV re-reads the shard per group of 4 queries
         # realised BM25 postings of one batch: sum of document frequencies of the query terms (local shard)
         qt = batches[0].q_terms.to(torch.int64)
         ok = (qt >= 0) & (qt < engine.sparse.vocab)
@@ -324,7 +329,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"hybrid top-{args.k}: BM25 pool {args.pool} over CSR + exact dense pool {args.pool} "
-                                   f"(tcgen05 variant {args.variant}) + fusion + router rerank; {args.passages} passages x {DIM} "
+                                   f"({'bf16 GEMV' if args.batch <= 8 else 'tcgen05 variant ' + str(args.variant)}) + fusion + router rerank; {args.passages} passages x {DIM} "
                                    f"bf16 row-sharded over {world} GPU(s), batch {args.batch} queries x 8 terms",
                        "l2": "inputs exceed L2 (embedding shard %.1f GB, postings %.1f GB per GPU); 4 rotating query batches"
                              % (n_local * DIM * 2 / 1e9, engine.sparse.nnz * 6 / 1e9),
@@ -333,10 +338,15 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "dense_mma_kernel (+ stripe merge)", "achieved": achieved,
-                         "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                         "traffic": None, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
-                         "ms_per_launch": dense_avg, "flops_per_launch": flops},
+            "roofline": ({"bound": "hbm", "kernel": "gemv_topk_kernel (+ block merge)",
+                          "achieved": dense_bytes / (dense_avg / 1000.0) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                          "frac": dense_bytes / (dense_avg / 1000.0) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                          "peak_source": pk["source"] + " copy bandwidth", "ms_per_launch": dense_avg,
+                          "bytes_per_launch": dense_bytes} if gemv else
+                         {"bound": "tensor", "kernel": "dense_mma_kernel (+ stripe merge)", "achieved": achieved,
+                          "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
+                          "traffic": None, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
+                          "ms_per_launch": dense_avg, "flops_per_launch": flops}),
             "kernels": {"bm25_ms": bm25_avg, "bm25_postings_per_batch": sum_df,
                         "bm25_posting_gbs": sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9,
                         "bm25_frac_of_hbm_peak": sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9 / pk["hbm_gbs"],
@@ -354,6 +364,11 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    if a.workload == "c2":
+        if "--passages" not in sys.argv:
+            a.passages = 1_000_000
+        if "--batch" not in sys.argv:
+            a.batch = 1
     if a.impl == "reference":
         run_reference(a)
     else:
