@@ -25,8 +25,9 @@
 // Which terms use the table is decided from GLOBAL document frequencies, so every shard makes
 // the same choice and the fp32 accumulation order (table terms in query order, then list terms
 // in query order) does not depend on how the corpus is sharded.
-// The block-wide running top-k (topk.cuh) then filters the 8x256 scores: one barrier per range
-// in steady state.
+// Selection is warp-private too (WarpTopK in topk.cuh: threshold in a register, appends through a
+// ballot prefix, rare warp-level bitonic merge), so the main loop has no block barrier at all; the
+// per-warp lists of all stripes are merged by topk_merge_kernel.
 #include <climits>
 
 #include "common.cuh"
@@ -137,8 +138,10 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   sp += sizeof(int64_t) * BM_WARPS * mt;
   int64_t* s_end = reinterpret_cast<int64_t*>(sp) + warp * mt;
   sp += sizeof(int64_t) * BM_WARPS * mt;
-  uint64_t* s_keys = reinterpret_cast<uint64_t*>(sp);
-  if (!DENSE_OUT) sp += sizeof(uint64_t) * a.capacity;
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(sp) + warp * a.capacity;  // this warp's candidate keys
+  if (!DENSE_OUT) sp += sizeof(uint64_t) * a.capacity * BM_WARPS;
+  const uint8_t** s_drow = reinterpret_cast<const uint8_t**>(sp) + warp * mt;  // dense-table row of each dense term
+  sp += sizeof(uint8_t*) * BM_WARPS * mt;
   float* accw = reinterpret_cast<float*>(sp) + warp * BM_RANGE;
   sp += sizeof(float) * BM_WARPS * BM_RANGE;
   float* nrmw = reinterpret_cast<float*>(sp) + warp * BM_RANGE;
@@ -151,13 +154,8 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   sp += sizeof(int) * BM_WARPS * mt;
   int* s_tmp = reinterpret_cast<int*>(sp) + warp * mt;        // term ids while the cursors are placed
   sp += sizeof(int) * BM_WARPS * mt;
-  unsigned short* s_dslot = reinterpret_cast<unsigned short*>(sp) + warp * mt;  // dense-table row of each dense term
-  sp += sizeof(unsigned short) * BM_WARPS * mt;
   unsigned char* s_dense = sp + warp * mt;                    // chunks per pass class of each sparse term
 
-  __shared__ int s_count;
-  __shared__ uint64_t s_threshold;
-  __shared__ int s_pending[3];
   __shared__ int s_dterms[BM_MAX_DENSE];
 
   const int q = blockIdx.x;
@@ -169,13 +167,9 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   const int n_iters = static_cast<int>(sub_docs / BM_RANGE);
 
   for (int i = tid; i < a.n_dense; i += BM_THREADS) s_dterms[i] = a.dense_terms[i];
-  BlockTopK<BM_THREADS> tk;
-  if (!DENSE_OUT) {
-    if (tid < 3) s_pending[tid] = 0;
-    tk.init(s_keys, &s_count, &s_threshold, a.k, a.capacity, positive_floor_key());
-  } else {
-    __syncthreads();
-  }
+  WarpTopK tk;
+  if (!DENSE_OUT) tk.init(s_keys, a.k, a.capacity, positive_floor_key(), lane);
+  __syncthreads();
 
   // ---- split the query's terms: rows of the dense tf table vs posting lists -------------------
   const int qb = a.q_off[q];
@@ -202,7 +196,7 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
     const unsigned ms = __ballot_sync(0xffffffffu, live && slot < 0);
     if (live && slot >= 0) {
       const int o = nd + __popc(md & ((1u << lane) - 1));
-      s_dslot[o] = static_cast<unsigned short>(slot);
+      s_drow[o] = a.dense_tf + static_cast<int64_t>(slot) * a.dense_stride;
       s_dwgt[o] = w;
     }
     if (live && slot < 0) s_tmp[ns + __popc(ms & ((1u << lane) - 1))] = t;
@@ -283,7 +277,6 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   }
   __syncwarp();
 
-  int local_count = 0;  // replica of tk.count, identical in every thread
   const int j0 = lane * 8;  // the 8 documents of the range this lane owns outside the posting phase
   for (int it = 0; it < n_iters; ++it) {
     const int64_t d0l = w_begin + static_cast<int64_t>(it) * BM_RANGE;
@@ -313,7 +306,7 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
           w4[u] = 0.0f;
           if (i0 + u < nd) {
             w4[u] = s_dwgt[i0 + u];
-            tf8[u] = __ldg(reinterpret_cast<const uint2*>(a.dense_tf + static_cast<int64_t>(s_dslot[i0 + u]) * a.dense_stride + d0 + j0));
+            tf8[u] = __ldg(reinterpret_cast<const uint2*>(s_drow[i0 + u] + d0 + j0));
           }
         }
 #pragma unroll
@@ -384,53 +377,22 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
       for (int j = lane; j < cnt; j += 32) dst[j] = accw[j];
       __syncwarp();
     } else {
-      // ---- block-wide selection: count what beats the threshold, one barrier, then append
-      const uint64_t thr = s_threshold;
-      const float thr_score = key_score(thr);
-      const int32_t gid0 = static_cast<int32_t>(a.id_base + d0) + j0;
-      unsigned mask = 0;
+      // ---- warp-private selection: no barrier; in steady state 8 compares and one vote per range
+      bool hot = false;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (ac[j] >= thr_score && (j0 + j) < cnt && make_key(ac[j], gid0 + j) > thr) mask |= 1u << j;
-      int mine = __popc(mask);
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, s);
-      if (lane == 0 && mine) atomicAdd(&s_pending[it % 3], mine);
-      __syncthreads();
-      const int pending = s_pending[it % 3];
-      if (tid == 0) s_pending[(it + 2) % 3] = 0;
-      if (local_count + pending <= tk.room()) {
+      for (int j = 0; j < 8; ++j) hot |= (ac[j] >= tk.thr_score) && (j0 + j) < cnt;
+      if (__any_sync(0xffffffffu, hot)) {
+        const int32_t gid0 = static_cast<int32_t>(a.id_base + d0) + j0;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (mask & (1u << j)) {
-            const int slot = atomicAdd(&s_count, 1);
-            s_keys[a.k + slot] = make_key(ac[j], gid0 + j);
-          }
-        local_count += pending;
-      } else {
-        // slow path (first ranges, adversarial data): 2 documents per lane at a time
-        for (int ph = 0; ph < 4; ++ph) {
-          tk.reserve(BM_WARPS * 64);
-          const uint64_t t2 = s_threshold;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int j = ph * 2 + u;
-            float v = 0.0f;
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-              if (jj == j) v = ac[jj];
-            if ((j0 + j) < cnt) tk.offer(make_key(v, gid0 + j), t2);
-          }
-        }
-        __syncthreads();
-        local_count = s_count;
+          tk.offer((ac[j] >= tk.thr_score) && (j0 + j) < cnt, make_key(ac[j], gid0 + j), lane);
       }
     }
   }
   if (!DENSE_OUT) {
-    tk.finish();
-    uint64_t* dst = a.part_keys + (static_cast<int64_t>(q) * gridDim.y + blockIdx.y) * a.k;
-    for (int i = tid; i < a.k; i += BM_THREADS) dst[i] = s_keys[i];
+    tk.flush(lane);
+    uint64_t* dst = a.part_keys + ((static_cast<int64_t>(q) * gridDim.y + blockIdx.y) * BM_WARPS + warp) * a.k;
+    for (int i = lane; i < a.k; i += 32) dst[i] = s_keys[i];
   }
 }
 
@@ -522,9 +484,10 @@ static int bm25_stripes(int n_queries, int64_t n_docs, int64_t* stripe_docs_out)
 static size_t bm25_smem_bytes(int max_terms, int capacity, bool dense_out) {
   size_t b = 0;
   b += 2 * sizeof(int64_t) * BM_WARPS * max_terms;
-  if (!dense_out) b += sizeof(uint64_t) * capacity;
+  if (!dense_out) b += sizeof(uint64_t) * capacity * BM_WARPS;
+  b += sizeof(void*) * BM_WARPS * max_terms;
   b += 2 * sizeof(float) * BM_WARPS * BM_RANGE;
-  b += (2 * sizeof(float) + 2 * sizeof(int) + 3) * BM_WARPS * max_terms;
+  b += (2 * sizeof(float) + 2 * sizeof(int) + 1) * BM_WARPS * max_terms;
   return (b + 15) & ~static_cast<size_t>(15);
 }
 
@@ -591,7 +554,7 @@ size_t ragb_bm25_topk_workspace_bytes(int32_t n_queries, int64_t n_docs, int32_t
   if (n_queries <= 0 || n_docs <= 0 || k <= 0) return 0;
   int64_t stripe_docs;
   const int stripes = bm25_stripes(n_queries, n_docs, &stripe_docs);
-  return static_cast<size_t>(n_queries) * stripes * k * sizeof(uint64_t);
+  return static_cast<size_t>(n_queries) * stripes * BM_WARPS * k * sizeof(uint64_t);
 }
 
 int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
@@ -628,7 +591,7 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   a.dense_stride = dense_stride;
   a.n_dense = n_dense;
   a.k = k;
-  a.capacity = topk_capacity(k);
+  a.capacity = warp_topk_capacity(k);
   a.part_keys = static_cast<uint64_t*>(workspace);
   a.out_scores = nullptr;
   const int stripes = bm25_stripes(n_queries, n_docs, &a.stripe_docs);
@@ -636,7 +599,7 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   bm25_kernel<false><<<dim3(n_queries, stripes), BM_THREADS, smem, stream>>>(a);
   RAGB_AFTER_LAUNCH(1);
-  return launch_merge_keys(a.part_keys, n_queries, stripes, k, k, out_score, out_id, stream);
+  return launch_merge_keys(a.part_keys, n_queries, stripes * BM_WARPS, k, k, out_score, out_id, stream);
 }
 
 int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,

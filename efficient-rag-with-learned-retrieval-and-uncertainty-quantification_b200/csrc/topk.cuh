@@ -100,6 +100,80 @@ struct BlockTopK {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Warp-scope variant: same algorithm, no block barrier anywhere.  One warp owns keys[0..capacity)
+// in shared memory; the threshold and the append count live in (warp-uniform) registers.
+// ---------------------------------------------------------------------------------------------
+// Sort the live prefix, clear what falls behind the best k, return the new threshold.  Kept out
+// of line (and free of references) so the caller's state stays in registers.
+__device__ __noinline__ uint64_t warp_topk_flush(uint64_t* keys, int k, int count, uint64_t floor_key, int lane) {
+  __syncwarp();
+  int n = 2;
+  while (n < k + count) n <<= 1;
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = lane; i < (n >> 1); i += 32) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool descending = ((lo & size) == 0);
+        const uint64_t x = keys[lo], y = keys[hi];
+        if ((x < y) == descending) {
+          keys[lo] = y;
+          keys[hi] = x;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = k + lane; i < n; i += 32) keys[i] = 0ull;
+  const uint64_t kth = keys[k - 1];
+  __syncwarp();
+  return kth > floor_key ? kth : floor_key;
+}
+
+struct WarpTopK {
+  uint64_t* keys;
+  int k, capacity, count;
+  uint64_t floor_key, thr;
+  float thr_score;
+
+  __device__ __forceinline__ void init(uint64_t* keys_, int k_, int capacity_, uint64_t floor_key_, int lane) {
+    keys = keys_;
+    k = k_;
+    capacity = capacity_;
+    floor_key = floor_key_;
+    thr = floor_key_;
+    thr_score = key_score(floor_key_);
+    count = 0;
+    for (int i = lane; i < capacity; i += 32) keys[i] = 0ull;
+    __syncwarp();
+  }
+
+  // Warp-wide: fold the appended candidates into the sorted top-k and tighten the threshold.
+  __device__ __forceinline__ void flush(int lane) {
+    if (count == 0) return;
+    thr = warp_topk_flush(keys, k, count, floor_key, lane);
+    thr_score = key_score(thr);
+    count = 0;
+  }
+
+  // Warp-wide: every lane offers at most one key (valid says whether it has one).
+  __device__ __forceinline__ void offer(bool valid, uint64_t key, int lane) {
+    bool c = valid && key > thr;
+    unsigned m = __ballot_sync(0xffffffffu, c);
+    if (m == 0) return;
+    if (count + __popc(m) > capacity - k) {
+      flush(lane);
+      c = valid && key > thr;
+      m = __ballot_sync(0xffffffffu, c);
+    }
+    if (c) keys[k + count + __popc(m & ((1u << lane) - 1))] = key;
+    count += __popc(m);
+  }
+};
+
+__host__ __device__ constexpr int warp_topk_capacity(int k) { return k <= 100 ? 256 : 512; }
+
 // Capacity used for a given k (entries of 8 bytes).
 __host__ __device__ constexpr int topk_capacity(int k) { return k <= 64 ? 1024 : 2048; }
 
