@@ -106,7 +106,7 @@ struct BlockTopK {
 // ---------------------------------------------------------------------------------------------
 // Sort the live prefix, clear what falls behind the best k, return the new threshold.  Kept out
 // of line (and free of references) so the caller's state stays in registers.
-__device__ __noinline__ uint64_t warp_topk_flush(uint64_t* keys, int k, int count, uint64_t floor_key, int lane) {
+static __device__ __noinline__ uint64_t warp_topk_flush(uint64_t* keys, int k, int count, uint64_t floor_key, int lane) {
   __syncwarp();
   int n = 2;
   while (n < k + count) n <<= 1;
