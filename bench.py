@@ -41,7 +41,7 @@ def parse_args():
     p.add_argument("--batch", type=int, default=1024)
     p.add_argument("--k", type=int, default=10)
     p.add_argument("--pool", type=int, default=50)
-    p.add_argument("--variant", type=int, default=int(os.environ.get("RAGB_MMA_VARIANT", "0")))
+    p.add_argument("--variant", type=int, default=int(os.environ.get("RAGB_MMA_VARIANT", "2")))
     p.add_argument("--cpu-sample-docs", type=int, default=20_000)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--workload", default="c3", choices=["c3", "c2"],
@@ -338,20 +338,29 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": ({"bound": "hbm", "kernel": "gemv_topk_kernel (+ block merge)",
-                          "achieved": dense_bytes / (dense_avg / 1000.0) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                          "frac": dense_bytes / (dense_avg / 1000.0) / 1e9 / pk["hbm_gbs"], "traffic": None,
-                          "peak_source": pk["source"] + " copy bandwidth", "ms_per_launch": dense_avg,
-                          "bytes_per_launch": dense_bytes} if gemv else
-                         {"bound": "tensor", "kernel": "dense_mma_kernel (+ stripe merge)", "achieved": achieved,
-                          "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                          "traffic": None, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
-                          "ms_per_launch": dense_avg, "flops_per_launch": flops}),
+            "roofline": None, "roofline_secondary": None,
             "kernels": {"bm25_ms": bm25_avg, "bm25_postings_per_batch": sum_df,
                         "bm25_posting_gbs": sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9,
                         "bm25_frac_of_hbm_peak": sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9 / pk["hbm_gbs"],
                         "dense_ms": dense_avg, "other_ms": ms / args.steps - dense_avg - bm25_avg},
         }
+        dense_roof = ({"bound": "hbm", "kernel": "gemv_topk_kernel (+ block merge)",
+                       "achieved": dense_bytes / (dense_avg / 1000.0) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                       "frac": dense_bytes / (dense_avg / 1000.0) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                       "peak_source": pk["source"] + " copy bandwidth", "ms_per_launch": dense_avg,
+                       "bytes_per_launch": dense_bytes} if gemv else
+                      {"bound": "tensor", "kernel": "dense_mma_kernel (+ stripe merge)", "achieved": achieved,
+                       "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
+                       "traffic": None, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
+                       "ms_per_launch": dense_avg, "flops_per_launch": flops})
+        bm25_gbs = sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9
+        bm25_roof = {"bound": "hbm", "kernel": "bm25_kernel (+ stripe merge)", "achieved": bm25_gbs, "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": bm25_gbs / pk["hbm_gbs"], "traffic": None,
+                     "peak_source": pk["source"] + " copy bandwidth", "ms_per_launch": bm25_avg,
+                     "bytes_per_launch": sum_df * 6.0,
+                     "note": "algorithmic bytes = 6 B x sum of document frequencies of the batch's query terms"}
+        # the roofline object describes the kernel that takes most of the step
+        line["roofline"], line["roofline_secondary"] = (dense_roof, bm25_roof) if dense_avg >= bm25_avg else (bm25_roof, dense_roof)
         if not args.no_cpu_baseline and world == 1:
             _, full, desc = cpu_baseline(args, 6, 1)
             line["cpu_baseline"] = {"value": full, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}

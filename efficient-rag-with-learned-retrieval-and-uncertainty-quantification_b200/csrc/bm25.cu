@@ -27,7 +27,8 @@
 // in query order) does not depend on how the corpus is sharded.
 // Selection is warp-private too (WarpTopK in topk.cuh: threshold in a register, appends through a
 // ballot prefix, rare warp-level bitonic merge), so the main loop has no block barrier at all; the
-// per-warp lists of all stripes are merged by topk_merge_kernel.
+// 8 warp lists are folded once at the end of the block and the per-block lists of all stripes
+// are merged by topk_merge_kernel.
 #include <climits>
 
 #include "common.cuh"
@@ -390,9 +391,29 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
     }
   }
   if (!DENSE_OUT) {
+    // fold the 8 warp lists of this block into one (8k <= 2048 keys, one bitonic sort), so the
+    // cross-stripe merge sees one list per block
     tk.flush(lane);
-    uint64_t* dst = a.part_keys + ((static_cast<int64_t>(q) * gridDim.y + blockIdx.y) * BM_WARPS + warp) * a.k;
-    for (int i = lane; i < a.k; i += 32) dst[i] = s_keys[i];
+    __syncthreads();
+    uint64_t* all_keys = s_keys - warp * a.capacity;  // [BM_WARPS][capacity], each sorted in its first k slots
+    int n = 2;
+    while (n < BM_WARPS * a.k) n <<= 1;               // <= BM_WARPS * capacity because k <= capacity / 2
+    uint64_t mine[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = r * BM_THREADS + tid;
+      mine[r] = e < BM_WARPS * a.k ? all_keys[(e / a.k) * a.capacity + (e % a.k)] : 0ull;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = r * BM_THREADS + tid;
+      if (e < n) all_keys[e] = mine[r];
+    }
+    __syncthreads();
+    bitonic_sort_desc<BM_THREADS>(all_keys, n);
+    uint64_t* dst = a.part_keys + (static_cast<int64_t>(q) * gridDim.y + blockIdx.y) * a.k;
+    for (int i = tid; i < a.k; i += BM_THREADS) dst[i] = all_keys[i];
   }
 }
 
@@ -554,7 +575,7 @@ size_t ragb_bm25_topk_workspace_bytes(int32_t n_queries, int64_t n_docs, int32_t
   if (n_queries <= 0 || n_docs <= 0 || k <= 0) return 0;
   int64_t stripe_docs;
   const int stripes = bm25_stripes(n_queries, n_docs, &stripe_docs);
-  return static_cast<size_t>(n_queries) * stripes * BM_WARPS * k * sizeof(uint64_t);
+  return static_cast<size_t>(n_queries) * stripes * k * sizeof(uint64_t);
 }
 
 int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
@@ -599,7 +620,7 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   bm25_kernel<false><<<dim3(n_queries, stripes), BM_THREADS, smem, stream>>>(a);
   RAGB_AFTER_LAUNCH(1);
-  return launch_merge_keys(a.part_keys, n_queries, stripes * BM_WARPS, k, k, out_score, out_id, stream);
+  return launch_merge_keys(a.part_keys, n_queries, stripes, k, k, out_score, out_id, stream);
 }
 
 int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,

@@ -25,6 +25,8 @@
 // variant 1 (TS): the query slab [128 x dim] is stored ONCE into TMEM (dim/2 columns of
 //   packed bf16 pairs) and used as the A operand from there; only passages stream through
 //   shared memory, which halves the L2 -> SM traffic per flop.  Needs dim <= 768.
+// variant 2: like 0 with 256-passage tiles (N = 256 per tcgen05.mma, all 512 TMEM columns as two
+//   accumulators): 25% less L2 -> SM traffic per flop, fewer pipeline stages.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
   const int tile_end = min(a.n_tiles, tile_begin + a.tiles_per_group);
   const int n_kb = a.dim / MM_BK;
   const int a_cols = A_IN_TMEM ? a.dim / 2 : 0;  // TMEM columns holding the packed query slab
-  const uint32_t tmem_cols = A_IN_TMEM ? 512u : (2 * BN <= 32 ? 32u : (2 * BN <= 64 ? 64u : (2 * BN <= 128 ? 128u : 256u)));
+  const uint32_t tmem_cols = A_IN_TMEM ? 512u : (2 * BN <= 32 ? 32u : (2 * BN <= 64 ? 64u : (2 * BN <= 128 ? 128u : (2 * BN <= 256 ? 256u : 512u))));
 
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -533,8 +535,8 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
   RAGB_REQUIRE(dim >= MM_BK && dim % MM_BK == 0, RAGB_EINVAL, "ragb_dense_mma_topk: dim=%d must be a multiple of %d", dim,
                MM_BK);
   RAGB_REQUIRE(k > 0 && k <= 100, RAGB_ELIMIT, "ragb_dense_mma_topk: k=%d outside [1,100]", k);
-  RAGB_REQUIRE(variant == 0 || variant == 1, RAGB_EINVAL, "ragb_dense_mma_topk: variant must be 0 or 1");
-  RAGB_REQUIRE(variant == 0 || dim <= 768, RAGB_ELIMIT, "ragb_dense_mma_topk: variant 1 keeps the query slab in TMEM and needs dim <= 768");
+  RAGB_REQUIRE(variant >= 0 && variant <= 2, RAGB_EINVAL, "ragb_dense_mma_topk: variant must be 0, 1 or 2");
+  RAGB_REQUIRE(variant != 1 || dim <= 768, RAGB_ELIMIT, "ragb_dense_mma_topk: variant 1 keeps the query slab in TMEM and needs dim <= 768");
   RAGB_REQUIRE(id_base >= 0 && id_base + n_rows < (1ll << 31), RAGB_ELIMIT, "ragb_dense_mma_topk: ids must fit int32");
   RAGB_REQUIRE(workspace_bytes >= ragb_dense_mma_workspace_bytes(n_queries, k), RAGB_ENOSPC,
                "ragb_dense_mma_topk: workspace too small");
@@ -547,10 +549,14 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
     if (k <= 16) rc = launch_mma<128, false, 1>(RAGB_MMA_ARGS);
     else if (k <= 50) rc = launch_mma<128, false, 2>(RAGB_MMA_ARGS);
     else rc = launch_mma<128, false, 4>(RAGB_MMA_ARGS);
-  } else {
+  } else if (variant == 1) {
     if (k <= 16) rc = launch_mma<64, true, 1>(RAGB_MMA_ARGS);
     else if (k <= 50) rc = launch_mma<64, true, 2>(RAGB_MMA_ARGS);
     else rc = launch_mma<64, true, 4>(RAGB_MMA_ARGS);
+  } else {
+    if (k <= 16) rc = launch_mma<256, false, 1>(RAGB_MMA_ARGS);
+    else if (k <= 50) rc = launch_mma<256, false, 2>(RAGB_MMA_ARGS);
+    else rc = launch_mma<256, false, 4>(RAGB_MMA_ARGS);
   }
 #undef RAGB_MMA_ARGS
   if (rc != RAGB_OK) return rc;
