@@ -109,3 +109,34 @@ class HybridEngine:
             bs, bi = ops.topk_merge(gs[:, :, 0].contiguous(), gi[:, :, 0].contiguous(), pool)
             ds, di = ops.topk_merge(gs[:, :, 1].contiguous(), gi[:, :, 1].contiguous(), pool)
         return ops.hybrid_fuse_topk(bs, bi, ds, di, k)
+
+    # ---- full-fusion mode ----------------------------------------------------------------
+    def full_fusion_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, router, k: int = 10,
+                         query_chunk: int = 64):
+        """Gate evaluated for EVERY (query, passage) pair on the true scores ("full-fusion").
+
+        Oracle: ``RetrievalRouter.hybrid_rerank(bm25_full[B,N], dense_full[B,N], k)`` (router.py:179-202).
+        Un-fused form: the [chunk, N_local] score matrices are materialised (BM25 get_scores kernel,
+        dense score kernel), gated and reduced per chunk of queries.  The router must be in
+        running-statistics mode: call-wide statistics over [B, N] would need a global reduction
+        first and are refused here.  -> (fused score [B,k], global id int32 [B,k]).
+        """
+        if not getattr(router, "stats_initialized", False):
+            raise ValueError("full-fusion mode needs router.stats_initialized = True (running statistics)")
+        w1, b1, w2, b2, stats = router._weights()
+        n_q = q_emb.shape[0]
+        out_s, out_i = [], []
+        q_off_host = q_off.tolist()
+        for lo in range(0, n_q, query_chunk):
+            hi = min(n_q, lo + query_chunk)
+            t0, t1 = q_off_host[lo], q_off_host[hi]
+            sub_terms = q_terms[t0:t1] if t1 > t0 else q_terms[:1]
+            sub_off = (q_off[lo:hi + 1] - t0).contiguous()
+            bm = self.sparse.scores(sub_terms.contiguous(), sub_off, max_terms)
+            de = ops.dense_scores(self.passages, q_emb[lo:hi].contiguous())
+            _, fused = ops.router_forward(bm, de, w1, b1, w2, b2, stats, 1)
+            val, idx = ops.topk_rows(fused, min(k, fused.shape[1]))
+            out_s.append(val)
+            out_i.append(torch.where(idx >= 0, idx + self.id_base, idx))
+        score, ids = torch.cat(out_s), torch.cat(out_i)
+        return self._merge(score, ids, score.shape[1])

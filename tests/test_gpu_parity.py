@@ -309,6 +309,33 @@ def test_hybrid_engine_end_to_end_c1(rq, dev, n_q):
     assert (di[:, 0].cpu() == qb.source_rows.cpu().to(torch.int32)).float().mean() > 0.95
 
 
+def test_full_fusion_mode_c1(rq, dev):
+    """Config C1 in full-fusion mode: gate on every (query, passage) pair, oracle = hybrid_rerank on [B, N]."""
+    from rag_uq_b200 import synth
+    n, dim, k, n_q = 10_000, 768, 10, 64
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    passages = synth.passage_embeddings(0, n, dim, dev)
+    engine = rq.HybridEngine(rq.build_shard(doc_off, doc_tok, vocab).finalize(), passages)
+    qb = synth.make_queries(n_q, n, dim, cdf, dev)
+    torch.manual_seed(7)
+    router = rq.RetrievalRouter().to(dev).eval()
+    with pytest.raises(ValueError):
+        engine.full_fusion_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k)
+    router.bm25_mean.fill_(6.0); router.bm25_std.fill_(5.0); router.dense_mean.fill_(0.0); router.dense_std.fill_(0.05)
+    router.stats_initialized = True
+    with torch.no_grad():
+        score, ids = engine.full_fusion_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, query_chunk=24)
+    okapi = bm25_okapi.OkapiCsr(doc_off.cpu().numpy(), doc_tok.cpu().numpy(), vocab)
+    terms = qb.q_terms.view(n_q, -1).cpu().numpy()
+    bm = torch.tensor(np.stack([okapi.get_scores(terms[q]) for q in range(n_q)]), dtype=torch.float32)
+    de = torch.tensor(dense_fusion.dense_scores(passages.float().cpu().numpy(), qb.q_emb.float().cpu().numpy()),
+                      dtype=torch.float32)
+    state = {key: v.detach().cpu() for key, v in router.state_dict().items()}
+    want_s, want_i = router_oracle.hybrid_rerank(bm, de, state, True, k)
+    torch.testing.assert_close(score.cpu(), want_s, rtol=2e-5, atol=2e-5)
+    assert (ids.cpu().long() == want_i).float().mean() > 0.99
+
+
 def test_row_sharded_engine_equals_single_engine(rq, dev):
     """Emulate G = 2 on one GPU: local pools per shard, merged exactly as the all-gather path merges."""
     from rag_uq_b200 import synth
