@@ -316,8 +316,8 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const unsigned word = j < 4 ? tf8[u].x : tf8[u].y;
-              const unsigned tfb = (word >> (8 * (j & 3))) & 0xffu;
-              const float f = __uint_as_float(0x4B000000u | tfb) - 8388608.0f;  // exact small-int -> float
+              // one PRMT builds 0x4B0000tt = 8388608.0f + tf; subtracting 2^23 gives tf exactly
+              const float f = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (j & 3))) - 8388608.0f;
               ac[j] = fmaf(w4[u], f * fast_rcp(f + nr[j]), ac[j]);
             }
           }
