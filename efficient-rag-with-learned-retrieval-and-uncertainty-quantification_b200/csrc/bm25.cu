@@ -296,32 +296,23 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) nr[j] = (j0 + j) < cnt ? __ldg(a.norm + d0 + j0 + j) : 1.0f;
     }
-    // ---- dense-table terms: 8 tf bytes per lane per term, accumulators stay in registers
-    if (cnt > 0) {
-      for (int i0 = 0; i0 < nd; i0 += 4) {
-        uint2 tf8[4];
-        float w4[4];
+    // ---- dense-table terms: 8 tf bytes per lane per term, accumulators stay in registers.
+    // One term at a time with the next term's bytes already in flight.
+    if (cnt > 0 && nd > 0) {
+      const int64_t off = static_cast<int64_t>(d0) + j0;
+      uint2 cur = __ldg(reinterpret_cast<const uint2*>(s_drow[0] + off));
+      for (int i = 0; i < nd; ++i) {
+        const float w = s_dwgt[i];
+        uint2 nxt = make_uint2(0u, 0u);
+        if (i + 1 < nd) nxt = __ldg(reinterpret_cast<const uint2*>(s_drow[i + 1] + off));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          tf8[u] = make_uint2(0u, 0u);
-          w4[u] = 0.0f;
-          if (i0 + u < nd) {
-            w4[u] = s_dwgt[i0 + u];
-            tf8[u] = __ldg(reinterpret_cast<const uint2*>(s_drow[i0 + u] + d0 + j0));
-          }
+        for (int j = 0; j < 8; ++j) {
+          const unsigned word = j < 4 ? cur.x : cur.y;
+          // one PRMT builds 0x4B0000tt = 8388608.0f + tf; subtracting 2^23 gives tf exactly
+          const float f = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (j & 3))) - 8388608.0f;
+          ac[j] = fmaf(w, f * fast_rcp(f + nr[j]), ac[j]);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (i0 + u < nd) {  // warp-uniform
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const unsigned word = j < 4 ? tf8[u].x : tf8[u].y;
-              // one PRMT builds 0x4B0000tt = 8388608.0f + tf; subtracting 2^23 gives tf exactly
-              const float f = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (j & 3))) - 8388608.0f;
-              ac[j] = fmaf(w4[u], f * fast_rcp(f + nr[j]), ac[j]);
-            }
-          }
-        }
+        cur = nxt;
       }
     }
     // ---- posting-list terms: shared-memory accumulator, only when some list reaches into the range
