@@ -11,12 +11,12 @@ from .confidence import ConfidenceResult, MCDropoutConfidence, RouterUncertainty
 from .engine import HybridEngine, gather_candidates, global_bm25_statistics, shard_rows
 from .retrieval import BM25Index, DenseIndex, Document, HybridRetriever, RetrievalResult, StreamingIndex
 from .router import RetrievalRouter, RouterConfig
-from .sparse import SparseShard, build_shard, build_shard_blocked
+from .sparse import SegmentedIndex, SparseShard, build_shard, build_shard_blocked
 
 __version__ = "0.1.0"
 __all__ = [
     "RetrievalRouter", "RouterConfig", "MCDropoutConfidence", "ConfidenceResult", "RouterUncertainty",
     "HybridRetriever", "StreamingIndex", "BM25Index", "DenseIndex", "Document", "RetrievalResult",
-    "HybridEngine", "SparseShard", "build_shard", "build_shard_blocked", "shard_rows", "gather_candidates",
+    "HybridEngine", "SparseShard", "SegmentedIndex", "build_shard", "build_shard_blocked", "shard_rows", "gather_candidates",
     "global_bm25_statistics",
 ]

@@ -30,7 +30,7 @@ import torch
 
 from . import _lib
 from .engine import HybridEngine
-from .sparse import SparseShard, build_shard
+from .sparse import SegmentedIndex
 
 logger = logging.getLogger(__name__)
 
@@ -82,7 +82,8 @@ class BM25Index:
         self.tokenized_corpus: List[List[str]] = []
         self.vocab: Dict[str, int] = {}
         self._doc_terms: List[np.ndarray] = []
-        self.bm25: Optional[SparseShard] = None   # the reference keeps its BM25Okapi here
+        self.bm25: Optional[SegmentedIndex] = None   # the reference keeps its BM25Okapi here
+        self._indexed = 0                             # documents already in a GPU segment
         self._stale = False
         if self.persist_path and self.persist_path.exists():
             self._load()
@@ -113,15 +114,19 @@ class BM25Index:
         return added
 
     def _ensure_built(self) -> None:
+        """Index the documents added since the last search as ONE new segment (incremental ingest)."""
         if not self._stale and self.bm25 is not None:
             return
         dev = torch.device(self.device) if self.device is not None else _default_device()
-        lens = np.fromiter((len(t) for t in self._doc_terms), dtype=np.int64, count=len(self._doc_terms))
+        fresh = self._doc_terms[self._indexed:]
+        lens = np.fromiter((len(t) for t in fresh), dtype=np.int64, count=len(fresh))
         doc_off = np.concatenate([[0], np.cumsum(lens)])
-        doc_tok = np.concatenate(self._doc_terms) if len(self._doc_terms) else np.zeros(0, np.int32)
-        shard = build_shard(torch.from_numpy(doc_off).to(dev), torch.from_numpy(doc_tok).to(dev),
-                            vocab=max(len(self.vocab), 1), k1=self.k1, b=self.b)
-        self.bm25 = shard.finalize()
+        doc_tok = np.concatenate(fresh) if len(fresh) else np.zeros(0, np.int32)
+        if self.bm25 is None:
+            self.bm25 = SegmentedIndex(k1=self.k1, b=self.b)
+        self.bm25.append(torch.from_numpy(doc_off).to(dev), torch.from_numpy(doc_tok).to(dev),
+                         vocab=max(len(self.vocab), 1))
+        self._indexed = len(self._doc_terms)
         self._stale = False
 
     def encode_queries(self, queries: Sequence[str]):
@@ -172,7 +177,7 @@ class BM25Index:
         self.doc_ids = payload["doc_ids"]
         self.tokenized_corpus = payload["tokenized_corpus"]
         self.k1, self.b = payload["k1"], payload["b"]
-        self.vocab, self._doc_terms = {}, []
+        self.vocab, self._doc_terms, self._indexed, self.bm25 = {}, [], 0, None
         for tokens in self.tokenized_corpus:
             self._doc_terms.append(self._intern(tokens))
         self._stale = bool(self.tokenized_corpus)

@@ -76,12 +76,16 @@ class SparseShard:
         a byte", so all shards pick the same terms and accumulate in the same order.
         """
         dev = self.post_doc.device
+        keep = (self.dense_tf, self.dense_terms) if (self.dense_terms is not None and self.dense_terms.numel()) else None
         empty_u8 = torch.empty(0, dtype=torch.uint8, device=dev)
         self.dense_tf, self.dense_terms = empty_u8, torch.empty(0, dtype=torch.int32, device=dev)
         if not self.use_dense_table or self.n_docs == 0:
             return
         cand = torch.nonzero(df_global.to(torch.int64) * DENSE_MIN_FRACTION >= self.corpus_size).flatten()
         if cand.numel() == 0:
+            return
+        if keep is not None and keep[1].numel() == cand.numel() and torch.equal(keep[1].to(torch.int64), cand):
+            self.dense_tf, self.dense_terms = keep     # same terms as before: the rows are still right
             return
         stride = (self.n_docs + 255) // 256 * 256
         # the row budget depends only on global quantities, so every shard keeps the same terms
@@ -178,3 +182,97 @@ def build_shard_blocked(block_iter, n_docs: int, vocab: int, device, id_base: in
         del term, doc, tf, counts, lens, t64, dst
     return SparseShard(term_off, post_doc, post_tf, doc_len, total_counts.to(torch.int32), n_docs=n_docs, vocab=vocab,
                        id_base=id_base, k1=k1, b=b, epsilon=epsilon)
+
+
+def grow_vocab(shard: SparseShard, vocab: int) -> None:
+    """New terms have no postings in an existing segment: extend its directory in O(V)."""
+    extra = vocab - shard.vocab
+    if extra <= 0:
+        return
+    dev = shard.term_off.device
+    shard.term_off = torch.cat([shard.term_off, shard.term_off[-1:].expand(extra)]).contiguous()
+    shard.df = torch.cat([shard.df, torch.zeros(extra, dtype=shard.df.dtype, device=dev)])
+    shard.vocab = vocab
+
+
+def merge_adjacent(a: SparseShard, b: SparseShard) -> SparseShard:
+    """Concatenate two segments of consecutive rows (a first) into one term-major CSR."""
+    assert a.vocab == b.vocab and b.id_base == a.id_base + a.n_docs
+    dev = a.post_doc.device
+    ca, cb = a.term_off[1:] - a.term_off[:-1], b.term_off[1:] - b.term_off[:-1]
+    term_off = torch.zeros(a.vocab + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(ca + cb, 0, out=term_off[1:])
+    post_doc = torch.empty(a.nnz + b.nnz, dtype=torch.int32, device=dev)
+    post_tf = torch.empty(a.nnz + b.nnz, dtype=torch.int16, device=dev)
+    terms = torch.arange(a.vocab, device=dev)
+    ta, tb = torch.repeat_interleave(terms, ca), torch.repeat_interleave(terms, cb)
+    dst_a = term_off[:-1][ta] + (torch.arange(a.nnz, device=dev) - a.term_off[:-1][ta])
+    dst_b = term_off[:-1][tb] + ca[tb] + (torch.arange(b.nnz, device=dev) - b.term_off[:-1][tb])
+    post_doc[dst_a], post_tf[dst_a] = a.post_doc, a.post_tf
+    post_doc[dst_b], post_tf[dst_b] = b.post_doc + a.n_docs, b.post_tf
+    return SparseShard(term_off, post_doc, post_tf, torch.cat([a.doc_len, b.doc_len]), a.df + b.df,
+                       n_docs=a.n_docs + b.n_docs, vocab=a.vocab, id_base=a.id_base, k1=a.k1, b=a.b, epsilon=a.epsilon,
+                       use_dense_table=a.use_dense_table)
+
+
+class SegmentedIndex:
+    """Append-only BM25 index: every ``append`` builds a CSR segment for the NEW documents only.
+
+    "Next" row N1 of SURVEY.md section 8f.  The reference rebuilds ``BM25Okapi`` over the whole
+    corpus on every ``add_documents`` (rag_uq/streaming_index.py:140-142) because every idf and
+    the average length change; here the postings of old documents never move: an append costs
+    O(new tokens) for the segment plus O(V + N) to refresh idf / norm on all segments (and the
+    dense tf rows only when the set of frequent terms changes).  Segments are row shards on one
+    GPU: each is scored with the global statistics and the per-segment lists are merged, exactly
+    like the multi-GPU path.  More than ``max_segments`` segments trigger a merge of the two
+    smallest neighbours.
+    """
+
+    def __init__(self, k1: float = 1.5, b: float = 0.75, epsilon: float = 0.25, max_segments: int = 8):
+        self.k1, self.b, self.epsilon, self.max_segments = k1, b, epsilon, max_segments
+        self.segments: List[SparseShard] = []
+        self.vocab = 0
+        self.n_docs = 0
+        self.total_len = 0
+        self.use_dense_table = True
+
+    def append(self, doc_off: Tensor, doc_tok: Tensor, vocab: int) -> None:
+        seg = build_shard(doc_off, doc_tok, vocab, id_base=self.n_docs, k1=self.k1, b=self.b, epsilon=self.epsilon)
+        seg.use_dense_table = self.use_dense_table
+        self.vocab = max(self.vocab, vocab)
+        self.segments.append(seg)
+        self.n_docs += seg.n_docs
+        self.total_len += int(seg.doc_len.sum())
+        while len(self.segments) > self.max_segments:
+            sizes = [self.segments[i].n_docs + self.segments[i + 1].n_docs for i in range(len(self.segments) - 1)]
+            i = sizes.index(min(sizes))
+            for s in (self.segments[i], self.segments[i + 1]):
+                grow_vocab(s, self.vocab)
+            self.segments[i:i + 2] = [merge_adjacent(self.segments[i], self.segments[i + 1])]
+        self.refresh()
+
+    def refresh(self) -> None:
+        for s in self.segments:
+            grow_vocab(s, self.vocab)
+        df = self.segments[0].df.clone()
+        for s in self.segments[1:]:
+            df += s.df
+        for s in self.segments:
+            s.finalize(df, self.n_docs, self.total_len)
+
+    @property
+    def post_doc(self) -> Tensor:   # device probe used by callers
+        return self.segments[0].post_doc
+
+    @property
+    def idf(self) -> Tensor:
+        return self.segments[0].idf
+
+    def score_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int):
+        parts = [s.score_topk(q_terms, q_off, max_terms, k) for s in self.segments]
+        if len(parts) == 1:
+            return parts[0]
+        return ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1), k)
+
+    def scores(self, q_terms: Tensor, q_off: Tensor, max_terms: int) -> Tensor:
+        return torch.cat([s.scores(q_terms, q_off, max_terms) for s in self.segments], dim=1)

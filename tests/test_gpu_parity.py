@@ -588,6 +588,40 @@ def test_hybrid_retriever_dropin(rq, dev, tmp_path):
         assert set(pickle.load(fh)) == {"documents", "doc_ids", "tokenized_corpus", "k1", "b"}
 
 
+def test_incremental_ingest_equals_full_rebuild(rq, dev):
+    """N1: documents added in batches (one GPU segment per batch, statistics refreshed, segments merged
+    beyond 8) score exactly like the reference semantics, which rebuild BM25Okapi over everything on every add."""
+    rng = np.random.default_rng(3)
+    words = [f"t{i}" for i in range(400)]
+    probs = 1.0 / np.arange(1, 401)
+    probs /= probs.sum()
+    texts = [" ".join(rng.choice(words, size=rng.integers(8, 60), p=probs)) for _ in range(1300)]
+    docs = [rq.Document(id=f"d{i}", text=t) for i, t in enumerate(texts)]
+    index = rq.BM25Index()
+    sizes = [1, 7, 300, 5, 120, 64, 33, 250, 11, 200, 309]          # 11 batches -> exercises the merge
+    queries = ["t0 t1 t17 t250", "t399 t3 t3", "t5", "unknown t2 t390 t391"]
+    done = 0
+    for n in sizes:
+        index.add_documents(docs[done:done + n])
+        done += n
+        okapi = bm25_okapi.OkapiLiteral([bm25_okapi.tokenize(t) for t in texts[:done]])
+        for q in queries:
+            want = bm25_okapi.index_search(okapi.get_scores(bm25_okapi.tokenize(q)), 20)
+            got = index.search(q, top_k=20)
+            assert len(got) == len(want), (done, q)
+            for (gid, gs), (wi, ws) in zip(got, want):
+                assert gs == pytest.approx(ws, rel=1e-5), (done, q)
+                assert gid == f"d{wi}" or okapi.get_scores(bm25_okapi.tokenize(q))[int(gid[1:])] == pytest.approx(ws, rel=2e-6)
+        assert len(index.bm25.segments) <= 8
+    assert done == 1300 and index.bm25.n_docs == 1300
+    fresh = rq.BM25Index()
+    fresh.add_documents(docs)
+    for q in queries:
+        a, b = index.search(q, 50), fresh.search(q, 50)
+        assert [d for d, _ in a] == [d for d, _ in b]
+        np.testing.assert_allclose([s for _, s in a], [s for _, s in b], rtol=2e-6)
+
+
 def test_error_behaviour(rq, dev):
     with pytest.raises(ValueError):
         rq.ops.topk_rows(torch.zeros(2, 10000, device=dev), 1000)           # k beyond RAGB_MAX_TOPK on a long row
