@@ -12,8 +12,8 @@
 //   warps 2..5  epilogue: tcgen05.ld of the accumulator; THREAD r OWNS QUERY r of the
 //               slab for the whole kernel, so its admission threshold is a register and
 //               the common case is "32 scores, one max, one compare".  Survivors are
-//               appended to the thread's private list in shared memory; a full list is
-//               compacted to its best k by the whole warp (shuffle bitonic sort).
+//               appended to the thread's private list (global workspace, L2-resident); a full
+//               list is compacted to its best k by the whole warp (shuffle bitonic sort).
 //   The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the
 //   MMAs of tile i+1.
 //
@@ -28,6 +28,8 @@
 // variant 2: like 0 with 256-passage tiles (N = 256 per tcgen05.mma, all 512 TMEM columns as two
 //   accumulators): 25% less L2 -> SM traffic per flop, fewer pipeline stages.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -56,6 +58,8 @@ struct MmaArgs {
   int n_stages;
   uint64_t* part_keys;  // [n_queries, n_groups, k]
   int* progress;        // [n_groups, n_slabs] tiles issued so far (soft pacing between the slabs of a group)
+  uint64_t* lists;      // [blocks, 128, list capacity + 1] per-thread candidate lists
+  int stage_limit;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -218,7 +222,8 @@ __device__ __noinline__ ListState compact_lists(uint64_t* warp_lists, unsigned l
     uint64_t* list = warp_lists + src * STRIDE;
     uint64_t v[KPL];
 #pragma unroll
-    for (int r = 0; r < KPL; ++r) v[r] = (r * 32 + lane) < n_src ? list[r * 32 + lane] : 0ull;
+    for (int r = 0; r < KPL; ++r)
+      v[r] = (r * 32 + lane) < n_src ? __ldcg(reinterpret_cast<const unsigned long long*>(list + r * 32 + lane)) : 0ull;
     warp_sort_desc<KPL>(v, lane);
 #pragma unroll
     for (int r = 0; r < KPL; ++r) list[r * 32 + lane] = v[r];
@@ -260,7 +265,9 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* stages = base;
-  uint64_t* lists = reinterpret_cast<uint64_t*>(base + static_cast<size_t>(a.n_stages) * STAGE_BYTES);
+  // candidate lists live in the caller's workspace (L2-resident, touched ~once per thousand scores), so
+  // shared memory holds only the operand ring and blocks of other kernels can share the SM
+  uint64_t* lists = a.lists + static_cast<size_t>(blockIdx.x) * MM_BM * (32 * KPL + 1);
   __shared__ __align__(8) uint64_t bar_full[MM_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[MM_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
     const int cnt = st.cnt;
     if (query < a.n_queries) {
       uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.n_groups + group) * a.k;
-      for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? my_list[j] : 0ull;
+      for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? __ldcg(reinterpret_cast<const unsigned long long*>(my_list + j)) : 0ull;
     }
   }
 
@@ -491,7 +498,8 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int dim, in
 
 template <int BN, bool A_IN_TMEM, int KPL>
 static int launch_mma(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
-                      int64_t id_base, uint64_t* part, int* progress, int* n_groups_out, cudaStream_t stream) {
+                      int64_t id_base, uint64_t* part, int* progress, uint64_t* lists, int stage_limit,
+                      int* n_groups_out, cudaStream_t stream) {
   constexpr int STAGE_BYTES = (A_IN_TMEM ? 0 : MM_A_STAGE_BYTES) + BN * MM_BK * 2;
   CUtensorMap map_q, map_e;
   int rc = make_map(&map_q, queries, n_queries, dim, MM_BM);
@@ -517,19 +525,27 @@ static int launch_mma(const void* passages, int64_t n_rows, int dim, const void*
   a.n_groups = (a.n_tiles + a.tiles_per_group - 1) / a.tiles_per_group;
   a.part_keys = part;
   a.progress = progress;
+  a.lists = lists;
   RAGB_CUDA(cudaMemsetAsync(progress, 0, MM_PROGRESS_BYTES, stream));
-  const size_t list_bytes = static_cast<size_t>(32 * KPL + 1) * MM_BM * sizeof(uint64_t);
-  int stages = static_cast<int>((MM_MAX_SMEM - 1024 - 256 - list_bytes) / STAGE_BYTES);
+  // Ring depth: deep enough to cover TMA latency, shallow enough (<= 144 KB) that two blocks of the
+  // BM25 kernel fit on the same SM when the two run concurrently on different streams.
+  int stages = static_cast<int>((MM_MAX_SMEM - 1024 - 256) / STAGE_BYTES);
+  const int cap = stage_limit > 0 ? stage_limit : (144 * 1024) / STAGE_BYTES;
+  if (stages > cap) stages = cap;
   if (stages > MM_MAX_STAGES) stages = MM_MAX_STAGES;
-  RAGB_REQUIRE(stages >= 2, RAGB_ELIMIT, "ragb_dense_mma_topk: k=%d leaves no room for a 2-stage pipeline", k);
   a.n_stages = stages;
-  const size_t smem = 1024 + static_cast<size_t>(stages) * STAGE_BYTES + list_bytes;
+  const size_t smem = 1024 + static_cast<size_t>(stages) * STAGE_BYTES;
   RAGB_CUDA(cudaFuncSetAttribute(dense_mma_kernel<BN, A_IN_TMEM, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   dense_mma_kernel<BN, A_IN_TMEM, KPL><<<a.n_slabs * a.n_groups, MM_THREADS, smem, stream>>>(map_q, map_e, a);
   RAGB_AFTER_LAUNCH(1);
   *n_groups_out = a.n_groups;
   return RAGB_OK;
+}
+
+static size_t mma_list_bytes(int k) {
+  const int cap = k <= 16 ? 32 : (k <= 50 ? 64 : 128);
+  return static_cast<size_t>(148) * MM_BM * (cap + 1) * sizeof(uint64_t);
 }
 
 }  // namespace ragb
@@ -540,7 +556,7 @@ extern "C" {
 
 size_t ragb_dense_mma_workspace_bytes(int32_t n_queries, int32_t k) {
   if (n_queries <= 0 || k <= 0) return 0;
-  return MM_PROGRESS_BYTES + static_cast<size_t>(n_queries) * 148 * k * sizeof(uint64_t);
+  return MM_PROGRESS_BYTES + mma_list_bytes(k) + static_cast<size_t>(n_queries) * 148 * k * sizeof(uint64_t);
 }
 
 int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
@@ -562,11 +578,16 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
   RAGB_REQUIRE(workspace_bytes >= ragb_dense_mma_workspace_bytes(n_queries, k), RAGB_ENOSPC,
                "ragb_dense_mma_topk: workspace too small");
   int* progress = static_cast<int*>(workspace);
-  uint64_t* part = reinterpret_cast<uint64_t*>(static_cast<unsigned char*>(workspace) + MM_PROGRESS_BYTES);
+  uint64_t* lists = reinterpret_cast<uint64_t*>(static_cast<unsigned char*>(workspace) + MM_PROGRESS_BYTES);
+  uint64_t* part = reinterpret_cast<uint64_t*>(static_cast<unsigned char*>(workspace) + MM_PROGRESS_BYTES + mma_list_bytes(k));
+  static const int stage_limit = [] {
+    const char* e = getenv("RAGB_MMA_STAGES");  // tuning aid only
+    return e ? atoi(e) : 0;
+  }();
   int n_groups = 0;
   int rc;
   // list capacity per query thread: 32 (k <= 16), 64 (k <= 50) or 128 (k <= 100) slots
-#define RAGB_MMA_ARGS passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, progress, &n_groups, stream
+#define RAGB_MMA_ARGS passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, progress, lists, stage_limit, &n_groups, stream
   if (variant == 0) {
     if (k <= 16) rc = launch_mma<128, false, 1>(RAGB_MMA_ARGS);
     else if (k <= 50) rc = launch_mma<128, false, 2>(RAGB_MMA_ARGS);

@@ -70,6 +70,7 @@ class HybridEngine:
         self.group = group
         self.mma_variant = mma_variant
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._side_stream = None
 
     # ---- single-retriever pools --------------------------------------------------------
     def _merge(self, score: Tensor, ids: Tensor, k: int) -> Tuple[Tensor, Tensor]:
@@ -94,11 +95,55 @@ class HybridEngine:
         return self._merge(score, ids, k)
 
     # ---- hybrid ------------------------------------------------------------------------
-    def hybrid_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, k: int = 10,
-                    pool: int = 50):
-        """-> ids int32 [B,k] (-1 pads), bm25 [B,k], dense [B,k], hybrid [B,k]."""
+    def local_pools(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, pool: int,
+                    overlap: bool = True, events=None):
+        """Local BM25 pool and local dense pool of one batch.
+
+        With ``overlap`` the two scoring kernels run on two streams: the tensor-core kernel keeps one
+        block per SM in 145 KB of shared memory and issues few instructions, the BM25 kernel is bound by
+        instruction issue, so two BM25 blocks share every SM with it and the shorter kernel disappears
+        behind the longer one.  The dense kernel is enqueued first so its blocks get their SMs.
+        ``events``: optional dict filled with (start, end) CUDA events per kernel, recorded on the stream
+        the kernel runs on.
+        """
+        cur = torch.cuda.current_stream()
+        big = q_emb.shape[0] > _lib.GEMV_MAX_BATCH
+
+        def mark():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+
+        if not (overlap and big):
+            t0 = mark() if events is not None else None
+            bs, bi = self.sparse.score_topk(q_terms, q_off, max_terms, pool)
+            t1 = mark() if events is not None else None
+            ds, di = self.dense_local_topk(q_emb, pool)
+            if events is not None:
+                events["bm25"], events["dense"] = (t0, t1), (t1, mark())
+            return bs, bi, ds, di
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=q_emb.device)
+        side = self._side_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            d0 = mark() if events is not None else None
+            ds, di = self.dense_local_topk(q_emb, pool)
+            d1 = mark() if events is not None else None
+        b0 = mark() if events is not None else None
         bs, bi = self.sparse.score_topk(q_terms, q_off, max_terms, pool)
-        ds, di = self.dense_local_topk(q_emb, pool)
+        b1 = mark() if events is not None else None
+        cur.wait_stream(side)
+        ds.record_stream(cur)
+        di.record_stream(cur)
+        if events is not None:
+            events["bm25"], events["dense"] = (b0, b1), (d0, d1)
+        return bs, bi, ds, di
+
+    def hybrid_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, k: int = 10,
+                    pool: int = 50, overlap: bool = True):
+        """-> ids int32 [B,k] (-1 pads), bm25 [B,k], dense [B,k], hybrid [B,k]."""
+        bs, bi, ds, di = self.local_pools(q_terms, q_off, max_terms, q_emb, pool, overlap)
         if self.world > 1:
             # one exchange for both pools: [B, 2, pool] score + id
             s = torch.stack([bs, ds], dim=1).reshape(bs.shape[0], 2 * pool)
