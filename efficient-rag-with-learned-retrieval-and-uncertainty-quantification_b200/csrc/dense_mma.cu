@@ -527,11 +527,10 @@ static int launch_mma(const void* passages, int64_t n_rows, int dim, const void*
   a.progress = progress;
   a.lists = lists;
   RAGB_CUDA(cudaMemsetAsync(progress, 0, MM_PROGRESS_BYTES, stream));
-  // Ring depth: deep enough to cover TMA latency, shallow enough (<= 144 KB) that two blocks of the
-  // BM25 kernel fit on the same SM when the two run concurrently on different streams.
+  // Ring depth: everything shared memory offers (RAGB_MMA_STAGES caps it, e.g. to leave room for
+  // blocks of another kernel on the same SM when experimenting with two-stream overlap).
   int stages = static_cast<int>((MM_MAX_SMEM - 1024 - 256) / STAGE_BYTES);
-  const int cap = stage_limit > 0 ? stage_limit : (144 * 1024) / STAGE_BYTES;
-  if (stages > cap) stages = cap;
+  if (stage_limit > 0 && stages > stage_limit) stages = stage_limit;
   if (stages > MM_MAX_STAGES) stages = MM_MAX_STAGES;
   a.n_stages = stages;
   const size_t smem = 1024 + static_cast<size_t>(stages) * STAGE_BYTES;
