@@ -19,9 +19,11 @@
 //  * every other term streams its posting list: lists are sorted by document, so a warp
 //    continues reading where it stopped (one cursor per term, placed once by a 32-ary search),
 //    128-byte coalesced, 1 to 8 independent 32-posting chunks per pass sized to the list's
-//    density, into a 256-float shared-memory accumulator.  All documents inside one chunk are
-//    distinct, so the update is a plain read-modify-write: no atomics anywhere.  Terms whose
-//    next posting lies beyond the range are skipped with one ballot.
+//    density, into a shared-memory accumulator that covers a super-range of 4 ranges (1024
+//    documents): these lists are sparse, so walking them once per kilodocument instead of once
+//    per range cuts their bookkeeping four-fold.  All documents inside one chunk are distinct,
+//    so the update is a plain read-modify-write: no atomics anywhere.  Terms whose next posting
+//    lies beyond the super-range are skipped with one ballot.
 // Which terms use the table is decided from GLOBAL document frequencies, so every shard makes
 // the same choice and the fp32 accumulation order (table terms in query order, then list terms
 // in query order) does not depend on how the corpus is sharded.
@@ -38,7 +40,9 @@ namespace ragb {
 
 constexpr int BM_THREADS = 256;
 constexpr int BM_WARPS = BM_THREADS / 32;
-constexpr int BM_RANGE = 256;          // documents per warp range
+constexpr int BM_RANGE = 256;          // documents per warp range (8 per lane)
+constexpr int BM_SUPER = 4;            // ranges per super-range: posting lists are streamed once per 1024 documents
+constexpr int BM_SUPER_DOCS = BM_RANGE * BM_SUPER;
 constexpr int BM_MAX_TERMS = 64;
 constexpr int BM_MAX_DENSE = 1024;  // rows of the dense tf table (term ids sorted ascending)
 constexpr int BM_SEARCH = 4;  // posting lists searched concurrently while placing the cursors
@@ -54,7 +58,7 @@ struct Bm25Args {
   int64_t vocab;
   int64_t n_docs;
   int64_t id_base;
-  int64_t stripe_docs;  // multiple of BM_WARPS * BM_RANGE
+  int64_t stripe_docs;  // multiple of BM_WARPS * BM_SUPER_DOCS
   float k1p1;
   int max_terms;
   int k;
@@ -84,7 +88,7 @@ template <int U>
 __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc,
                                             const uint16_t* __restrict__ post_tf, int64_t& pos, const int64_t end,
                                             const int d0, const int d1, const float weight, float* accw,
-                                            const float* nrmw, const int lane, int& next_doc) {
+                                            const float* __restrict__ norm, const int lane, int& next_doc) {
   while (true) {
     int doc[U];
     unsigned tf[U];
@@ -105,7 +109,7 @@ __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc
       if (take) {
         const float f = static_cast<float>(tf[u]);
         const int o = doc[u] - d0;
-        accw[o] += weight * (f * fast_rcp(f + nrmw[o]));
+        accw[o] += weight * (f * fast_rcp(f + __ldg(norm + doc[u])));
       }
       taken += __popc(__ballot_sync(0xffffffffu, take));
     }
@@ -143,10 +147,8 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   if (!DENSE_OUT) sp += sizeof(uint64_t) * a.capacity * BM_WARPS;
   const uint8_t** s_drow = reinterpret_cast<const uint8_t**>(sp) + warp * mt;  // dense-table row of each dense term
   sp += sizeof(uint8_t*) * BM_WARPS * mt;
-  float* accw = reinterpret_cast<float*>(sp) + warp * BM_RANGE;
-  sp += sizeof(float) * BM_WARPS * BM_RANGE;
-  float* nrmw = reinterpret_cast<float*>(sp) + warp * BM_RANGE;
-  sp += sizeof(float) * BM_WARPS * BM_RANGE;
+  float* sacc = reinterpret_cast<float*>(sp) + warp * BM_SUPER_DOCS;  // posting-list contributions of a super-range
+  sp += sizeof(float) * BM_WARPS * BM_SUPER_DOCS;
   float* s_wgt = reinterpret_cast<float*>(sp) + warp * mt;    // sparse term weights
   sp += sizeof(float) * BM_WARPS * mt;
   float* s_dwgt = reinterpret_cast<float*>(sp) + warp * mt;   // dense-table term weights
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   const int64_t sub_docs = a.stripe_docs / BM_WARPS;
   const int64_t w_begin = min(stripe_end, stripe_begin + warp * sub_docs);
   const int64_t w_end = min(stripe_end, w_begin + sub_docs);
-  const int n_iters = static_cast<int>(sub_docs / BM_RANGE);
+  const int n_super = static_cast<int>(sub_docs / BM_SUPER_DOCS);
 
   for (int i = tid; i < a.n_dense; i += BM_THREADS) s_dterms[i] = a.dense_terms[i];
   WarpTopK tk;
@@ -268,8 +270,8 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
           s_end[ntv] = te[j];
           s_wgt[ntv] = wg[j];
           s_nxt[ntv] = nx;
-          // expected postings of this term per 256-document range
-          const double per_range = static_cast<double>(te[j] - ts[j]) * BM_RANGE / static_cast<double>(a.n_docs);
+          // expected postings of this term per super-range
+          const double per_range = static_cast<double>(te[j] - ts[j]) * BM_SUPER_DOCS / static_cast<double>(a.n_docs);
           s_dense[ntv] = per_range < 24.0 ? 0 : (per_range < 56.0 ? 1 : (per_range < 120.0 ? 2 : 3));
         }
         ++ntv;
@@ -278,68 +280,35 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   }
   __syncwarp();
 
-  const int j0 = lane * 8;  // the 8 documents of the range this lane owns outside the posting phase
-  for (int it = 0; it < n_iters; ++it) {
-    const int64_t d0l = w_begin + static_cast<int64_t>(it) * BM_RANGE;
-    const int d0 = static_cast<int>(d0l < w_end ? d0l : w_end);
-    const int d1 = static_cast<int>(min(w_end, d0l + BM_RANGE));
-    const int cnt = d1 > d0 ? d1 - d0 : 0;
-    float ac[8], nr[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ac[j] = 0.0f;
-    if (cnt == BM_RANGE) {
-      const float4 n0 = __ldg(reinterpret_cast<const float4*>(a.norm + d0 + j0));
-      const float4 n1 = __ldg(reinterpret_cast<const float4*>(a.norm + d0 + j0 + 4));
-      nr[0] = n0.x; nr[1] = n0.y; nr[2] = n0.z; nr[3] = n0.w;
-      nr[4] = n1.x; nr[5] = n1.y; nr[6] = n1.z; nr[7] = n1.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) nr[j] = (j0 + j) < cnt ? __ldg(a.norm + d0 + j0 + j) : 1.0f;
-    }
-    // ---- dense-table terms: 8 tf bytes per lane per term, accumulators stay in registers.
-    // One term at a time with the next term's bytes already in flight.
-    if (cnt > 0 && nd > 0) {
-      const int64_t off = static_cast<int64_t>(d0) + j0;
-      uint2 cur = __ldg(reinterpret_cast<const uint2*>(s_drow[0] + off));
-      for (int i = 0; i < nd; ++i) {
-        const float w = s_dwgt[i];
-        uint2 nxt = make_uint2(0u, 0u);
-        if (i + 1 < nd) nxt = __ldg(reinterpret_cast<const uint2*>(s_drow[i + 1] + off));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const unsigned word = j < 4 ? cur.x : cur.y;
-          // one PRMT builds 0x4B0000tt = 8388608.0f + tf; subtracting 2^23 gives tf exactly
-          const float f = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (j & 3))) - 8388608.0f;
-          ac[j] = fmaf(w, f * fast_rcp(f + nr[j]), ac[j]);
-        }
-        cur = nxt;
-      }
-    }
-    // ---- posting-list terms: shared-memory accumulator, only when some list reaches into the range
-    unsigned active = 0;  // terms ti < 32 with a posting in the range; longer queries fall back to a scan
-    bool any_sparse = false;
-    if (cnt > 0 && ntv > 0) {
+  const int j0 = lane * 8;  // the 8 documents of a range this lane owns
+  for (int sup = 0; sup < n_super; ++sup) {
+    const int64_t s0l = w_begin + static_cast<int64_t>(sup) * BM_SUPER_DOCS;
+    const int s0 = static_cast<int>(s0l < w_end ? s0l : w_end);
+    const int s1 = static_cast<int>(min(w_end, s0l + BM_SUPER_DOCS));
+    if (s1 <= s0) break;  // warp-uniform; nothing below synchronises the block
+    // ---- posting-list terms: streamed once per super-range into shared memory, and only when
+    //      some list actually reaches into it (one ballot decides)
+    unsigned active = 0;
+    bool have_sparse = false;
+    if (ntv > 0) {
       if (ntv <= 32) {
-        active = __ballot_sync(0xffffffffu, lane < ntv && s_nxt[lane] < d1);
-        any_sparse = active != 0;
+        active = __ballot_sync(0xffffffffu, lane < ntv && s_nxt[lane] < s1);
+        have_sparse = active != 0;
       } else {
-        any_sparse = true;
+        have_sparse = true;
       }
     }
-    if (any_sparse || DENSE_OUT) {
-      *reinterpret_cast<float4*>(accw + j0) = make_float4(ac[0], ac[1], ac[2], ac[3]);
-      *reinterpret_cast<float4*>(accw + j0 + 4) = make_float4(ac[4], ac[5], ac[6], ac[7]);
-    }
-    if (any_sparse) {
-      *reinterpret_cast<float4*>(nrmw + j0) = make_float4(nr[0], nr[1], nr[2], nr[3]);
-      *reinterpret_cast<float4*>(nrmw + j0 + 4) = make_float4(nr[4], nr[5], nr[6], nr[7]);
+    if (have_sparse) {
+#pragma unroll
+      for (int i = 0; i < BM_SUPER_DOCS / 128; ++i)
+        *reinterpret_cast<float4*>(sacc + (i * 32 + lane) * 4) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       __syncwarp();
       for (int ti = 0; ti < ntv; ++ti) {
         if (ntv <= 32) {
           if (active == 0) break;
           ti = __ffs(active) - 1;
           active &= active - 1;
-        } else if (s_nxt[ti] >= d1) {
+        } else if (s_nxt[ti] >= s1) {
           continue;
         }
         int64_t pos = s_pos[ti];
@@ -347,10 +316,10 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         const float w = s_wgt[ti];
         int next_doc;
         switch (s_dense[ti]) {  // chunks per pass sized to the term's density (warp-uniform)
-          case 0: stream_term<1>(a.post_doc, a.post_tf, pos, end, d0, d1, w, accw, nrmw, lane, next_doc); break;
-          case 1: stream_term<2>(a.post_doc, a.post_tf, pos, end, d0, d1, w, accw, nrmw, lane, next_doc); break;
-          case 2: stream_term<4>(a.post_doc, a.post_tf, pos, end, d0, d1, w, accw, nrmw, lane, next_doc); break;
-          default: stream_term<8>(a.post_doc, a.post_tf, pos, end, d0, d1, w, accw, nrmw, lane, next_doc); break;
+          case 0: stream_term<1>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, lane, next_doc); break;
+          case 1: stream_term<2>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, lane, next_doc); break;
+          case 2: stream_term<4>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, lane, next_doc); break;
+          default: stream_term<8>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, lane, next_doc); break;
         }
         if (lane == 0) {
           s_pos[ti] = pos;
@@ -358,28 +327,69 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         }
         __syncwarp();
       }
-      const float4 r0 = *reinterpret_cast<const float4*>(accw + j0);
-      const float4 r1 = *reinterpret_cast<const float4*>(accw + j0 + 4);
-      ac[0] = r0.x; ac[1] = r0.y; ac[2] = r0.z; ac[3] = r0.w;
-      ac[4] = r1.x; ac[5] = r1.y; ac[6] = r1.z; ac[7] = r1.w;
     }
-    if (DENSE_OUT) {
-      __syncwarp();
-      float* dst = a.out_scores + static_cast<int64_t>(q) * a.n_docs + d0;
-      for (int j = lane; j < cnt; j += 32) dst[j] = accw[j];
-      __syncwarp();
-    } else {
-      // ---- warp-private selection: no barrier; in steady state 8 compares and one vote per range
-      bool hot = false;
+#pragma unroll 1
+    for (int r = 0; r < BM_SUPER; ++r) {
+      const int d0 = s0 + r * BM_RANGE;
+      if (d0 >= s1) break;
+      const int d1 = min(s1, d0 + BM_RANGE);
+      const int cnt = d1 - d0;
+      float ac[8], nr[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) hot |= (ac[j] >= tk.thr_score) && (j0 + j) < cnt;
-      if (__any_sync(0xffffffffu, hot)) {
-        const int32_t gid0 = static_cast<int32_t>(a.id_base + d0) + j0;
+      for (int j = 0; j < 8; ++j) ac[j] = 0.0f;
+      if (cnt == BM_RANGE) {
+        const float4 n0 = __ldg(reinterpret_cast<const float4*>(a.norm + d0 + j0));
+        const float4 n1 = __ldg(reinterpret_cast<const float4*>(a.norm + d0 + j0 + 4));
+        nr[0] = n0.x; nr[1] = n0.y; nr[2] = n0.z; nr[3] = n0.w;
+        nr[4] = n1.x; nr[5] = n1.y; nr[6] = n1.z; nr[7] = n1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nr[j] = (j0 + j) < cnt ? __ldg(a.norm + d0 + j0 + j) : 1.0f;
+      }
+      // ---- dense-table terms: 8 tf bytes per lane per term, accumulators stay in registers.
+      // One term at a time with the next term's bytes already in flight.
+      if (nd > 0) {
+        const int64_t off = static_cast<int64_t>(d0) + j0;
+        uint2 cur = __ldg(reinterpret_cast<const uint2*>(s_drow[0] + off));
+        for (int i = 0; i < nd; ++i) {
+          const float w = s_dwgt[i];
+          uint2 nxt = make_uint2(0u, 0u);
+          if (i + 1 < nd) nxt = __ldg(reinterpret_cast<const uint2*>(s_drow[i + 1] + off));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const unsigned word = j < 4 ? cur.x : cur.y;
+            // one PRMT builds 0x4B0000tt = 8388608.0f + tf; subtracting 2^23 gives tf exactly
+            const float f = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (j & 3))) - 8388608.0f;
+            ac[j] = fmaf(w, f * fast_rcp(f + nr[j]), ac[j]);
+          }
+          cur = nxt;
+        }
+      }
+      if (have_sparse) {  // score = (table terms in query order) + (list terms in query order)
+        const float4 r0 = *reinterpret_cast<const float4*>(sacc + r * BM_RANGE + j0);
+        const float4 r1 = *reinterpret_cast<const float4*>(sacc + r * BM_RANGE + j0 + 4);
+        ac[0] += r0.x; ac[1] += r0.y; ac[2] += r0.z; ac[3] += r0.w;
+        ac[4] += r1.x; ac[5] += r1.y; ac[6] += r1.z; ac[7] += r1.w;
+      }
+      if (DENSE_OUT) {
+        float* dst = a.out_scores + static_cast<int64_t>(q) * a.n_docs + d0 + j0;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          tk.offer((ac[j] >= tk.thr_score) && (j0 + j) < cnt, make_key(ac[j], gid0 + j), lane);
+          if ((j0 + j) < cnt) dst[j] = ac[j];
+      } else {
+        // ---- warp-private selection: no barrier; in steady state 8 compares and one vote per range
+        bool hot = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hot |= (ac[j] >= tk.thr_score) && (j0 + j) < cnt;
+        if (__any_sync(0xffffffffu, hot)) {
+          const int32_t gid0 = static_cast<int32_t>(a.id_base + d0) + j0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            tk.offer((ac[j] >= tk.thr_score) && (j0 + j) < cnt, make_key(ac[j], gid0 + j), lane);
+        }
       }
     }
+    __syncwarp();  // the next super-range clears sacc
   }
   if (!DENSE_OUT) {
     // fold the 8 warp lists of this block into one (8k <= 2048 keys, one bitonic sort), so the
@@ -481,7 +491,7 @@ __global__ void norm_kernel(const int32_t* __restrict__ doc_len, int64_t n_docs,
 }
 
 static int bm25_stripes(int n_queries, int64_t n_docs, int64_t* stripe_docs_out) {
-  const int64_t unit = static_cast<int64_t>(BM_WARPS) * BM_RANGE;
+  const int64_t unit = static_cast<int64_t>(BM_WARPS) * BM_SUPER_DOCS;
   const int64_t target_blocks = 148 * 6 * 2;
   int64_t stripes = ceil_div64(target_blocks, n_queries);
   const int64_t max_stripes = ceil_div64(n_docs, unit);
@@ -498,7 +508,7 @@ static size_t bm25_smem_bytes(int max_terms, int capacity, bool dense_out) {
   b += 2 * sizeof(int64_t) * BM_WARPS * max_terms;
   if (!dense_out) b += sizeof(uint64_t) * capacity * BM_WARPS;
   b += sizeof(void*) * BM_WARPS * max_terms;
-  b += 2 * sizeof(float) * BM_WARPS * BM_RANGE;
+  b += sizeof(float) * BM_WARPS * BM_SUPER_DOCS;
   b += (2 * sizeof(float) + 2 * sizeof(int) + 1) * BM_WARPS * max_terms;
   return (b + 15) & ~static_cast<size_t>(15);
 }
