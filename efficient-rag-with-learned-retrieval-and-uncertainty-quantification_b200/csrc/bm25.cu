@@ -27,6 +27,10 @@
 // Which terms use the table is decided from GLOBAL document frequencies, so every shard makes
 // the same choice and the fp32 accumulation order (table terms in query order, then list terms
 // in query order) does not depend on how the corpus is sharded.
+// Pruning (exact): a document with no posting-list term can score at most the sum of the table
+// terms' weights; once a warp's k-th best exceeds that bound it only scores the documents its
+// posting lists touched in the super-range (bitmap + byte gathers from the table), which is what
+// the rarer query terms leave of 10M documents: ~80k per query.
 // Selection is warp-private too (WarpTopK in topk.cuh: threshold in a register, appends through a
 // ballot prefix, rare warp-level bitonic merge), so the main loop has no block barrier at all; the
 // 8 warp lists are folded once at the end of the block and the per-block lists of all stripes
@@ -88,7 +92,8 @@ template <int U>
 __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc,
                                             const uint16_t* __restrict__ post_tf, int64_t& pos, const int64_t end,
                                             const int d0, const int d1, const float weight, float* accw,
-                                            const float* __restrict__ norm, const int lane, int& next_doc) {
+                                            const float* __restrict__ norm, unsigned* touched, const int lane,
+                                            int& next_doc) {
   while (true) {
     int doc[U];
     unsigned tf[U];
@@ -110,6 +115,7 @@ __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc
         const float f = static_cast<float>(tf[u]);
         const int o = doc[u] - d0;
         accw[o] += weight * (f * fast_rcp(f + __ldg(norm + doc[u])));
+        if (touched != nullptr) atomicOr(touched + (o >> 5), 1u << (o & 31));
       }
       taken += __popc(__ballot_sync(0xffffffffu, take));
     }
@@ -149,6 +155,9 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   sp += sizeof(uint8_t*) * BM_WARPS * mt;
   float* sacc = reinterpret_cast<float*>(sp) + warp * BM_SUPER_DOCS;  // posting-list contributions of a super-range
   sp += sizeof(float) * BM_WARPS * BM_SUPER_DOCS;
+  unsigned* s_bits = reinterpret_cast<unsigned*>(sp) + warp * (BM_SUPER_DOCS / 32);  // documents touched by a posting
+  sp += sizeof(unsigned) * BM_WARPS * (BM_SUPER_DOCS / 32);
+  unsigned* const touched = DENSE_OUT ? nullptr : s_bits;
   float* s_wgt = reinterpret_cast<float*>(sp) + warp * mt;    // sparse term weights
   sp += sizeof(float) * BM_WARPS * mt;
   float* s_dwgt = reinterpret_cast<float*>(sp) + warp * mt;   // dense-table term weights
@@ -207,6 +216,15 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
     ns += __popc(ms);
   }
   __syncwarp();
+
+  // A document without any posting-list term scores at most ub_table = sum of the positive weights
+  // of the table terms (tf / (tf + norm) < 1).  Once the warp's k-th best score exceeds that bound,
+  // only documents touched by a posting list can still qualify (the "essential lists" of MaxScore):
+  // exact, and it turns ~10M evaluations per query into the ~80k documents its rarer terms occur in.
+  float ub_table = 0.0f;
+  for (int i = lane; i < nd; i += 32) ub_table += fmaxf(s_dwgt[i], 0.0f);
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) ub_table += __shfl_xor_sync(0xffffffffu, ub_table, sh);
 
   // ---- per-warp cursors: lower_bound(post_doc[term], w_begin) by a 32-ary search, 4 terms at a time
   int ntv = 0;  // sparse terms with a non-empty posting list (warp-uniform)
@@ -302,6 +320,7 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
 #pragma unroll
       for (int i = 0; i < BM_SUPER_DOCS / 128; ++i)
         *reinterpret_cast<float4*>(sacc + (i * 32 + lane) * 4) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (!DENSE_OUT) s_bits[lane] = 0u;
       __syncwarp();
       for (int ti = 0; ti < ntv; ++ti) {
         if (ntv <= 32) {
@@ -316,10 +335,10 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         const float w = s_wgt[ti];
         int next_doc;
         switch (s_dense[ti]) {  // chunks per pass sized to the term's density (warp-uniform)
-          case 0: stream_term<1>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, lane, next_doc); break;
-          case 1: stream_term<2>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, lane, next_doc); break;
-          case 2: stream_term<4>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, lane, next_doc); break;
-          default: stream_term<8>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, lane, next_doc); break;
+          case 0: stream_term<1>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, touched, lane, next_doc); break;
+          case 1: stream_term<2>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, touched, lane, next_doc); break;
+          case 2: stream_term<4>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, touched, lane, next_doc); break;
+          default: stream_term<8>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, touched, lane, next_doc); break;
         }
         if (lane == 0) {
           s_pos[ti] = pos;
@@ -327,6 +346,32 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         }
         __syncwarp();
       }
+    }
+    if (!DENSE_OUT && tk.thr_score > ub_table) {
+      // ---- pruned mode: score only the documents a posting list touched (one bit each)
+      if (have_sparse) {
+        unsigned word = s_bits[lane];
+        while (__any_sync(0xffffffffu, word != 0u)) {
+          const bool valid = word != 0u;
+          float total = 0.0f;
+          int doc = s0;
+          if (valid) {
+            const int o = lane * 32 + __ffs(word) - 1;
+            word &= word - 1;
+            doc = s0 + o;
+            const float nrm = __ldg(a.norm + doc);
+            for (int i = 0; i < nd; ++i) {  // same arithmetic, same order as the full path below
+              const unsigned tfb = __ldg(s_drow[i] + doc);
+              const float f = __uint_as_float(0x4B000000u | tfb) - 8388608.0f;
+              total = fmaf(s_dwgt[i], f * fast_rcp(f + nrm), total);
+            }
+            total += sacc[o];
+          }
+          tk.offer(valid && total >= tk.thr_score, make_key(total, static_cast<int32_t>(a.id_base + doc)), lane);
+        }
+      }
+      __syncwarp();
+      continue;
     }
 #pragma unroll 1
     for (int r = 0; r < BM_SUPER; ++r) {
@@ -509,6 +554,7 @@ static size_t bm25_smem_bytes(int max_terms, int capacity, bool dense_out) {
   if (!dense_out) b += sizeof(uint64_t) * capacity * BM_WARPS;
   b += sizeof(void*) * BM_WARPS * max_terms;
   b += sizeof(float) * BM_WARPS * BM_SUPER_DOCS;
+  b += sizeof(unsigned) * BM_WARPS * (BM_SUPER_DOCS / 32);
   b += (2 * sizeof(float) + 2 * sizeof(int) + 1) * BM_WARPS * max_terms;
   return (b + 15) & ~static_cast<size_t>(15);
 }

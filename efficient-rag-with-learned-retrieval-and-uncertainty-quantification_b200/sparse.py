@@ -18,6 +18,7 @@ statistics and all scoring run in the library's own kernels.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -28,7 +29,7 @@ from torch import Tensor
 from . import ops
 
 MAX_DENSE_TERMS = 1024          # rows the kernel's table directory can hold
-DENSE_MIN_FRACTION = 64         # a term gets a row when df >= N / 64 ...
+DENSE_MIN_FRACTION = int(os.environ.get("RAGB_DENSE_MIN_FRACTION", "64"))  # a term gets a row when df >= N / this ...
 DENSE_TABLE_BYTES = 8 << 30     # ... while the table stays under this many bytes per shard
 
 
