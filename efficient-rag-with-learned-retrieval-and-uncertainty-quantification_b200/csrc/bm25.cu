@@ -73,6 +73,7 @@ struct Bm25Args {
   const int32_t* dense_terms;  // [n_dense] term id of each row
   int64_t dense_stride;      // multiple of BM_RANGE, >= n_docs
   int n_dense;
+  float* seed_thr;           // [queries] proven lower bound of each query's k-th best score (0 = none)
 };
 
 // 1/x for x in the normal range (here x = tf + norm in [0.3, 7e4]): one MUFU.RCP, none of the
@@ -180,7 +181,10 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
 
   for (int i = tid; i < a.n_dense; i += BM_THREADS) s_dterms[i] = a.dense_terms[i];
   WarpTopK tk;
-  if (!DENSE_OUT) tk.init(s_keys, a.k, a.capacity, positive_floor_key(), lane);
+  if (!DENSE_OUT) {
+    tk.init(s_keys, a.k, a.capacity, positive_floor_key(), lane);
+    if (a.seed_thr != nullptr) tk.raise(a.seed_thr[q]);
+  }
   __syncthreads();
 
   // ---- split the query's terms: rows of the dense tf table vs posting lists -------------------
@@ -464,6 +468,107 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Threshold seeding.  For one posting-list term e of the query, every document d in its list has
+//   score(q, d) >= w_e * imp_e(d) + sum over table terms (exact)        (other list terms add >= 0)
+// so the k-th largest of these lower bounds over (a prefix of) the list is a proven lower bound of
+// the query's k-th best score: at least k distinct documents reach it.  The best bound over the
+// query's list terms lets the main kernel start in pruned mode.  Skipped (bound 0) when a list
+// term has a negative weight or no list is k documents long.
+// ---------------------------------------------------------------------------------------
+constexpr int SEED_THREADS = 256;
+constexpr int SEED_DOCS = 1024;
+
+__global__ void __launch_bounds__(SEED_THREADS) bm25_seed_kernel(const Bm25Args a) {
+  __shared__ int s_dterms[BM_MAX_DENSE];
+  __shared__ const uint8_t* s_row[BM_MAX_TERMS];
+  __shared__ float s_roww[BM_MAX_TERMS];
+  __shared__ int64_t s_lo[BM_MAX_TERMS];
+  __shared__ int s_len[BM_MAX_TERMS];
+  __shared__ float s_lw[BM_MAX_TERMS];
+  __shared__ uint32_t s_lb[SEED_DOCS];
+  __shared__ int s_nrow, s_nlist, s_negative;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < a.n_dense; i += SEED_THREADS) s_dterms[i] = a.dense_terms[i];
+  if (tid == 0) s_nrow = s_nlist = s_negative = 0;
+  __syncthreads();
+  const int qb = a.q_off[q];
+  const int nt = min(a.q_off[q + 1] - qb, a.max_terms);
+  if (tid < nt) {
+    const int t = a.q_terms[qb + tid];
+    if (t >= 0 && t < a.vocab) {
+      const float w = a.idf[t] * a.k1p1;
+      int lo_e = 0, hi_e = a.n_dense;
+      while (lo_e < hi_e) {
+        const int mid = (lo_e + hi_e) >> 1;
+        if (s_dterms[mid] < t) lo_e = mid + 1; else hi_e = mid;
+      }
+      if (w != 0.0f) {
+        if (lo_e < a.n_dense && s_dterms[lo_e] == t) {
+          const int o = atomicAdd(&s_nrow, 1);
+          s_row[o] = a.dense_tf + static_cast<int64_t>(lo_e) * a.dense_stride;
+          s_roww[o] = w;
+        } else {
+          if (w < 0.0f) s_negative = 1;
+          const int64_t lo = a.term_off[t], hi = a.term_off[t + 1];
+          if (hi - lo >= a.k) {
+            const int o = atomicAdd(&s_nlist, 1);
+            s_lo[o] = lo;
+            s_len[o] = static_cast<int>(min(hi - lo, static_cast<int64_t>(SEED_DOCS)));
+            s_lw[o] = w;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float best = 0.0f;
+  if (!s_negative) {
+    const int nrow = s_nrow, nlist = s_nlist;
+    for (int e = 0; e < nlist; ++e) {
+      const int64_t lo = s_lo[e];
+      const int n = s_len[e];
+      const float w = s_lw[e];
+      for (int i = tid; i < SEED_DOCS; i += SEED_THREADS) {
+        uint32_t key = 0u;
+        if (i < n) {
+          const int doc = __ldg(a.post_doc + lo + i);
+          const float nrm = __ldg(a.norm + doc);
+          const float f = static_cast<float>(__ldg(a.post_tf + lo + i));
+          float lb = w * (f * fast_rcp(f + nrm));
+          for (int r = 0; r < nrow; ++r) {
+            const float g = static_cast<float>(__ldg(s_row[r] + doc));
+            lb = fmaf(s_roww[r], g * fast_rcp(g + nrm), lb);
+          }
+          key = float_to_ordered(lb);
+        }
+        s_lb[i] = key;
+      }
+      __syncthreads();
+      // descending bitonic sort of the 1024 ordered bounds
+      for (int size = 2; size <= SEED_DOCS; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int i = tid; i < SEED_DOCS / 2; i += SEED_THREADS) {
+            const int lo_i = 2 * i - (i & (stride - 1)), hi_i = lo_i + stride;
+            const bool desc = ((lo_i & size) == 0);
+            const uint32_t x = s_lb[lo_i], y = s_lb[hi_i];
+            if ((x < y) == desc) {
+              s_lb[lo_i] = y;
+              s_lb[hi_i] = x;
+            }
+          }
+          __syncthreads();
+        }
+      }
+      const uint32_t kth = s_lb[a.k - 1];
+      if (kth != 0u) best = fmaxf(best, ordered_to_float(kth));
+      __syncthreads();
+    }
+  }
+  // a hair below the bound: the main kernel sums the same terms in another order
+  if (tid == 0) a.seed_thr[q] = best > 0.0f ? best * (1.0f - 8e-6f) : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------
 // Statistics: idf with the epsilon floor (two deterministic passes), length norm.
 // ---------------------------------------------------------------------------------------
 constexpr int IDF_BLOCKS = 256;
@@ -622,7 +727,7 @@ size_t ragb_bm25_topk_workspace_bytes(int32_t n_queries, int64_t n_docs, int32_t
   if (n_queries <= 0 || n_docs <= 0 || k <= 0) return 0;
   int64_t stripe_docs;
   const int stripes = bm25_stripes(n_queries, n_docs, &stripe_docs);
-  return static_cast<size_t>(n_queries) * stripes * k * sizeof(uint64_t);
+  return static_cast<size_t>(n_queries) * stripes * k * sizeof(uint64_t) + static_cast<size_t>(n_queries) * sizeof(float);
 }
 
 int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
@@ -663,6 +768,9 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   a.part_keys = static_cast<uint64_t*>(workspace);
   a.out_scores = nullptr;
   const int stripes = bm25_stripes(n_queries, n_docs, &a.stripe_docs);
+  a.seed_thr = reinterpret_cast<float*>(a.part_keys + static_cast<size_t>(n_queries) * stripes * k);
+  bm25_seed_kernel<<<n_queries, SEED_THREADS, 0, stream>>>(a);
+  RAGB_AFTER_LAUNCH(1);
   const size_t smem = bm25_smem_bytes(a.max_terms, a.capacity, false);
   RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   bm25_kernel<false><<<dim3(n_queries, stripes), BM_THREADS, smem, stream>>>(a);

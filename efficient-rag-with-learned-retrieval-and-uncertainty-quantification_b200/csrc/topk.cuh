@@ -152,9 +152,21 @@ struct WarpTopK {
   // Warp-wide: fold the appended candidates into the sorted top-k and tighten the threshold.
   __device__ __forceinline__ void flush(int lane) {
     if (count == 0) return;
-    thr = warp_topk_flush(keys, k, count, floor_key, lane);
-    thr_score = key_score(thr);
+    const uint64_t t = warp_topk_flush(keys, k, count, floor_key, lane);
+    if (t > thr) {   // never loosen: an external bound may already be tighter
+      thr = t;
+      thr_score = key_score(t);
+    }
     count = 0;
+  }
+
+  // A proven lower bound of the final k-th best score (e.g. from another warp or a seeding pass):
+  // nothing below it can end up in the result, so it may serve as admission threshold right away.
+  __device__ __forceinline__ void raise(float score) {
+    if (score > thr_score) {
+      thr_score = score;
+      thr = static_cast<uint64_t>(float_to_ordered(score)) << 32;
+    }
   }
 
   // Warp-wide: every lane offers at most one key (valid says whether it has one).
