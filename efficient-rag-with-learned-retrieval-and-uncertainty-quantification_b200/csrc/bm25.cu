@@ -36,6 +36,7 @@
 // 8 warp lists are folded once at the end of the block and the per-block lists of all stripes
 // are merged by topk_merge_kernel.
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "topk.cuh"
@@ -50,6 +51,10 @@ constexpr int BM_SUPER_DOCS = BM_RANGE * BM_SUPER;
 constexpr int BM_MAX_TERMS = 64;
 constexpr int BM_MAX_DENSE = 1024;  // rows of the dense tf table (term ids sorted ascending)
 constexpr int BM_SEARCH = 4;  // posting lists searched concurrently while placing the cursors
+
+// debug counters (RAGB_BM25_DEBUG=1): [0] super-ranges full mode, [1] pruned, [2] pruned with postings,
+// [3] documents scored in pruned mode, [4] queries seeded, [5] queries with seed > table bound
+__device__ unsigned long long g_bm25_dbg[8];
 
 struct Bm25Args {
   const int64_t* term_off;
@@ -74,6 +79,7 @@ struct Bm25Args {
   int64_t dense_stride;      // multiple of BM_RANGE, >= n_docs
   int n_dense;
   float* seed_thr;           // [queries] proven lower bound of each query's k-th best score (0 = none)
+  int debug;
 };
 
 // 1/x for x in the normal range (here x = tf + norm in [0.3, 7e4]): one MUFU.RCP, none of the
@@ -185,6 +191,7 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
     tk.init(s_keys, a.k, a.capacity, positive_floor_key(), lane);
     if (a.seed_thr != nullptr) tk.raise(a.seed_thr[q]);
   }
+  const float seed_dbg = (!DENSE_OUT && a.seed_thr != nullptr) ? a.seed_thr[q] : 0.0f;
   __syncthreads();
 
   // ---- split the query's terms: rows of the dense tf table vs posting lists -------------------
@@ -230,6 +237,10 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
 #pragma unroll
   for (int sh = 16; sh > 0; sh >>= 1) ub_table += __shfl_xor_sync(0xffffffffu, ub_table, sh);
 
+  if (a.debug && tid == 0 && blockIdx.y == 0) {
+    if (seed_dbg > 0.0f) atomicAdd(&g_bm25_dbg[4], 1ull);
+    if (seed_dbg > ub_table) atomicAdd(&g_bm25_dbg[5], 1ull);
+  }
   // ---- per-warp cursors: lower_bound(post_doc[term], w_begin) by a 32-ary search, 4 terms at a time
   int ntv = 0;  // sparse terms with a non-empty posting list (warp-uniform)
   for (int g = 0; g < ns; g += BM_SEARCH) {
@@ -351,10 +362,12 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         __syncwarp();
       }
     }
+    if (a.debug && lane == 0) atomicAdd(&g_bm25_dbg[(!DENSE_OUT && tk.thr_score > ub_table) ? (have_sparse ? 2 : 1) : 0], 1ull);
     if (!DENSE_OUT && tk.thr_score > ub_table) {
       // ---- pruned mode: score only the documents a posting list touched (one bit each)
       if (have_sparse) {
         unsigned word = s_bits[lane];
+        if (a.debug) atomicAdd(&g_bm25_dbg[3], static_cast<unsigned long long>(__popc(word)));
         while (__any_sync(0xffffffffu, word != 0u)) {
           const bool valid = word != 0u;
           float total = 0.0f;
@@ -692,6 +705,14 @@ using namespace ragb;
 
 extern "C" {
 
+// Debug aid (not part of the documented ABI): synchronously copy and clear the kernel counters.
+int ragb_debug_bm25_counters(unsigned long long* out8) {
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out8, g_bm25_dbg, sizeof(zero)) != cudaSuccess) return RAGB_ECUDA;
+  if (cudaMemcpyToSymbol(g_bm25_dbg, zero, sizeof(zero)) != cudaSuccess) return RAGB_ECUDA;
+  return RAGB_OK;
+}
+
 size_t ragb_bm25_idf_scratch_bytes(int64_t) { return 2 * IDF_BLOCKS * sizeof(double); }
 
 int ragb_bm25_build_idf(const int32_t* df, int64_t vocab, int64_t corpus_size, double epsilon, float* idf_out,
@@ -769,6 +790,8 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   a.out_scores = nullptr;
   const int stripes = bm25_stripes(n_queries, n_docs, &a.stripe_docs);
   a.seed_thr = reinterpret_cast<float*>(a.part_keys + static_cast<size_t>(n_queries) * stripes * k);
+  static const int debug_flag = [] { const char* e = getenv("RAGB_BM25_DEBUG"); return e ? atoi(e) : 0; }();
+  a.debug = debug_flag;
   bm25_seed_kernel<<<n_queries, SEED_THREADS, 0, stream>>>(a);
   RAGB_AFTER_LAUNCH(1);
   const size_t smem = bm25_smem_bytes(a.max_terms, a.capacity, false);
