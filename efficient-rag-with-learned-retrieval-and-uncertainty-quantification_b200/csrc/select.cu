@@ -240,6 +240,44 @@ __global__ void __launch_bounds__(FUSE_THREADS) hybrid_fuse_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Retrieval uncertainty of a ranked list, docs/uncertainty_theory.md:48-56 of the reference:
+//   U = std(s_top-k) + lambda * (1 - |s_1 - s_k|)      (population std, like numpy's default)
+// over the valid entries (id >= 0) of each row.  One warp per query.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) retrieval_uncertainty_kernel(const float* __restrict__ score,
+                                                                    const int32_t* __restrict__ id, int n_queries,
+                                                                    int k, float lambda, float* __restrict__ out) {
+  const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= n_queries) return;
+  float sum = 0.0f, hi = -INFINITY, lo = INFINITY;
+  int n = 0;
+  for (int j = lane; j < k; j += 32) {
+    if (id[static_cast<int64_t>(q) * k + j] >= 0) {
+      const float v = score[static_cast<int64_t>(q) * k + j];
+      sum += v;
+      hi = fmaxf(hi, v);
+      lo = fminf(lo, v);
+      ++n;
+    }
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+    n += __shfl_xor_sync(0xffffffffu, n, s);
+  }
+  const float mean = n > 0 ? sum / n : 0.0f;
+  float ss = 0.0f;
+  for (int j = lane; j < k; j += 32)
+    if (id[static_cast<int64_t>(q) * k + j] >= 0) {
+      const float d = score[static_cast<int64_t>(q) * k + j] - mean;
+      ss = fmaf(d, d, ss);
+    }
+  for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+  if (lane == 0) out[q] = n > 0 ? sqrtf(ss / n) + lambda * (1.0f - fabsf(hi - lo)) : lambda;
+}
+
 // Host-side helpers shared with the scoring kernels ---------------------------------------
 int launch_merge_keys(const uint64_t* keys, int n_queries, int n_lists, int k_in, int k_out, float* out_score,
                       int32_t* out_id, cudaStream_t stream) {
@@ -317,6 +355,18 @@ int ragb_topk_merge(const float* in_score, const int32_t* in_id, int32_t n_queri
   const int capacity = topk_capacity(k_out);
   topk_merge_kernel<<<n_queries, SEL_THREADS, capacity * sizeof(uint64_t), stream>>>(
       nullptr, in_score, in_id, n_lists, k_in, k_out, capacity, out_score, out_id);
+  RAGB_AFTER_LAUNCH(1);
+  return RAGB_OK;
+}
+
+int ragb_retrieval_uncertainty(const float* score, const int32_t* id, int32_t n_queries, int32_t k, double lambda,
+                               float* out, ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(score && id && out, RAGB_EINVAL, "ragb_retrieval_uncertainty: null pointer");
+  RAGB_REQUIRE(n_queries > 0 && k > 0, RAGB_EINVAL, "ragb_retrieval_uncertainty: empty shape");
+  retrieval_uncertainty_kernel<<<(n_queries + 7) / 8, 256, 0, stream>>>(score, id, n_queries, k,
+                                                                        static_cast<float>(lambda), out);
   RAGB_AFTER_LAUNCH(1);
   return RAGB_OK;
 }

@@ -156,6 +156,27 @@ class HybridEngine:
             ds, di = ops.topk_merge(gs[:, :, 1].contiguous(), gi[:, :, 1].contiguous(), pool)
         return ops.hybrid_fuse_topk(bs, bi, ds, di, k)
 
+    def retrieve_and_rerank(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, router, k: int = 10,
+                            pool: int = 50, mc_samples: int = 0, lam: float = 1.0, seed: Optional[int] = None):
+        """The per-query loop of experiments/run_evaluation.py:165-196 for a whole batch.
+
+        get_scores_for_router (hybrid top-k, padded) -> router gate -> fused score -> reorder, plus the
+        confidence the reference left as a TODO (:194-196): the retrieval uncertainty of
+        docs/uncertainty_theory.md:48-56 on the fused ranking and, with ``mc_samples`` > 0, the
+        MC-Dropout confidence of the router on these candidates.  Returns a dict of device tensors.
+        """
+        ids, sb, sd, sh = self.hybrid_topk(q_terms, q_off, max_terms, q_emb, k, pool)
+        fused, order = router.hybrid_rerank(sb, sd, top_k=k)
+        ranked = torch.gather(ids, 1, order)
+        out = {"ids": ranked, "fused": fused, "bm25": torch.gather(sb, 1, order), "dense": torch.gather(sd, 1, order),
+               "hybrid": torch.gather(sh, 1, order),
+               "retrieval_uncertainty": ops.retrieval_uncertainty(fused.contiguous(), ranked.contiguous(), lam)}
+        if mc_samples > 0:
+            unc = router.mc_dropout(sb, sd, n_samples=mc_samples, seed=seed)
+            out["router_confidence"] = unc.confidence
+            out["gate_mean"], out["gate_std"] = unc.mean_gate, unc.std_gate
+        return out
+
     # ---- full-fusion mode ----------------------------------------------------------------
     def full_fusion_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, router, k: int = 10,
                          query_chunk: int = 64):

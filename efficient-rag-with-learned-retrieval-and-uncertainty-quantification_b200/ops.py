@@ -279,6 +279,25 @@ def _(bm25_score, bm25_id, dense_score, dense_id, k):
     return bm25_id.new_empty((n_q, k)), f, f.clone(), f.clone()
 
 
+@torch.library.custom_op(f"{NS}::retrieval_uncertainty", mutates_args=(), device_types="cuda")
+def retrieval_uncertainty(scores: Tensor, ids: Tensor, lam: float) -> Tensor:
+    """U = std(top-k scores) + lam * (1 - |s_1 - s_k|) per ranked list [B, k] (ids < 0 are padding)."""
+    scores = _need(scores, torch.float32, "scores")
+    ids = _need(ids, torch.int32, "ids")
+    if scores.dim() != 2 or scores.shape != ids.shape:
+        raise ValueError("scores and ids must both be [B, k]")
+    out = torch.empty(scores.shape[0], dtype=torch.float32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        check(lib.ragb_retrieval_uncertainty(_ptr(scores), _ptr(ids), scores.shape[0], scores.shape[1], lam, _ptr(out),
+                                             _stream()))
+    return out
+
+
+@retrieval_uncertainty.register_fake
+def _(scores, ids, lam):
+    return scores.new_empty((scores.shape[0],))
+
+
 # ------------------------------------------------------------------------------------------
 # router
 # ------------------------------------------------------------------------------------------

@@ -136,6 +136,12 @@ int ragb_hybrid_fuse_topk(const float* bm25_score, const int32_t* bm25_id,
                           int32_t* out_id, float* out_bm25, float* out_dense, float* out_hybrid,
                           ragb_stream_t stream);
 
+/* ---- retrieval uncertainty : docs/uncertainty_theory.md:48-56 ("next" row N4) ---------
+ * U = std(s_top-k) + lambda * (1 - |s_1 - s_k|) over the valid entries (id >= 0) of each of
+ * the n_queries ranked lists [n_queries, k]; population std; an empty list gives lambda. */
+int ragb_retrieval_uncertainty(const float* score, const int32_t* id, int32_t n_queries, int32_t k,
+                               double lambda, float* out, ragb_stream_t stream);
+
 /* ---- router gate : RetrievalRouter.forward / hybrid_rerank (rag_uq/router.py:100-202)
  * Inputs bm25 / dense [n_rows, n_cand] fp32.  w1 [hidden,3], b1 [hidden], w2 [hidden],
  * b2 [1], stats [4] = bm25_mean, bm25_std, dense_mean, dense_std - all DEVICE float32

@@ -77,3 +77,11 @@ def merge_topk(parts: Sequence[Sequence[Tuple[int, float]]], k: int) -> List[Tup
     flat = [c for part in parts for c in part]
     flat.sort(key=lambda c: (-c[1], c[0]))
     return flat[:k]
+
+
+def retrieval_uncertainty(scores: Sequence[float], lam: float = 1.0) -> float:
+    """docs/uncertainty_theory.md:48-56: U = std(s_top-k) + lambda * (1 - |s_1 - s_k|)."""
+    if len(scores) == 0:
+        return lam
+    arr = np.asarray(scores, dtype=np.float64)
+    return float(arr.std() + lam * (1.0 - abs(arr.max() - arr.min())))

@@ -304,6 +304,19 @@ def test_hybrid_engine_end_to_end_c1(rq, dev, n_q):
         exact += got == [w[0] for w in want]
         assert set(got) == set(w[0] for w in want) or abs(want[-1][3] - sh[q, len(want) - 1]) < 1e-5
     assert exact >= n_q - 1          # a pool-boundary tie may flip at most very rarely
+    # router-in-the-loop + confidence (run_evaluation.py:165-196) on the same batch
+    torch.manual_seed(7)
+    router = rq.RetrievalRouter().to(dev).eval()
+    with torch.no_grad():
+        res = engine.retrieve_and_rerank(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, pool, mc_samples=10, seed=5)
+    state = {key: v.detach().cpu() for key, v in router.state_dict().items()}
+    ov, oi = router_oracle.hybrid_rerank(torch.tensor(sb), torch.tensor(sd), state, False, k)
+    torch.testing.assert_close(res["fused"].cpu(), ov, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(res["ids"].cpu().numpy(), np.take_along_axis(ids, oi.numpy(), axis=1))
+    for q in range(n_q):
+        valid = [float(v) for v, i in zip(res["fused"][q], res["ids"][q]) if i >= 0]
+        assert float(res["retrieval_uncertainty"][q]) == pytest.approx(dense_fusion.retrieval_uncertainty(valid, 1.0), rel=1e-4, abs=1e-5)
+    assert res["router_confidence"].shape == (n_q,) and bool(((res["router_confidence"] >= 0) & (res["router_confidence"] <= 1)).all())
     # the source passage of every query must be its best dense hit (sanity of the synthetic design)
     ds, di = engine.dense_topk(qb.q_emb, 1)
     assert (di[:, 0].cpu() == qb.source_rows.cpu().to(torch.int32)).float().mean() > 0.95
@@ -620,6 +633,18 @@ def test_incremental_ingest_equals_full_rebuild(rq, dev):
         a, b = index.search(q, 50), fresh.search(q, 50)
         assert [d for d, _ in a] == [d for d, _ in b]
         np.testing.assert_allclose([s for _, s in a], [s for _, s in b], rtol=2e-6)
+
+
+def test_retrieval_uncertainty(rq, dev):
+    g = torch.Generator().manual_seed(9)
+    scores = torch.rand(7, 10, generator=g)
+    ids = torch.arange(70, dtype=torch.int32).view(7, 10)
+    ids[2, 6:] = -1
+    ids[5, :] = -1
+    got = rq.ops.retrieval_uncertainty(scores.to(dev), ids.to(dev), 0.5).cpu()
+    for q in range(7):
+        valid = [float(s) for s, i in zip(scores[q], ids[q]) if i >= 0]
+        assert float(got[q]) == pytest.approx(dense_fusion.retrieval_uncertainty(valid, 0.5), rel=1e-5, abs=1e-6)
 
 
 def test_error_behaviour(rq, dev):
