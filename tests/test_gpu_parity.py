@@ -647,6 +647,56 @@ def test_retrieval_uncertainty(rq, dev):
         assert float(got[q]) == pytest.approx(dense_fusion.retrieval_uncertainty(valid, 0.5), rel=1e-5, abs=1e-6)
 
 
+@pytest.mark.parametrize("n,n_q", [(2_000_000, 256)])
+def test_large_corpus_properties(rq, dev, n, n_q):
+    """Size-independent properties at a corpus the CPU oracle cannot score: the pruned / seeded top-k
+    kernels against the library's own exhaustive score kernels, sortedness, uniqueness, shard invariance."""
+    from rag_uq_b200 import synth
+    k = 50
+    engine, cdf = synth.build_synthetic_engine(n, 768, dev)
+    qb = synth.make_queries(n_q, n, 768, cdf, dev)
+    bs, bi = engine.sparse.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+    ds, di = engine.dense_local_topk(qb.q_emb, k)
+    for score, ids in ((bs, bi), (ds, di)):
+        assert int(ids.min()) >= 0 and int(ids.max()) < n                          # full lists, valid rows
+        assert bool((score[:, :-1] >= score[:, 1:]).all())                          # sorted best first
+        tie = score[:, :-1] == score[:, 1:]
+        assert bool((ids[:, :-1][tie] < ids[:, 1:][tie]).all())                     # ties: lower id first
+        assert all(len(set(r)) == k for r in ids[:8].tolist())                      # no duplicates
+    # exhaustive check on a few queries: top-k of the full score vectors (library sort only as the checker)
+    sub = slice(0, 6)
+    t0, t1 = int(qb.q_off[0]), int(qb.q_off[6])
+    full_b = engine.sparse.scores(qb.q_terms[t0:t1].contiguous(), (qb.q_off[0:7] - t0).contiguous(), qb.max_terms)
+    full_d = rq.ops.dense_scores(engine.passages, qb.q_emb[sub].contiguous())
+    for full, score, ids, tol in ((full_b, bs, bi, 1e-6), (full_d, ds, di, 2e-6)):
+        want_s, want_i = torch.topk(full, k, dim=1)
+        torch.testing.assert_close(score[sub], want_s, rtol=tol, atol=tol)
+        got_at_ids = torch.gather(full, 1, ids[sub].long())
+        torch.testing.assert_close(score[sub], got_at_ids, rtol=tol, atol=tol)      # reported score == score of that row
+        assert (ids[sub].long() == want_i).float().mean() > 0.97                    # identical modulo ties
+    # the source passage is the top dense hit, and its BM25 score is among the query's best
+    assert (di[:, 0].long() == qb.source_rows).float().mean() > 0.95
+    # shard invariance at scale: two row shards with global statistics, merged == unsharded, bit for bit
+    lo, hi = rq.shard_rows(n, 2, 1)
+    vocab = engine.sparse.vocab
+    parts_b, parts_d = [], []
+    shards = []
+    for r in range(2):
+        a, b = rq.shard_rows(n, 2, r)
+        off, tok = synth.doc_tokens(a, b, cdf)
+        shards.append((rq.build_shard(off, tok, vocab, id_base=a), a, b))
+    df = shards[0][0].df + shards[1][0].df
+    total = int(shards[0][0].doc_len.sum() + shards[1][0].doc_len.sum())
+    for sp, a, b in shards:
+        sp.finalize(df, n, total)
+        parts_b.append(sp.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k))
+        parts_d.append(rq.ops.dense_mma_topk(engine.passages[a:b].contiguous(), qb.q_emb, k, a, 2))
+    ms, mi = rq.ops.topk_merge(torch.stack([p[0] for p in parts_b], 1), torch.stack([p[1] for p in parts_b], 1), k)
+    assert torch.equal(mi, bi) and torch.equal(ms, bs)
+    ms, mi = rq.ops.topk_merge(torch.stack([p[0] for p in parts_d], 1), torch.stack([p[1] for p in parts_d], 1), k)
+    assert torch.equal(mi, di) and torch.equal(ms, ds)
+
+
 def test_error_behaviour(rq, dev):
     with pytest.raises(ValueError):
         rq.ops.topk_rows(torch.zeros(2, 10000, device=dev), 1000)           # k beyond RAGB_MAX_TOPK on a long row
