@@ -466,6 +466,230 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
   }
 }
 
+// =============================================================================================
+// variant 3: CTA pair (cta_group::2).  Two blocks of a cluster form one 256 x 256 MMA tile: each
+// holds the A rows of ITS 128-query slab and HALF of the passage tile (128 rows) in shared memory,
+// the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256), each block's TMEM receives
+// its 128 x 256 half of the accumulator.  Per SM this moves 32 KB per k-block instead of 48 KB, so
+// the same shared memory holds a 7-deep ring instead of 4 and L2 -> SM traffic per FLOP drops by a
+// third.  TMA loads of both blocks complete on the LEADER's full barrier; tcgen05.commit multicasts
+// "stage free" / "accumulator ready" to both blocks; both epilogues release the accumulator with a
+// remote arrive on the leader's barrier.
+// =============================================================================================
+constexpr uint32_t MM_PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
+constexpr int MM2_BN = 256;
+constexpr int MM2_STAGE_BYTES = MM_A_STAGE_BYTES + (MM2_BN / 2) * MM_BK * 2;  // 32 KB per block
+
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                                                                       const __grid_constant__ CUtensorMap tmap_e,
+                                                                       const MmaArgs a) {
+  constexpr int BN = MM2_BN;
+  constexpr uint32_t IDESC = make_idesc(2 * MM_BM, BN);
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1;                 // cluster index
+  const int n_pairs_slab = (a.n_slabs + 1) >> 1;    // slab pairs per passage group
+  // every block of the grid belongs to a live pair (the host sizes the grid exactly)
+  const int slab = 2 * (pair % n_pairs_slab) + static_cast<int>(cta_rank);
+  const int group = pair / n_pairs_slab;
+  const int tile_begin = min(a.n_tiles, group * a.tiles_per_group);
+  const int tile_end = min(a.n_tiles, tile_begin + a.tiles_per_group);
+  const int n_kb = a.dim / MM_BK;
+
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* stages = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* lists = a.lists + static_cast<size_t>(blockIdx.x) * MM_BM * (32 * KPL + 1);
+  __shared__ __align__(8) uint64_t bar_full[MM_MAX_STAGES];   // used in the leader only
+  __shared__ __align__(8) uint64_t bar_empty[MM_MAX_STAGES];  // one per block, fed by the multicast commit
+  __shared__ __align__(8) uint64_t bar_tmem_full[2];          // one per block
+  __shared__ __align__(8) uint64_t bar_tmem_empty[2];         // leader only: 8 epilogue warps arrive
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.n_stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tmem_full[b]), 1);
+      mbar_init(smem_u32(&bar_tmem_empty[b]), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_e)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both blocks initialised, TMEM allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // ================= TMA producer (both blocks; bytes complete on the leader's barrier) =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      volatile int* group_progress = a.progress + group * n_pairs_slab;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int it = tile - tile_begin;
+        if (leader && n_pairs_slab > 1 && (it & 3) == 0) {   // soft pacing between the pairs of a group
+          group_progress[pair % n_pairs_slab] = it;
+          for (int spins = 0; spins < 256; ++spins) {
+            int slowest = it;
+            for (int sl = 0; sl < n_pairs_slab; ++sl) slowest = min(slowest, group_progress[sl]);
+            if (it - slowest <= MM_PACE_TILES) break;
+            __nanosleep(256);
+          }
+        }
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+          const uint32_t leader_full = smem_u32(&bar_full[stage]) & MM_PEER_MASK;
+          unsigned char* st = stages + static_cast<size_t>(stage) * MM2_STAGE_BYTES;
+          if (leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * MM2_STAGE_BYTES);
+          tma_load_2d_2sm(smem_u32(st), &tmap_q, leader_full, kb * MM_BK, slab * MM_BM);
+          tma_load_2d_2sm(smem_u32(st + MM_A_STAGE_BYTES), &tmap_e, leader_full, kb * MM_BK,
+                          tile * BN + static_cast<int>(cta_rank) * (BN / 2));
+          if (++stage == static_cast<uint32_t>(a.n_stages)) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      if (leader && n_pairs_slab > 1) group_progress[pair % n_pairs_slab] = 0x7fffffff;
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: one thread of the leader drives both tensor cores =================
+    if (leader && lane == 0) {
+      uint32_t stage = 0, phase = 0, buf = 0, acc_phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        mbar_wait(smem_u32(&bar_tmem_empty[buf]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          unsigned char* st = stages + static_cast<size_t>(stage) * MM2_STAGE_BYTES;
+          const uint32_t a_addr = smem_u32(st);
+          const uint32_t b_addr = smem_u32(st + MM_A_STAGE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < MM_BK / 16; ++kk)
+            tc_mma_ss_pair(d_tmem, make_sw128_desc(a_addr + kk * 32), make_sw128_desc(b_addr + kk * 32), IDESC,
+                           (kb | kk) != 0 ? 1u : 0u);
+          tc_commit_pair(smem_u32(&bar_empty[stage]));   // frees the stage in BOTH blocks
+          if (++stage == static_cast<uint32_t>(a.n_stages)) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit_pair(smem_u32(&bar_tmem_full[buf]));   // accumulator ready in BOTH blocks
+        buf ^= 1;
+        if (buf == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================= epilogue: thread owns one query of this block's slab =================
+    const int quad = warp & 3;
+    const int tslot = quad * 32 + lane;
+    const int query = slab * MM_BM + tslot;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    constexpr int LIST_CAP = 32 * KPL;
+    constexpr int LIST_STRIDE = LIST_CAP + 1;
+    uint64_t* warp_lists = lists + static_cast<size_t>(quad) * 32 * LIST_STRIDE;
+    uint64_t* my_list = warp_lists + lane * LIST_STRIDE;
+    ListState st{0, -INFINITY, 0ull};
+    uint32_t buf = 0, acc_phase = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_phase);
+      tc_fence_after();
+      const int64_t row0 = static_cast<int64_t>(tile) * BN;
+      const int valid = static_cast<int>(min(static_cast<int64_t>(BN), a.n_rows - row0));
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        tc_ld32(tmem_base + lane_addr + buf * BN + c * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float m = __uint_as_float(v[0]);
+#pragma unroll
+        for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+        if (__any_sync(0xffffffffu, m >= st.thr_score)) {
+          const int32_t id0 = static_cast<int32_t>(a.id_base + row0) + c * 32;
+          const int lim = valid - c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float s = __uint_as_float(v[i]);
+            if (s >= st.thr_score && i < lim) {
+              const uint64_t key = make_key(s, id0 + i);
+              if (key > st.thr_key) my_list[st.cnt++] = key;
+            }
+            const unsigned full = __ballot_sync(0xffffffffu, st.cnt == LIST_CAP);
+            if (full) st = compact_lists<KPL>(warp_lists, full, lane, a.k, st);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(smem_u32(&bar_tmem_empty[buf]) & MM_PEER_MASK);  // leader's barrier
+      buf ^= 1;
+      if (buf == 0) acc_phase ^= 1;
+    }
+    st = compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, st);
+    const int cnt = st.cnt;
+    if (query < a.n_queries) {
+      uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.n_groups + group) * a.k;
+      for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? __ldcg(reinterpret_cast<const unsigned long long*>(my_list + j)) : 0ull;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody frees TMEM or exits while the peer may still touch this block
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int KPL>
+static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
+                           int64_t id_base, uint64_t* part, int* progress, uint64_t* lists, int stage_limit,
+                           int* n_groups_out, cudaStream_t stream);
+
 // ---- host ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -542,6 +766,61 @@ static int launch_mma(const void* passages, int64_t n_rows, int dim, const void*
   return RAGB_OK;
 }
 
+template <int KPL>
+static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
+                           int64_t id_base, uint64_t* part, int* progress, uint64_t* lists, int stage_limit,
+                           int* n_groups_out, cudaStream_t stream) {
+  CUtensorMap map_q, map_e;
+  int rc = make_map(&map_q, queries, n_queries, dim, MM_BM);
+  if (rc != RAGB_OK) return rc;
+  rc = make_map(&map_e, passages, n_rows, dim, MM2_BN / 2);   // each block loads half a passage tile
+  if (rc != RAGB_OK) return rc;
+  MmaArgs a{};
+  a.queries = static_cast<const uint4*>(queries);
+  a.n_rows = n_rows;
+  a.id_base = id_base;
+  a.n_queries = n_queries;
+  a.dim = dim;
+  a.k = k;
+  a.n_slabs = (n_queries + MM_BM - 1) / MM_BM;
+  const int n_pairs_slab = (a.n_slabs + 1) / 2;
+  const int clusters = device_sm_count() / 2;
+  RAGB_REQUIRE(n_pairs_slab <= clusters, RAGB_ELIMIT, "ragb_dense_mma_topk: n_queries=%d needs more than %d CTA pairs",
+               n_queries, clusters);
+  a.n_tiles = static_cast<int>(ceil_div64(n_rows, MM2_BN));
+  a.n_groups = clusters / n_pairs_slab;
+  if (a.n_groups > a.n_tiles) a.n_groups = a.n_tiles;
+  a.tiles_per_group = (a.n_tiles + a.n_groups - 1) / a.n_groups;
+  a.n_groups = (a.n_tiles + a.tiles_per_group - 1) / a.tiles_per_group;
+  a.part_keys = part;
+  a.progress = progress;
+  a.lists = lists;
+  RAGB_CUDA(cudaMemsetAsync(progress, 0, MM_PROGRESS_BYTES, stream));
+  int stages = (MM_MAX_SMEM - 1024 - 256) / MM2_STAGE_BYTES;
+  if (stage_limit > 0 && stages > stage_limit) stages = stage_limit;
+  if (stages > MM_MAX_STAGES) stages = MM_MAX_STAGES;
+  a.n_stages = stages;
+  const size_t smem = 1024 + static_cast<size_t>(stages) * MM2_STAGE_BYTES;
+  RAGB_CUDA(cudaFuncSetAttribute(dense_mma_pair_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * n_pairs_slab * a.n_groups);
+  cfg.blockDim = dim3(MM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RAGB_CUDA(cudaLaunchKernelEx(&cfg, dense_mma_pair_kernel<KPL>, map_q, map_e, a));
+  RAGB_AFTER_LAUNCH(1);
+  *n_groups_out = a.n_groups;
+  return RAGB_OK;
+}
+
 static size_t mma_list_bytes(int k) {
   const int cap = k <= 16 ? 32 : (k <= 50 ? 64 : 128);
   return static_cast<size_t>(148) * MM_BM * (cap + 1) * sizeof(uint64_t);
@@ -571,7 +850,7 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
   RAGB_REQUIRE(dim >= MM_BK && dim % MM_BK == 0, RAGB_EINVAL, "ragb_dense_mma_topk: dim=%d must be a multiple of %d", dim,
                MM_BK);
   RAGB_REQUIRE(k > 0 && k <= 100, RAGB_ELIMIT, "ragb_dense_mma_topk: k=%d outside [1,100]", k);
-  RAGB_REQUIRE(variant >= 0 && variant <= 2, RAGB_EINVAL, "ragb_dense_mma_topk: variant must be 0, 1 or 2");
+  RAGB_REQUIRE(variant >= 0 && variant <= 3, RAGB_EINVAL, "ragb_dense_mma_topk: variant must be 0, 1, 2 or 3");
   RAGB_REQUIRE(variant != 1 || dim <= 768, RAGB_ELIMIT, "ragb_dense_mma_topk: variant 1 keeps the query slab in TMEM and needs dim <= 768");
   RAGB_REQUIRE(id_base >= 0 && id_base + n_rows < (1ll << 31), RAGB_ELIMIT, "ragb_dense_mma_topk: ids must fit int32");
   RAGB_REQUIRE(workspace_bytes >= ragb_dense_mma_workspace_bytes(n_queries, k), RAGB_ENOSPC,
@@ -595,10 +874,14 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
     if (k <= 16) rc = launch_mma<64, true, 1>(RAGB_MMA_ARGS);
     else if (k <= 50) rc = launch_mma<64, true, 2>(RAGB_MMA_ARGS);
     else rc = launch_mma<64, true, 4>(RAGB_MMA_ARGS);
-  } else {
+  } else if (variant == 2 || n_queries <= MM_BM) {   // a lone slab has no partner for a CTA pair
     if (k <= 16) rc = launch_mma<256, false, 1>(RAGB_MMA_ARGS);
     else if (k <= 50) rc = launch_mma<256, false, 2>(RAGB_MMA_ARGS);
     else rc = launch_mma<256, false, 4>(RAGB_MMA_ARGS);
+  } else {
+    if (k <= 16) rc = launch_mma_pair<1>(RAGB_MMA_ARGS);
+    else if (k <= 50) rc = launch_mma_pair<2>(RAGB_MMA_ARGS);
+    else rc = launch_mma_pair<4>(RAGB_MMA_ARGS);
   }
 #undef RAGB_MMA_ARGS
   if (rc != RAGB_OK) return rc;

@@ -104,7 +104,8 @@ int ragb_dense_gemv_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
  * multiple of 128 (queries_bf16 must hold n_queries rows; padding rows are zero-filled
  * by TMA out-of-bounds handling).  variant: 0 = A (queries) and B (passages) both
  * streamed through shared memory, 128-passage tiles; 1 = query slab resident in TMEM;
- * 2 = as 0 with 256-passage tiles.  */
+ * 2 = as 0 with 256-passage tiles; 3 = CTA pairs (tcgen05 cta_group::2, 256 queries x 256
+ * passages per MMA, falls back to 2 for a single slab).  */
 size_t ragb_dense_mma_workspace_bytes(int32_t n_queries, int32_t k);
 int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
                         const void* queries_bf16, int32_t n_queries, int32_t k, int64_t id_base,

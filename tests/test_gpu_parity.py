@@ -233,7 +233,7 @@ def test_dense_gemv_topk(rq, dev, n, b, k, dim):
     np.testing.assert_allclose(full, want, atol=2e-6)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("n,b,k,dim", [(10_000, 64, 10, 768), (4096, 128, 50, 768), (33_333, 200, 10, 768),
                                        (1000, 9, 100, 768), (2048, 300, 50, 128), (127, 130, 10, 768)])
 def test_dense_mma_topk(rq, dev, variant, n, b, k, dim):
