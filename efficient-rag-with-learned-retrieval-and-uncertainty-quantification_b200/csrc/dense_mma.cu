@@ -5,11 +5,12 @@
 // Replaces DenseIndex.search -> collection.query (rag_uq/streaming_index.py:353-370) for
 // query batches; the reference answers one query at a time through ChromaDB's HNSW.
 //
-// Roles (192 threads, 1 block per SM, persistent):
+// Roles (320 threads, 1 block per SM, persistent):
 //   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles into a ring of
 //               shared-memory stages, completion on mbarriers.
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M = 128 queries).
-//   warps 2..5  epilogue: tcgen05.ld of the accumulator; THREAD r OWNS QUERY r of the
+//   warps 2..9  epilogue (two warps per TMEM lane quadrant, one per half of the accumulator
+//               columns): tcgen05.ld of the accumulator; THREAD r OWNS QUERY r of the
 //               slab for the whole kernel, so its admission threshold is a register and
 //               the common case is "32 scores, one max, one compare".  Survivors are
 //               appended to the thread's private list (global workspace, L2-resident); a full
@@ -37,7 +38,7 @@ namespace ragb {
 
 constexpr int MM_BM = 128;
 constexpr int MM_BK = 64;
-constexpr int MM_THREADS = 192;
+constexpr int MM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MM_A_STAGE_BYTES = MM_BM * MM_BK * 2;  // 16 KB
 constexpr int MM_MAX_STAGES = 16;
 constexpr int MM_MAX_SMEM = 227 * 1024;
@@ -56,7 +57,7 @@ struct MmaArgs {
   int tiles_per_group;
   int n_tiles;
   int n_stages;
-  uint64_t* part_keys;  // [n_queries, n_groups, k]
+  uint64_t* part_keys;  // [n_queries, n_groups, 2 column halves, k]
   int* progress;        // [n_groups, n_slabs] tiles issued so far (soft pacing between the slabs of a group)
   uint64_t* lists;      // [blocks, 128, list capacity + 1] per-thread candidate lists
   int stage_limit;
@@ -244,6 +245,80 @@ __device__ __noinline__ ListState compact_lists(uint64_t* warp_lists, unsigned l
   return st;
 }
 
+// Epilogue shared by the 1-CTA and the CTA-pair kernel.  8 warps: two per TMEM lane quadrant, each
+// scanning one half of the accumulator columns (a single warp per scheduler could not keep up with
+// the tensor core at k = 50: measured +3 ms).  Thread (quadrant, lane) owns query row 32*quadrant+lane
+// of the slab for the whole kernel and keeps its candidates of "its" column half in a private list.
+template <int BN, int KPL>
+__device__ __forceinline__ void epilogue_scan(const MmaArgs& a, const uint32_t tmem_base, const uint32_t acc_col0,
+                                              uint64_t* block_lists, const int warp, const int lane, const int slab,
+                                              const int group, const int tile_begin, const int tile_end,
+                                              uint64_t* bar_tmem_full, const uint32_t empty_addr0,
+                                              const uint32_t empty_addr1, const bool remote_arrive) {
+  constexpr int LIST_CAP = 32 * KPL;
+  constexpr int LIST_STRIDE = LIST_CAP + 1;
+  constexpr int HALF_CHUNKS = BN / 64;  // 32-column chunks per half
+  const int quad = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const int query = slab * MM_BM + quad * 32 + lane;
+  const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+  uint64_t* warp_lists = block_lists + static_cast<size_t>(half * 4 + quad) * 32 * LIST_STRIDE;
+  uint64_t* my_list = warp_lists + lane * LIST_STRIDE;
+  ListState st{0, -INFINITY, 0ull};
+  uint32_t buf = 0, acc_phase = 0;
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_phase);
+    tc_fence_after();
+    const int64_t row0 = static_cast<int64_t>(tile) * BN;
+    const int valid = static_cast<int>(min(static_cast<int64_t>(BN), a.n_rows - row0));  // rows of this tile that exist
+#pragma unroll 1
+    for (int cc = 0; cc < HALF_CHUNKS; ++cc) {
+      const int c = half * HALF_CHUNKS + cc;
+      uint32_t v[32];
+      __syncwarp();
+      tc_ld32(tmem_base + lane_addr + acc_col0 + buf * BN + c * 32, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float m = __uint_as_float(v[0]);
+#pragma unroll
+      for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+      if (__any_sync(0xffffffffu, m >= st.thr_score)) {
+        // room for a whole chunk is guaranteed up front, so the admission loop has no votes in it
+        const unsigned full = __ballot_sync(0xffffffffu, st.cnt > LIST_CAP - 32);
+        if (full) st = compact_lists<KPL>(warp_lists, full, lane, a.k, st);
+        if (m >= st.thr_score) {
+          const int32_t id0 = static_cast<int32_t>(a.id_base + row0) + c * 32;
+          const int lim = valid - c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float s = __uint_as_float(v[i]);
+            if (s >= st.thr_score && i < lim) {
+              const uint64_t key = make_key(s, id0 + i);
+              if (key > st.thr_key) my_list[st.cnt++] = key;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t bar = buf == 0 ? empty_addr0 : empty_addr1;
+      if (remote_arrive)
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+      else
+        mbar_arrive(bar);
+    }
+    buf ^= 1;
+    if (buf == 0) acc_phase ^= 1;
+  }
+  st = compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, st);
+  const int cnt = st.cnt;
+  if (query < a.n_queries) {
+    uint64_t* dst = a.part_keys + ((static_cast<int64_t>(query) * a.n_groups + group) * 2 + half) * a.k;
+    for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? __ldcg(reinterpret_cast<const unsigned long long*>(my_list + j)) : 0ull;
+  }
+}
+
 template <int BN, bool A_IN_TMEM, int KPL>
 __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                   const __grid_constant__ CUtensorMap tmap_e,
@@ -267,7 +342,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
   unsigned char* stages = base;
   // candidate lists live in the caller's workspace (L2-resident, touched ~once per thousand scores), so
   // shared memory holds only the operand ring and blocks of other kernels can share the SM
-  uint64_t* lists = a.lists + static_cast<size_t>(blockIdx.x) * MM_BM * (32 * KPL + 1);
+  uint64_t* lists = a.lists + static_cast<size_t>(blockIdx.x) * 2 * MM_BM * (32 * KPL + 1);
   __shared__ __align__(8) uint64_t bar_full[MM_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[MM_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
@@ -284,7 +359,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tmem_full[b]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[b]), 4);
+      mbar_init(smem_u32(&bar_tmem_empty[b]), 8);
     }
     mbar_init(smem_u32(&bar_a_ready), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -383,17 +458,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
     }
   } else {
     // ================= epilogue: thread owns one query =================
-    const int quad = warp & 3;
-    const int tslot = quad * 32 + lane;  // TMEM lane == query row inside the slab
-    const int query = slab * MM_BM + tslot;
-    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    constexpr int LIST_CAP = 32 * KPL;
-    constexpr int LIST_STRIDE = LIST_CAP + 1;
-    uint64_t* warp_lists = lists + static_cast<size_t>(quad) * 32 * LIST_STRIDE;
-    uint64_t* my_list = warp_lists + lane * LIST_STRIDE;
-
-    if (A_IN_TMEM) {
+    if (A_IN_TMEM && warp < 6) {
       // store the thread's query row (packed bf16 pairs, K ascending) into its TMEM lane
+      const int quad = warp & 3;
+      const int query = slab * MM_BM + quad * 32 + lane;
+      const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
       const uint4* qrow = a.queries + static_cast<int64_t>(query) * (a.dim / 8);
       for (int c = 0; c < a_cols / 32; ++c) {
         uint32_t v[32];
@@ -412,50 +481,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_a_ready));
     }
-
-    ListState st{0, -INFINITY, 0ull};
-    uint32_t buf = 0, acc_phase = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_phase);
-      tc_fence_after();
-      const int64_t row0 = static_cast<int64_t>(tile) * BN;
-      const int valid = static_cast<int>(min(static_cast<int64_t>(BN), a.n_rows - row0));  // rows of this tile that exist
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tc_ld32(tmem_base + lane_addr + acc_col0 + buf * BN + c * 32, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float m = __uint_as_float(v[0]);
-#pragma unroll
-        for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-        if (__any_sync(0xffffffffu, m >= st.thr_score)) {
-          const int32_t id0 = static_cast<int32_t>(a.id_base + row0) + c * 32;
-          const int lim = valid - c * 32;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float s = __uint_as_float(v[i]);
-            if (s >= st.thr_score && i < lim) {
-              const uint64_t key = make_key(s, id0 + i);
-              if (key > st.thr_key) my_list[st.cnt++] = key;
-            }
-            const unsigned full = __ballot_sync(0xffffffffu, st.cnt == LIST_CAP);
-            if (full) st = compact_lists<KPL>(warp_lists, full, lane, a.k, st);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
-      buf ^= 1;
-      if (buf == 0) acc_phase ^= 1;
-    }
-    st = compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, st);
-    const int cnt = st.cnt;
-    if (query < a.n_queries) {
-      uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.n_groups + group) * a.k;
-      for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? __ldcg(reinterpret_cast<const unsigned long long*>(my_list + j)) : 0ull;
-    }
+    epilogue_scan<BN, KPL>(a, tmem_base, acc_col0, lists, warp, lane, slab, group, tile_begin, tile_end, bar_tmem_full,
+                           smem_u32(&bar_tmem_empty[0]), smem_u32(&bar_tmem_empty[1]), false);
   }
 
   tc_fence_before();
@@ -529,7 +556,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_pair_kernel(const __g
 
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* stages = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* lists = a.lists + static_cast<size_t>(blockIdx.x) * MM_BM * (32 * KPL + 1);
+  uint64_t* lists = a.lists + static_cast<size_t>(blockIdx.x) * 2 * MM_BM * (32 * KPL + 1);
   __shared__ __align__(8) uint64_t bar_full[MM_MAX_STAGES];   // used in the leader only
   __shared__ __align__(8) uint64_t bar_empty[MM_MAX_STAGES];  // one per block, fed by the multicast commit
   __shared__ __align__(8) uint64_t bar_tmem_full[2];          // one per block
@@ -544,7 +571,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_pair_kernel(const __g
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tmem_full[b]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[b]), 8);
+      mbar_init(smem_u32(&bar_tmem_empty[b]), 16);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_e)) : "memory");
@@ -624,57 +651,9 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_pair_kernel(const __g
     }
   } else {
     // ================= epilogue: thread owns one query of this block's slab =================
-    const int quad = warp & 3;
-    const int tslot = quad * 32 + lane;
-    const int query = slab * MM_BM + tslot;
-    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    constexpr int LIST_CAP = 32 * KPL;
-    constexpr int LIST_STRIDE = LIST_CAP + 1;
-    uint64_t* warp_lists = lists + static_cast<size_t>(quad) * 32 * LIST_STRIDE;
-    uint64_t* my_list = warp_lists + lane * LIST_STRIDE;
-    ListState st{0, -INFINITY, 0ull};
-    uint32_t buf = 0, acc_phase = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_phase);
-      tc_fence_after();
-      const int64_t row0 = static_cast<int64_t>(tile) * BN;
-      const int valid = static_cast<int>(min(static_cast<int64_t>(BN), a.n_rows - row0));
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tc_ld32(tmem_base + lane_addr + buf * BN + c * 32, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float m = __uint_as_float(v[0]);
-#pragma unroll
-        for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-        if (__any_sync(0xffffffffu, m >= st.thr_score)) {
-          const int32_t id0 = static_cast<int32_t>(a.id_base + row0) + c * 32;
-          const int lim = valid - c * 32;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float s = __uint_as_float(v[i]);
-            if (s >= st.thr_score && i < lim) {
-              const uint64_t key = make_key(s, id0 + i);
-              if (key > st.thr_key) my_list[st.cnt++] = key;
-            }
-            const unsigned full = __ballot_sync(0xffffffffu, st.cnt == LIST_CAP);
-            if (full) st = compact_lists<KPL>(warp_lists, full, lane, a.k, st);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(smem_u32(&bar_tmem_empty[buf]) & MM_PEER_MASK);  // leader's barrier
-      buf ^= 1;
-      if (buf == 0) acc_phase ^= 1;
-    }
-    st = compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, st);
-    const int cnt = st.cnt;
-    if (query < a.n_queries) {
-      uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.n_groups + group) * a.k;
-      for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? __ldcg(reinterpret_cast<const unsigned long long*>(my_list + j)) : 0ull;
-    }
+    epilogue_scan<MM2_BN, KPL>(a, tmem_base, 0u, lists, warp, lane, slab, group, tile_begin, tile_end, bar_tmem_full,
+                               smem_u32(&bar_tmem_empty[0]) & MM_PEER_MASK, smem_u32(&bar_tmem_empty[1]) & MM_PEER_MASK,
+                               true);   // both blocks release the accumulator on the LEADER's barrier
   }
 
   tc_fence_before();
@@ -821,9 +800,9 @@ static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const 
   return RAGB_OK;
 }
 
+static int mma_list_kpl(int k) { return k <= 32 ? 2 : (k <= 96 ? 4 : 8); }  // capacity 32*KPL >= k + 32
 static size_t mma_list_bytes(int k) {
-  const int cap = k <= 16 ? 32 : (k <= 50 ? 64 : 128);
-  return static_cast<size_t>(148) * MM_BM * (cap + 1) * sizeof(uint64_t);
+  return static_cast<size_t>(148) * 2 * MM_BM * (32 * mma_list_kpl(k) + 1) * sizeof(uint64_t);
 }
 
 }  // namespace ragb
@@ -834,7 +813,7 @@ extern "C" {
 
 size_t ragb_dense_mma_workspace_bytes(int32_t n_queries, int32_t k) {
   if (n_queries <= 0 || k <= 0) return 0;
-  return MM_PROGRESS_BYTES + mma_list_bytes(k) + static_cast<size_t>(n_queries) * 148 * k * sizeof(uint64_t);
+  return MM_PROGRESS_BYTES + mma_list_bytes(k) + static_cast<size_t>(n_queries) * 148 * 2 * k * sizeof(uint64_t);
 }
 
 int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
@@ -864,28 +843,30 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
   }();
   int n_groups = 0;
   int rc;
-  // list capacity per query thread: 32 (k <= 16), 64 (k <= 50) or 128 (k <= 100) slots
+  // list capacity per query thread: 64 (k <= 32), 128 (k <= 96) or 256 slots: always k + 32 or more
 #define RAGB_MMA_ARGS passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, progress, lists, stage_limit, &n_groups, stream
+#define RAGB_MMA_DISPATCH(FN, ...)                                   \
+  do {                                                              \
+    const int kpl = mma_list_kpl(k);                                \
+    if (kpl == 2) rc = FN<__VA_ARGS__ 2>(RAGB_MMA_ARGS);            \
+    else if (kpl == 4) rc = FN<__VA_ARGS__ 4>(RAGB_MMA_ARGS);       \
+    else rc = FN<__VA_ARGS__ 8>(RAGB_MMA_ARGS);                     \
+  } while (0)
+#define RAGB_COMMA ,
   if (variant == 0) {
-    if (k <= 16) rc = launch_mma<128, false, 1>(RAGB_MMA_ARGS);
-    else if (k <= 50) rc = launch_mma<128, false, 2>(RAGB_MMA_ARGS);
-    else rc = launch_mma<128, false, 4>(RAGB_MMA_ARGS);
+    RAGB_MMA_DISPATCH(launch_mma, 128 RAGB_COMMA false RAGB_COMMA);
   } else if (variant == 1) {
-    if (k <= 16) rc = launch_mma<64, true, 1>(RAGB_MMA_ARGS);
-    else if (k <= 50) rc = launch_mma<64, true, 2>(RAGB_MMA_ARGS);
-    else rc = launch_mma<64, true, 4>(RAGB_MMA_ARGS);
+    RAGB_MMA_DISPATCH(launch_mma, 64 RAGB_COMMA true RAGB_COMMA);
   } else if (variant == 2 || n_queries <= MM_BM) {   // a lone slab has no partner for a CTA pair
-    if (k <= 16) rc = launch_mma<256, false, 1>(RAGB_MMA_ARGS);
-    else if (k <= 50) rc = launch_mma<256, false, 2>(RAGB_MMA_ARGS);
-    else rc = launch_mma<256, false, 4>(RAGB_MMA_ARGS);
+    RAGB_MMA_DISPATCH(launch_mma, 256 RAGB_COMMA false RAGB_COMMA);
   } else {
-    if (k <= 16) rc = launch_mma_pair<1>(RAGB_MMA_ARGS);
-    else if (k <= 50) rc = launch_mma_pair<2>(RAGB_MMA_ARGS);
-    else rc = launch_mma_pair<4>(RAGB_MMA_ARGS);
+    RAGB_MMA_DISPATCH(launch_mma_pair, );
   }
+#undef RAGB_MMA_DISPATCH
+#undef RAGB_COMMA
 #undef RAGB_MMA_ARGS
   if (rc != RAGB_OK) return rc;
-  return launch_merge_keys(part, n_queries, n_groups, k, k, out_score, out_id, stream);
+  return launch_merge_keys(part, n_queries, n_groups * 2, k, k, out_score, out_id, stream);
 }
 
 }  // extern "C"
