@@ -41,7 +41,7 @@ def parse_args():
     p.add_argument("--batch", type=int, default=1024)
     p.add_argument("--k", type=int, default=10)
     p.add_argument("--pool", type=int, default=50)
-    p.add_argument("--variant", type=int, default=int(os.environ.get("RAGB_MMA_VARIANT", "2")))
+    p.add_argument("--variant", type=int, default=int(os.environ.get("RAGB_MMA_VARIANT", "3")))
     p.add_argument("--cpu-sample-docs", type=int, default=20_000)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--overlap", action="store_true",

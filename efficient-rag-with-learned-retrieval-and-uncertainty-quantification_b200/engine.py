@@ -58,7 +58,7 @@ def gather_candidates(score: Tensor, ids: Tensor, group=None) -> Tuple[Tensor, T
 
 class HybridEngine:
     def __init__(self, sparse: Optional[SparseShard], passages: Optional[Tensor], id_base: int = 0, group=None,
-                 mma_variant: int = 2):
+                 mma_variant: int = 3):
         if passages is not None:
             if passages.dtype != torch.bfloat16 or passages.dim() != 2:
                 raise TypeError("passages must be a bf16 [rows, dim] tensor")

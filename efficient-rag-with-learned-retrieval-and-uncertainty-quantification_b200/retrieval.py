@@ -193,7 +193,7 @@ class DenseIndex:
 
     def __init__(self, collection_name: str = "rag_documents", persist_directory: str = "./data/chroma_db",
                  embedding_model: str = "nomic-embed-text", chroma_host: Optional[str] = None, chroma_port: int = 8000,
-                 embed_fn: Optional[Callable[[List[str]], Any]] = None, device=None, mma_variant: int = 2):
+                 embed_fn: Optional[Callable[[List[str]], Any]] = None, device=None, mma_variant: int = 3):
         self.collection_name = collection_name
         self.persist_directory = persist_directory
         self.embedding_model = embedding_model
@@ -308,7 +308,7 @@ class HybridRetriever:
     def __init__(self, bm25_persist_path: Optional[str] = "./data/bm25_index.pkl",
                  chroma_persist_path: str = "./data/chroma_db", chroma_host: Optional[str] = None,
                  embedding_model: str = "nomic-embed-text", embed_fn: Optional[Callable] = None, device=None,
-                 mma_variant: int = 2):
+                 mma_variant: int = 3):
         self.bm25_index = BM25Index(persist_path=bm25_persist_path, device=device)
         self.dense_index = DenseIndex(persist_directory=chroma_persist_path,
                                       chroma_host=chroma_host or os.environ.get("CHROMA_HOST"),

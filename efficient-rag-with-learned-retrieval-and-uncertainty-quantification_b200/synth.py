@@ -143,7 +143,7 @@ def make_queries(n_queries: int, n_passages: int, dim: int, cdf: Tensor, device,
 
 
 def build_synthetic_engine(n_passages: int, dim: int, device, rank: int = 0, world: int = 1, group=None,
-                           block_docs: int = 250_000, mma_variant: int = 2, with_sparse: bool = True,
+                           block_docs: int = 250_000, mma_variant: int = 3, with_sparse: bool = True,
                            with_dense: bool = True):
     """Generate this rank's row shard of the synthetic corpus and wrap it in a HybridEngine.
 
