@@ -73,7 +73,9 @@ struct Bm25Args {
   int k;
   int capacity;
   uint64_t* part_keys;  // [queries, stripes, k]            (top-k mode)
-  float* out_scores;    // [queries, n_docs]                (dense mode)
+  float* out_scores;    // [queries, out_ld]                (dense mode)
+  int64_t out_ld;       // row stride of out_scores in floats (>= n_docs); tiled: query rows per tile
+  int out_tiled;        // 1: out_scores[(d / 256) * out_ld + q][d % 256] (256-document tiles, query rows inside a tile)
   const uint8_t* dense_tf;   // [n_dense, dense_stride] tf of the most frequent terms, 0 = absent
   const int32_t* dense_terms;  // [n_dense] term id of each row
   int64_t dense_stride;      // multiple of BM_RANGE, >= n_docs
@@ -434,10 +436,19 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         ac[4] += r1.x; ac[5] += r1.y; ac[6] += r1.z; ac[7] += r1.w;
       }
       if (DENSE_OUT) {
-        float* dst = a.out_scores + static_cast<int64_t>(q) * a.n_docs + d0 + j0;
+        // d0 is a multiple of BM_RANGE = 256 = the tile width, so a warp range is one row segment of one tile
+        float* dst = a.out_tiled
+                         ? a.out_scores + (static_cast<int64_t>(d0 / BM_RANGE) * a.out_ld + q) * BM_RANGE + j0
+                         : a.out_scores + static_cast<int64_t>(q) * a.out_ld + d0 + j0;
+        if (cnt == BM_RANGE && (a.out_tiled || (a.out_ld & 3) == 0) && (reinterpret_cast<uintptr_t>(a.out_scores) & 15) == 0) {
+          // d0 and j0 are multiples of 8: two 128-bit stores per lane, 32 contiguous bytes
+          reinterpret_cast<float4*>(dst)[0] = make_float4(ac[0], ac[1], ac[2], ac[3]);
+          reinterpret_cast<float4*>(dst)[1] = make_float4(ac[4], ac[5], ac[6], ac[7]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if ((j0 + j) < cnt) dst[j] = ac[j];
+          for (int j = 0; j < 8; ++j)
+            if ((j0 + j) < cnt) dst[j] = ac[j];
+        }
       } else {
         // ---- warp-private selection: no barrier; in steady state 8 compares and one vote per range
         bool hot = false;
@@ -804,14 +815,17 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
 int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
                      const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
                      const int32_t* dense_terms, int32_t n_dense, const int32_t* q_terms, const int32_t* q_off,
-                     int32_t n_queries, int32_t max_query_terms, int64_t n_docs, float* out_scores,
-                     ragb_stream_t stream_) {
+                     int32_t n_queries, int32_t max_query_terms, int64_t n_docs, float* out_scores, int64_t out_ld,
+                     int32_t tiled, ragb_stream_t stream_) {
   RAGB_ENTRY();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = bm25_common_checks("ragb_bm25_scores", term_off, post_doc, post_tf, norm, idf, vocab, q_terms, q_off,
                               n_queries, n_docs, max_query_terms, dense_tf, dense_stride, dense_terms, n_dense);
   if (rc != RAGB_OK) return rc;
   RAGB_REQUIRE(out_scores, RAGB_EINVAL, "ragb_bm25_scores: null pointer");
+  RAGB_REQUIRE(tiled == 0 || tiled == 1, RAGB_EINVAL, "ragb_bm25_scores: tiled must be 0 or 1");
+  RAGB_REQUIRE(tiled ? out_ld >= n_queries : out_ld >= n_docs, RAGB_EINVAL,
+               "ragb_bm25_scores: out_ld=%lld too small (row-major: >= n_docs, tiled: >= n_queries)", static_cast<long long>(out_ld));
   Bm25Args a{};
   a.term_off = term_off;
   a.post_doc = post_doc;
@@ -833,6 +847,8 @@ int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uin
   a.capacity = 0;
   const int stripes = bm25_stripes(n_queries, n_docs, &a.stripe_docs);
   a.out_scores = out_scores;
+  a.out_ld = out_ld;
+  a.out_tiled = tiled;
   const size_t smem = bm25_smem_bytes(a.max_terms, 0, true);
   RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   bm25_kernel<true><<<dim3(n_queries, stripes), BM_THREADS, smem, stream>>>(a);

@@ -33,6 +33,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "router.cuh"
 
 namespace ragb {
 
@@ -61,6 +62,17 @@ struct MmaArgs {
   int* progress;        // [n_groups, n_slabs] tiles issued so far (soft pacing between the slabs of a group)
   uint64_t* lists;      // [blocks, 128, list capacity + 1] per-thread candidate lists
   int stage_limit;
+  // ---- full-fusion epilogue only (FUSED kernels) ----
+  const float* bm25;    // [ceil(n_rows / 256), bm25_rows, 256] fp32 BM25 scores of this shard's rows, 256-passage tiles
+  int64_t bm25_ld;      // query rows per tile (>= n_queries)
+  RouterWeights rw;     // running-statistics router (router.py:130-132)
+  const uint32_t* ff_table;  // [ff_nb, ff_nd] fp16 pair (lo, hi): bounds of the gate on each (bm25, dense) cell
+  int ff_nb, ff_nd;
+  float ff_inv_wb;        // ff_nb / b_cap
+  float ff_inv_wd;        // ff_nd / (2 * d_hi)
+  float ff_d_hi;          // |dense| <= d_hi for every pair (caller's guarantee)
+  unsigned long long* counters;  // optional [2]: gate evaluations, admissions (debug / bench)
+  int ff_debug;           // RAGB_FF_DEBUG (timing attribution only): 1 = no bm25 loads, 2 = no bound scan
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -319,7 +331,240 @@ __device__ __forceinline__ void epilogue_scan(const MmaArgs& a, const uint32_t t
   }
 }
 
-template <int BN, bool A_IN_TMEM, int KPL>
+// =============================================================================================
+// Full-fusion epilogue (RetrievalRouter.hybrid_rerank over ALL passages,
+// rag_uq/router.py:179-202): the candidate score is
+//     fused = g * dense + (1 - g) * bm25 = bm25 + g * (dense - bm25),   g = gate(bm25, dense)
+// with dense taken from the TMEM accumulator and bm25 read from the [n_queries, n_rows] matrix the
+// BM25 kernel wrote.  Evaluating the 3 -> H -> 1 gate for every (query, passage) pair would cost
+// ~7x the GEMM on the CUDA cores, so the scan is driven by an EXACT bound instead.  The host hands in
+// a table of gate bounds lo[ib][id] <= g(b, d) <= hi[ib][id] for every (b, d) of a cell (computed from
+// the vertices of the gate's piecewise-linear pre-activation, router.py full_fusion_bounds; two
+// bf16 per cell, 32 KB, kept in shared memory).  Then
+//     fused <= b + (d <= b ? lo : hi) * (d - b)
+// so a pair whose bound is below the thread's admission threshold cannot enter its top-k.  Per
+// pair that is ~15 instructions and one shared-memory lookup.  The gate itself runs only for the
+// survivors (~0.1 % of the pairs), evaluated by the whole warp: each lane owns hidden units
+// lane, lane+32, ... with their weights in registers, the partial sums are folded by shuffles.
+// =============================================================================================
+constexpr int FF_TABLE_CELLS = 8192;   // gate-bound cells (n_b * n_d <= this), 4 bytes each: 32 KB of shared memory
+constexpr int FF_MAX_UNITS = RAGB_ROUTER_MAX_HIDDEN / 32;
+
+// 256-bit streaming load (sm_100): read once, keep out of L1, first in line for L2 eviction so the
+// bm25 matrix does not push the passage tiles (which the other query slabs re-read) out of L2
+__device__ __forceinline__ void ldg_stream_f8(const float* p, float* dst) {
+  uint32_t r[8];
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dst[i] = __uint_as_float(r[i]);
+}
+
+// bm25 values of 32 consecutive passages of one query.  The matrix is stored in 256-passage tiles with the
+// query rows of a tile next to each other ([tile][query][256]): the 128 rows a block reads for one passage
+// tile are one contiguous 128 KB piece (one DRAM / TLB page instead of 128 rows 4*n_rows bytes apart), and
+// the last tile is padded, so the load is never out of bounds (columns beyond n_rows are masked by the caller).
+__device__ __forceinline__ void load_bm25_chunk(const float* __restrict__ p, float (&b)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ldg_stream_f8(p + 8 * i, b + 8 * i);
+}
+
+struct FusedBound {
+  const uint32_t* table;  // shared memory, [n_b][n_d]: bf16 lo in bits 0-15, bf16 hi in bits 16-31
+  float inv_wb, inv_wd, d_off;
+  uint32_t nb_max, nd_mask;  // n_b - 1, n_d - 1 (n_d is a power of two)
+  int nd_shift;
+  // Full-rate ALU only (no F2I / F2F): x + (2^23 - 0.5) rounds to 2^23 + floor(x), so the low mantissa bits
+  // are the cell index (a point exactly on a cell boundary may land in either neighbour: both closed
+  // cells contain it).  Negative, huge or NaN bm25 wrap to a large unsigned and clamp into the last row
+  // (lo = 0, hi = 1: bound = max(b, d)); dense stays inside +-d_hi by contract and is masked so that a
+  // violation can never read outside the table.
+  __device__ __forceinline__ float operator()(const float b, const float d) const {
+    const uint32_t ib = min(__float_as_uint(fmaf(b, inv_wb, 8388607.5f)) - 0x4B000000u, nb_max);
+    const uint32_t id = __float_as_uint(fmaf(d, inv_wd, d_off)) & nd_mask;
+    const uint32_t e = table[(ib << nd_shift) + id];
+    const float diff = d - b;
+    const float g = __uint_as_float(diff <= 0.0f ? (e << 16) : (e & 0xffff0000u));
+    return fmaf(g, diff, b);
+  }
+};
+
+// This lane's share of the gate MLP (hidden units lane, lane + 32, ...; absent units have zero weights).
+struct LaneGate {
+  float w0[FF_MAX_UNITS], w1[FF_MAX_UNITS], w2[FF_MAX_UNITS], b1[FF_MAX_UNITS], v[FF_MAX_UNITS];
+  float b2, mean_b, den_b, mean_d, den_d;
+  int units;
+  __device__ __forceinline__ void load(const RouterWeights& rw, const int lane) {
+    units = (rw.hidden + 31) >> 5;
+#pragma unroll
+    for (int u = 0; u < FF_MAX_UNITS; ++u) {
+      const int j = u * 32 + lane;
+      const bool ok = j < rw.hidden;
+      w0[u] = ok ? __ldg(rw.w1 + 3 * j) : 0.0f;
+      w1[u] = ok ? __ldg(rw.w1 + 3 * j + 1) : 0.0f;
+      w2[u] = ok ? __ldg(rw.w1 + 3 * j + 2) : 0.0f;
+      b1[u] = ok ? __ldg(rw.b1 + j) : 0.0f;
+      v[u] = ok ? __ldg(rw.w2 + j) : 0.0f;
+    }
+    b2 = __ldg(rw.b2);
+    mean_b = __ldg(rw.stats);
+    den_b = __ldg(rw.stats + 1) + RT_EPS;
+    mean_d = __ldg(rw.stats + 2);
+    den_d = __ldg(rw.stats + 3) + RT_EPS;
+  }
+  // all 32 lanes call this with the same (xb, xd); everyone gets the gate
+  __device__ __forceinline__ float operator()(const float xb, const float xd) const {
+    const float bn = (xb - mean_b) / den_b;
+    const float dn = (xd - mean_d) / den_d;
+    const float df = dn - bn;
+    float p = 0.0f;
+#pragma unroll
+    for (int u = 0; u < FF_MAX_UNITS; ++u) {
+      if (u < units) {
+        float h = fmaf(w2[u], df, fmaf(w1[u], dn, fmaf(w0[u], bn, b1[u])));
+        h = h < 0.0f ? 0.0f : h;
+        p = fmaf(v[u], h, p);
+      }
+    }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) p += __shfl_xor_sync(0xffffffffu, p, sh);
+    return sigmoidf_exact(b2 + p);
+  }
+};
+
+template <int BN, int KPL>
+__device__ __forceinline__ void epilogue_scan_fused(const MmaArgs& a, const uint32_t* s_table, const uint32_t tmem_base,
+                                                    const uint32_t acc_col0, uint64_t* block_lists, const int warp,
+                                                    const int lane, const int slab, const int group,
+                                                    const int tile_begin, const int tile_end, uint64_t* bar_tmem_full,
+                                                    const uint32_t empty_addr0, const uint32_t empty_addr1,
+                                                    const bool remote_arrive) {
+  constexpr int LIST_CAP = 32 * KPL;
+  constexpr int LIST_STRIDE = LIST_CAP + 1;
+  constexpr int HALF_CHUNKS = BN / 64;  // 32-column chunks per half
+  const int quad = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const int query = slab * MM_BM + quad * 32 + lane;
+  const bool live = query < a.n_queries;
+  const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+  uint64_t* warp_lists = block_lists + static_cast<size_t>(half * 4 + quad) * 32 * LIST_STRIDE;
+  uint64_t* my_list = warp_lists + lane * LIST_STRIDE;
+  // this thread's row inside tile 0; tile t is t * bm25_ld * BN floats further (BN == 256 == the tile width)
+  static_assert(BN == 256, "the bm25 matrix is stored in 256-passage tiles");
+  const float* brow = a.bm25 + static_cast<int64_t>(live ? query : 0) * BN;
+  const int64_t tile_stride = a.bm25_ld * BN;
+  const FusedBound bound{s_table, a.ff_inv_wb, a.ff_inv_wd, fmaf(a.ff_d_hi, a.ff_inv_wd, 8388607.5f),
+                         static_cast<uint32_t>(a.ff_nb - 1), static_cast<uint32_t>(a.ff_nd - 1), 31 - __clz(a.ff_nd)};
+  LaneGate gate;
+  gate.load(a.rw, lane);
+  ListState st{0, -INFINITY, 0ull};
+  // pruning threshold = admission threshold minus rounding slack; padding rows of the slab never pass
+  float thr_cmp = live ? -INFINITY : INFINITY;
+  unsigned long long n_eval = 0, n_admit = 0;
+  uint32_t buf = 0, acc_phase = 0;
+  float nb[32];  // bm25 values of the NEXT chunk, in flight while the current one is scanned
+  if (tile_begin < tile_end) load_bm25_chunk(brow + tile_begin * tile_stride + half * HALF_CHUNKS * 32, nb);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_phase);
+    tc_fence_after();
+    const int64_t row0 = static_cast<int64_t>(tile) * BN;
+    const int valid = static_cast<int>(min(static_cast<int64_t>(BN), a.n_rows - row0));
+#pragma unroll 1
+    for (int cc = 0; cc < HALF_CHUNKS; ++cc) {
+      const int c = half * HALF_CHUNKS + cc;
+      float b[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) b[i] = nb[i];
+      {  // prefetch: next chunk of this tile, or the first chunk of the next tile
+        const bool last = cc + 1 == HALF_CHUNKS;
+        const int nt = last ? tile + 1 : tile;
+        const int nc = last ? half * HALF_CHUNKS : c + 1;
+        if (nt < tile_end && !(a.ff_debug & 1)) load_bm25_chunk(brow + nt * tile_stride + nc * 32, nb);
+      }
+      uint32_t v[32];
+      __syncwarp();
+      tc_ld32(tmem_base + lane_addr + acc_col0 + buf * BN + c * 32, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // one bit per pair of this lane's query that may still be admitted
+      uint32_t pm = 0u;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pm |= (bound(b[i], __uint_as_float(v[i])) >= thr_cmp) ? (1u << i) : 0u;
+      if (a.ff_debug & 2) pm = 0u;
+      const int lim = valid - c * 32;
+      if (lim < 32) pm &= lim <= 0 ? 0u : ((1u << lim) - 1u);
+      if (__any_sync(0xffffffffu, pm != 0u)) {
+        const unsigned full = __ballot_sync(0xffffffffu, st.cnt > LIST_CAP - 32);
+        if (full) {
+          st = compact_lists<KPL>(warp_lists, full, lane, a.k, st);
+          if (live && st.cnt >= a.k) thr_cmp = st.thr_score - 1e-5f * fabsf(st.thr_score) - 1e-6f;
+        }
+        const int32_t id0 = static_cast<int32_t>(a.id_base + row0) + c * 32;
+        unsigned active;
+        while ((active = __ballot_sync(0xffffffffu, pm != 0u)) != 0u) {
+          // every lane with work picks its next pair (register select, no dynamic indexing) ...
+          const int sel = __ffs(pm) - 1;
+          float bs = 0.0f, ds = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            bs = i == sel ? b[i] : bs;
+            ds = i == sel ? __uint_as_float(v[i]) : ds;
+          }
+          pm &= pm - 1u;
+          // ... and the warp evaluates the gate of one pair at a time
+          while (active) {
+            const int src = __ffs(active) - 1;
+            active &= active - 1u;
+            const float xb = __shfl_sync(0xffffffffu, bs, src);
+            const float xd = __shfl_sync(0xffffffffu, ds, src);
+            const float g = gate(xb, xd);
+            if (lane == src) {
+              const float h = fuse_scores(g, xb, xd);
+              ++n_eval;
+              if (h >= st.thr_score) {
+                const uint64_t key = make_key(h, id0 + sel);
+                if (key > st.thr_key) {
+                  my_list[st.cnt++] = key;
+                  ++n_admit;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t bar = buf == 0 ? empty_addr0 : empty_addr1;
+      if (remote_arrive)
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+      else
+        mbar_arrive(bar);
+    }
+    buf ^= 1;
+    if (buf == 0) acc_phase ^= 1;
+  }
+  st = compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, st);
+  const int cnt = st.cnt;
+  if (live) {
+    uint64_t* dst = a.part_keys + ((static_cast<int64_t>(query) * a.n_groups + group) * 2 + half) * a.k;
+    for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? __ldcg(reinterpret_cast<const unsigned long long*>(my_list + j)) : 0ull;
+  }
+  if (a.counters != nullptr) {
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+      n_eval += __shfl_xor_sync(0xffffffffu, n_eval, sh);
+      n_admit += __shfl_xor_sync(0xffffffffu, n_admit, sh);
+    }
+    if (lane == 0) {
+      atomicAdd(a.counters, n_eval);
+      atomicAdd(a.counters + 1, n_admit);
+    }
+  }
+}
+
+template <int BN, bool A_IN_TMEM, int KPL, bool FUSED = false>
 __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                   const __grid_constant__ CUtensorMap tmap_e,
                                                                   const MmaArgs a) {
@@ -340,6 +585,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* stages = base;
+  uint32_t* s_table = reinterpret_cast<uint32_t*>(stages + static_cast<size_t>(a.n_stages) * STAGE_BYTES);  // FUSED only
+  if constexpr (FUSED) {
+    for (int i = threadIdx.x; i < a.ff_nb * a.ff_nd; i += MM_THREADS) s_table[i] = __ldg(a.ff_table + i);
+  }
   // candidate lists live in the caller's workspace (L2-resident, touched ~once per thousand scores), so
   // shared memory holds only the operand ring and blocks of other kernels can share the SM
   uint64_t* lists = a.lists + static_cast<size_t>(blockIdx.x) * 2 * MM_BM * (32 * KPL + 1);
@@ -481,8 +730,12 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_a_ready));
     }
-    epilogue_scan<BN, KPL>(a, tmem_base, acc_col0, lists, warp, lane, slab, group, tile_begin, tile_end, bar_tmem_full,
-                           smem_u32(&bar_tmem_empty[0]), smem_u32(&bar_tmem_empty[1]), false);
+    if constexpr (FUSED)
+      epilogue_scan_fused<BN, KPL>(a, s_table, tmem_base, acc_col0, lists, warp, lane, slab, group, tile_begin, tile_end,
+                                   bar_tmem_full, smem_u32(&bar_tmem_empty[0]), smem_u32(&bar_tmem_empty[1]), false);
+    else
+      epilogue_scan<BN, KPL>(a, tmem_base, acc_col0, lists, warp, lane, slab, group, tile_begin, tile_end, bar_tmem_full,
+                             smem_u32(&bar_tmem_empty[0]), smem_u32(&bar_tmem_empty[1]), false);
   }
 
   tc_fence_before();
@@ -536,7 +789,7 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int KPL>
+template <int KPL, bool FUSED = false>
 __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                        const __grid_constant__ CUtensorMap tmap_e,
                                                                        const MmaArgs a) {
@@ -556,6 +809,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_pair_kernel(const __g
 
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* stages = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint32_t* s_table = reinterpret_cast<uint32_t*>(stages + static_cast<size_t>(a.n_stages) * MM2_STAGE_BYTES);  // FUSED only
+  if constexpr (FUSED) {
+    for (int i = threadIdx.x; i < a.ff_nb * a.ff_nd; i += MM_THREADS) s_table[i] = __ldg(a.ff_table + i);
+  }
   uint64_t* lists = a.lists + static_cast<size_t>(blockIdx.x) * 2 * MM_BM * (32 * KPL + 1);
   __shared__ __align__(8) uint64_t bar_full[MM_MAX_STAGES];   // used in the leader only
   __shared__ __align__(8) uint64_t bar_empty[MM_MAX_STAGES];  // one per block, fed by the multicast commit
@@ -651,9 +908,15 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_pair_kernel(const __g
     }
   } else {
     // ================= epilogue: thread owns one query of this block's slab =================
-    epilogue_scan<MM2_BN, KPL>(a, tmem_base, 0u, lists, warp, lane, slab, group, tile_begin, tile_end, bar_tmem_full,
-                               smem_u32(&bar_tmem_empty[0]) & MM_PEER_MASK, smem_u32(&bar_tmem_empty[1]) & MM_PEER_MASK,
-                               true);   // both blocks release the accumulator on the LEADER's barrier
+    // both blocks release the accumulator on the LEADER's barrier
+    if constexpr (FUSED)
+      epilogue_scan_fused<MM2_BN, KPL>(a, s_table, tmem_base, 0u, lists, warp, lane, slab, group, tile_begin, tile_end,
+                                       bar_tmem_full, smem_u32(&bar_tmem_empty[0]) & MM_PEER_MASK,
+                                       smem_u32(&bar_tmem_empty[1]) & MM_PEER_MASK, true);
+    else
+      epilogue_scan<MM2_BN, KPL>(a, tmem_base, 0u, lists, warp, lane, slab, group, tile_begin, tile_end, bar_tmem_full,
+                                 smem_u32(&bar_tmem_empty[0]) & MM_PEER_MASK, smem_u32(&bar_tmem_empty[1]) & MM_PEER_MASK,
+                                 true);
   }
 
   tc_fence_before();
@@ -663,11 +926,6 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_pair_kernel(const __g
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
-
-template <int KPL>
-static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
-                           int64_t id_base, uint64_t* part, int* progress, uint64_t* lists, int stage_limit,
-                           int* n_groups_out, cudaStream_t stream);
 
 // ---- host ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -699,10 +957,26 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int dim, in
   return RAGB_OK;
 }
 
-template <int BN, bool A_IN_TMEM, int KPL>
+// fused: null (dense-only top-k) or the full-fusion fields of MmaArgs (bm25, router, bound table)
+static void copy_fused_fields(MmaArgs& a, const MmaArgs* fused) {
+  if (fused == nullptr) return;
+  a.bm25 = fused->bm25;
+  a.bm25_ld = fused->bm25_ld;
+  a.rw = fused->rw;
+  a.ff_table = fused->ff_table;
+  a.ff_nb = fused->ff_nb;
+  a.ff_nd = fused->ff_nd;
+  a.ff_inv_wb = fused->ff_inv_wb;
+  a.ff_inv_wd = fused->ff_inv_wd;
+  a.ff_d_hi = fused->ff_d_hi;
+  a.counters = fused->counters;
+  a.ff_debug = fused->ff_debug;
+}
+
+template <int BN, bool A_IN_TMEM, int KPL, bool FUSED = false>
 static int launch_mma(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
                       int64_t id_base, uint64_t* part, int* progress, uint64_t* lists, int stage_limit,
-                      int* n_groups_out, cudaStream_t stream) {
+                      int* n_groups_out, cudaStream_t stream, const MmaArgs* fused = nullptr) {
   constexpr int STAGE_BYTES = (A_IN_TMEM ? 0 : MM_A_STAGE_BYTES) + BN * MM_BK * 2;
   CUtensorMap map_q, map_e;
   int rc = make_map(&map_q, queries, n_queries, dim, MM_BM);
@@ -729,26 +1003,28 @@ static int launch_mma(const void* passages, int64_t n_rows, int dim, const void*
   a.part_keys = part;
   a.progress = progress;
   a.lists = lists;
+  copy_fused_fields(a, fused);
   RAGB_CUDA(cudaMemsetAsync(progress, 0, MM_PROGRESS_BYTES, stream));
   // Ring depth: everything shared memory offers (RAGB_MMA_STAGES caps it, e.g. to leave room for
   // blocks of another kernel on the same SM when experimenting with two-stream overlap).
-  int stages = static_cast<int>((MM_MAX_SMEM - 1024 - 256) / STAGE_BYTES);
+  constexpr int TABLE_BYTES = FUSED ? FF_TABLE_CELLS * static_cast<int>(sizeof(uint32_t)) : 0;
+  int stages = static_cast<int>((MM_MAX_SMEM - 1024 - 256 - TABLE_BYTES) / STAGE_BYTES);
   if (stage_limit > 0 && stages > stage_limit) stages = stage_limit;
   if (stages > MM_MAX_STAGES) stages = MM_MAX_STAGES;
   a.n_stages = stages;
-  const size_t smem = 1024 + static_cast<size_t>(stages) * STAGE_BYTES;
-  RAGB_CUDA(cudaFuncSetAttribute(dense_mma_kernel<BN, A_IN_TMEM, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem = 1024 + static_cast<size_t>(stages) * STAGE_BYTES + TABLE_BYTES;
+  RAGB_CUDA(cudaFuncSetAttribute(dense_mma_kernel<BN, A_IN_TMEM, KPL, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-  dense_mma_kernel<BN, A_IN_TMEM, KPL><<<a.n_slabs * a.n_groups, MM_THREADS, smem, stream>>>(map_q, map_e, a);
+  dense_mma_kernel<BN, A_IN_TMEM, KPL, FUSED><<<a.n_slabs * a.n_groups, MM_THREADS, smem, stream>>>(map_q, map_e, a);
   RAGB_AFTER_LAUNCH(1);
   *n_groups_out = a.n_groups;
   return RAGB_OK;
 }
 
-template <int KPL>
+template <int KPL, bool FUSED = false>
 static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
                            int64_t id_base, uint64_t* part, int* progress, uint64_t* lists, int stage_limit,
-                           int* n_groups_out, cudaStream_t stream) {
+                           int* n_groups_out, cudaStream_t stream, const MmaArgs* fused = nullptr) {
   CUtensorMap map_q, map_e;
   int rc = make_map(&map_q, queries, n_queries, dim, MM_BM);
   if (rc != RAGB_OK) return rc;
@@ -774,13 +1050,15 @@ static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const 
   a.part_keys = part;
   a.progress = progress;
   a.lists = lists;
+  copy_fused_fields(a, fused);
   RAGB_CUDA(cudaMemsetAsync(progress, 0, MM_PROGRESS_BYTES, stream));
-  int stages = (MM_MAX_SMEM - 1024 - 256) / MM2_STAGE_BYTES;
+  constexpr int TABLE_BYTES = FUSED ? FF_TABLE_CELLS * static_cast<int>(sizeof(uint32_t)) : 0;
+  int stages = (MM_MAX_SMEM - 1024 - 256 - TABLE_BYTES) / MM2_STAGE_BYTES;
   if (stage_limit > 0 && stages > stage_limit) stages = stage_limit;
   if (stages > MM_MAX_STAGES) stages = MM_MAX_STAGES;
   a.n_stages = stages;
-  const size_t smem = 1024 + static_cast<size_t>(stages) * MM2_STAGE_BYTES;
-  RAGB_CUDA(cudaFuncSetAttribute(dense_mma_pair_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem = 1024 + static_cast<size_t>(stages) * MM2_STAGE_BYTES + TABLE_BYTES;
+  RAGB_CUDA(cudaFuncSetAttribute(dense_mma_pair_kernel<KPL, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * n_pairs_slab * a.n_groups);
@@ -794,7 +1072,7 @@ static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RAGB_CUDA(cudaLaunchKernelEx(&cfg, dense_mma_pair_kernel<KPL>, map_q, map_e, a));
+  RAGB_CUDA(cudaLaunchKernelEx(&cfg, dense_mma_pair_kernel<KPL, FUSED>, map_q, map_e, a));
   RAGB_AFTER_LAUNCH(1);
   *n_groups_out = a.n_groups;
   return RAGB_OK;
@@ -865,6 +1143,73 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
 #undef RAGB_MMA_DISPATCH
 #undef RAGB_COMMA
 #undef RAGB_MMA_ARGS
+  if (rc != RAGB_OK) return rc;
+  return launch_merge_keys(part, n_queries, n_groups * 2, k, k, out_score, out_id, stream);
+}
+
+int ragb_dense_mma_fused_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
+                              int32_t n_queries, int32_t k, int64_t id_base, const float* bm25_scores, int64_t bm25_rows,
+                              const float* w1, const float* b1, const float* w2, const float* b2, const float* stats,
+                              int32_t hidden, const uint32_t* gate_bound_table, int32_t n_b, int32_t n_d, float b_cap,
+                              float d_hi, float* out_score, int32_t* out_id, unsigned long long* counters,
+                              void* workspace, size_t workspace_bytes, ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(passages_bf16 && queries_bf16 && bm25_scores && out_score && out_id && workspace, RAGB_EINVAL,
+               "ragb_dense_mma_fused_topk: null pointer");
+  RAGB_REQUIRE(w1 && b1 && w2 && b2 && stats && gate_bound_table, RAGB_EINVAL,
+               "ragb_dense_mma_fused_topk: router weights, running statistics and gate bound table are required");
+  RAGB_REQUIRE(((reinterpret_cast<uintptr_t>(passages_bf16) | reinterpret_cast<uintptr_t>(queries_bf16)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(bm25_scores) & 31) == 0,
+               RAGB_EINVAL, "ragb_dense_mma_fused_topk: passages / queries must be 16-byte, bm25_scores 32-byte aligned");
+  RAGB_REQUIRE(n_rows > 0 && n_queries > 0, RAGB_EINVAL, "ragb_dense_mma_fused_topk: empty shape");
+  RAGB_REQUIRE(bm25_rows >= n_queries, RAGB_EINVAL,
+               "ragb_dense_mma_fused_topk: bm25_rows=%lld must be >= n_queries", static_cast<long long>(bm25_rows));
+  RAGB_REQUIRE(dim >= MM_BK && dim % MM_BK == 0, RAGB_EINVAL, "ragb_dense_mma_fused_topk: dim=%d must be a multiple of %d",
+               dim, MM_BK);
+  RAGB_REQUIRE(k > 0 && k <= 100, RAGB_ELIMIT, "ragb_dense_mma_fused_topk: k=%d outside [1,100]", k);
+  RAGB_REQUIRE(hidden >= 4 && hidden <= RAGB_ROUTER_MAX_HIDDEN && hidden % 4 == 0, RAGB_ELIMIT,
+               "ragb_dense_mma_fused_topk: hidden=%d must be a multiple of 4 in [4,%d]", hidden, RAGB_ROUTER_MAX_HIDDEN);
+  RAGB_REQUIRE(n_b >= 2 && n_d >= 1 && (n_d & (n_d - 1)) == 0 && static_cast<int64_t>(n_b) * n_d <= FF_TABLE_CELLS,
+               RAGB_ELIMIT, "ragb_dense_mma_fused_topk: gate bound table %d x %d: n_d must be a power of two, at most %d cells",
+               n_b, n_d, FF_TABLE_CELLS);
+  RAGB_REQUIRE(b_cap > 0.0f && d_hi > 0.0f, RAGB_EINVAL, "ragb_dense_mma_fused_topk: b_cap and d_hi must be positive");
+  RAGB_REQUIRE(id_base >= 0 && id_base + n_rows < (1ll << 31), RAGB_ELIMIT, "ragb_dense_mma_fused_topk: ids must fit int32");
+  RAGB_REQUIRE(workspace_bytes >= ragb_dense_mma_workspace_bytes(n_queries, k), RAGB_ENOSPC,
+               "ragb_dense_mma_fused_topk: workspace too small");
+  int* progress = static_cast<int*>(workspace);
+  uint64_t* lists = reinterpret_cast<uint64_t*>(static_cast<unsigned char*>(workspace) + MM_PROGRESS_BYTES);
+  uint64_t* part = reinterpret_cast<uint64_t*>(static_cast<unsigned char*>(workspace) + MM_PROGRESS_BYTES + mma_list_bytes(k));
+  MmaArgs f{};
+  f.bm25 = bm25_scores;
+  f.bm25_ld = bm25_rows;
+  f.rw = RouterWeights{w1, b1, w2, b2, stats, hidden};
+  f.ff_table = gate_bound_table;
+  f.ff_nb = n_b;
+  f.ff_nd = n_d;
+  f.ff_inv_wb = static_cast<float>(n_b) / b_cap;
+  f.ff_inv_wd = static_cast<float>(n_d) / (2.0f * d_hi);
+  f.ff_d_hi = d_hi;
+  f.counters = counters;
+  static const int ff_debug = [] {
+    const char* e = getenv("RAGB_FF_DEBUG");  // timing attribution only: results are wrong when set
+    return e ? atoi(e) : 0;
+  }();
+  f.ff_debug = ff_debug;
+  int n_groups = 0;
+  int rc;
+  const int kpl = mma_list_kpl(k);
+#define RAGB_FUSED_ARGS passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, progress, lists, 0, &n_groups, stream, &f
+  if (n_queries <= MM_BM) {   // a lone slab has no partner for a CTA pair
+    if (kpl == 2) rc = launch_mma<256, false, 2, true>(RAGB_FUSED_ARGS);
+    else if (kpl == 4) rc = launch_mma<256, false, 4, true>(RAGB_FUSED_ARGS);
+    else rc = launch_mma<256, false, 8, true>(RAGB_FUSED_ARGS);
+  } else {
+    if (kpl == 2) rc = launch_mma_pair<2, true>(RAGB_FUSED_ARGS);
+    else if (kpl == 4) rc = launch_mma_pair<4, true>(RAGB_FUSED_ARGS);
+    else rc = launch_mma_pair<8, true>(RAGB_FUSED_ARGS);
+  }
+#undef RAGB_FUSED_ARGS
   if (rc != RAGB_OK) return rc;
   return launch_merge_keys(part, n_queries, n_groups * 2, k, k, out_score, out_id, stream);
 }

@@ -9,21 +9,12 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "router.cuh"
 
 namespace ragb {
 
 constexpr int RT_THREADS = 256;
 constexpr int RT_STAT_BLOCKS = 128;
-constexpr float RT_EPS = 1e-6f;  // router.py:112
-
-struct RouterWeights {
-  const float* w1;  // [H,3]
-  const float* b1;  // [H]
-  const float* w2;  // [H]
-  const float* b2;  // [1]
-  const float* stats;  // [4] bm25_mean, bm25_std, dense_mean, dense_std
-  int hidden;
-};
 
 // ---- statistics of the call's own scores (norm_mode 0 / 2) ------------------------------
 // partial[b] = {sum_b, sumsq_b, sum_d, sumsq_d} in float64, fixed grid, fixed reduction order.
@@ -106,8 +97,6 @@ __global__ void __launch_bounds__(RT_THREADS) stats_rows_kernel(const float* __r
   }
 }
 
-__device__ __forceinline__ float sigmoidf_exact(float x) { return 1.0f / (1.0f + expf(-x)); }
-
 // ---- gate ---------------------------------------------------------------------------------
 // stats_ptr: [4] (modes 0/1) or [rows,4] (mode 2, row = element / p)
 __global__ void __launch_bounds__(RT_THREADS) router_forward_kernel(const float* __restrict__ bm25,
@@ -130,18 +119,9 @@ __global__ void __launch_bounds__(RT_THREADS) router_forward_kernel(const float*
        i += static_cast<int64_t>(gridDim.x) * RT_THREADS) {
     const float* st = per_row_p > 0 ? stats_ptr + 4 * (i / per_row_p) : stats_ptr;
     const float xb = bm25[i], xd = dense[i];
-    const float bn = (xb - st[0]) / (st[1] + RT_EPS);
-    const float dn = (xd - st[2]) / (st[3] + RT_EPS);
-    const float df = dn - bn;
-    float z = b2;
-    for (int j = 0; j < H; ++j) {
-      float h = fmaf(s_w1[3 * j + 2], df, fmaf(s_w1[3 * j + 1], dn, fmaf(s_w1[3 * j], bn, s_b1[j])));
-      h = h < 0.0f ? 0.0f : h;  // ReLU that lets NaN through like torch.relu
-      z = fmaf(s_w2[j], h, z);
-    }
-    const float g = sigmoidf_exact(z);
+    const float g = gate_eval(s_w1, s_b1, s_w2, b2, H, st, xb, xd);
     if (out_gate) out_gate[i] = g;
-    if (out_fused) out_fused[i] = g * xd + (1.0f - g) * xb;  // router.py:199, raw scores
+    if (out_fused) out_fused[i] = fuse_scores(g, xb, xd);  // router.py:199, raw scores
   }
 }
 
@@ -247,14 +227,14 @@ __global__ void __launch_bounds__(RT_THREADS) router_mc_kernel(const McArgs a) {
     for (int t = 0; t < T; ++t) {
       const float g = s_gate[t * P + p];
       mg += g;
-      mf += g * xd + (1.0f - g) * xb;
+      mf += fuse_scores(g, xb, xd);
     }
     mg /= T;
     mf /= T;
     float vg = 0.0f, vf = 0.0f;
     for (int t = 0; t < T; ++t) {
       const float g = s_gate[t * P + p];
-      const float f = g * xd + (1.0f - g) * xb;
+      const float f = fuse_scores(g, xb, xd);
       vg += (g - mg) * (g - mg);
       vf += (f - mf) * (f - mf);
     }

@@ -178,32 +178,96 @@ class HybridEngine:
         return out
 
     # ---- full-fusion mode ----------------------------------------------------------------
+    def _max_passage_norm(self) -> float:
+        """Largest L2 norm of a passage row (computed once, chunked): with the largest query norm it bounds |dense|."""
+        if getattr(self, "_max_norm", None) is None:
+            best = torch.zeros((), dtype=torch.float32, device=self.passages.device)
+            for r0 in range(0, self.passages.shape[0], 1 << 18):
+                best = torch.maximum(best, self.passages[r0:r0 + (1 << 18)].float().norm(dim=1).max())
+            self._max_norm = float(best)
+        return self._max_norm
+
+    def bm25_score_cap(self, q_terms: Tensor, q_off: Tensor) -> float:
+        """An upper bound of every BM25 score of the batch: tf (k1+1) / (tf + norm) < k1 + 1 per occurrence."""
+        idf = self.sparse.idf
+        ok = (q_terms >= 0) & (q_terms < idf.shape[0])
+        w = torch.where(ok, idf[q_terms.clamp(0, idf.shape[0] - 1).long()].clamp(min=0.0), idf.new_zeros(()))
+        csum = torch.cat([w.new_zeros(1), torch.cumsum(w.double(), 0).float()])
+        per_query = csum[q_off[1:].long()] - csum[q_off[:-1].long()]
+        k1 = float(getattr(self.sparse, "k1", 1.5))
+        return float(per_query.max()) * (k1 + 1.0) if per_query.numel() else 0.0
+
     def full_fusion_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, router, k: int = 10,
-                         query_chunk: int = 64):
+                         query_chunk: Optional[int] = None, fused: Optional[bool] = None, counters: Optional[Tensor] = None,
+                         events=None):
         """Gate evaluated for EVERY (query, passage) pair on the true scores ("full-fusion").
 
         Oracle: ``RetrievalRouter.hybrid_rerank(bm25_full[B,N], dense_full[B,N], k)`` (router.py:179-202).
-        Un-fused form: the [chunk, N_local] score matrices are materialised (BM25 get_scores kernel,
-        dense score kernel), gated and reduced per chunk of queries.  The router must be in
-        running-statistics mode: call-wide statistics over [B, N] would need a global reduction
-        first and are refused here.  -> (fused score [B,k], global id int32 [B,k]).
+        The router must be in running-statistics mode: call-wide statistics over [B, N] would need a
+        global reduction first and are refused here.  -> (fused score [B,k], global id int32 [B,k]).
+
+        ``fused`` (default: whenever the batch is large enough for the tensor-core kernel): the BM25
+        kernel writes get_scores for a chunk of queries into a tiled [N_local / 256, chunk, 256] fp32 matrix and the
+        tcgen05 GEMM's epilogue reads it, evaluates gate and fusion on the accumulator in TMEM and keeps
+        the per-query top-k: neither the dense nor the fused score matrix ever exists.  Otherwise the
+        un-fused form materialises both matrices per chunk (small shapes, tests).
+        ``query_chunk`` defaults to what fits in 60 % of the free device memory.
         """
         if not getattr(router, "stats_initialized", False):
             raise ValueError("full-fusion mode needs router.stats_initialized = True (running statistics)")
         w1, b1, w2, b2, stats = router._weights()
-        n_q = q_emb.shape[0]
+        n_q, n_local = q_emb.shape[0], self.passages.shape[0]
+        if fused is None:
+            fused = n_q > _lib.GEMV_MAX_BATCH and k <= _lib.MMA_MAX_TOPK and hasattr(self.sparse, "scores_tiled")
+        tiles = -(-n_local // ops.SCORE_TILE)
+        ld = tiles * ops.SCORE_TILE
+        if query_chunk is None:
+            free, _ = torch.cuda.mem_get_info(q_emb.device)
+            per_query = ld * 4 * (1 if fused else 3)
+            query_chunk = max(1, min(n_q, int(free * 0.6) // per_query))
+            if fused and query_chunk >= 128:
+                query_chunk = query_chunk // 128 * 128
         out_s, out_i = [], []
         q_off_host = q_off.tolist()
+        if fused:
+            b_cap = self.bm25_score_cap(q_terms, q_off)
+            b_cap = float(min(64.0, 2.0 ** max(0, int(b_cap - 1e-9).bit_length()))) if b_cap > 0 else 1.0
+            d_hi = self._max_passage_norm() * float(q_emb.float().norm(dim=1).max()) * 1.002 + 1e-3
+            d_hi = float(-(-d_hi * 64 // 1) / 64)   # round up to 1/64 so the cached table is reused across batches
+            gate_bounds = router.full_fusion_table(b_cap, d_hi)
+            bm = torch.empty((tiles, min(query_chunk, n_q), ops.SCORE_TILE), dtype=torch.float32, device=q_emb.device)
+            if counters is None:
+                counters = torch.empty(0, dtype=torch.int64, device=q_emb.device)
         for lo in range(0, n_q, query_chunk):
             hi = min(n_q, lo + query_chunk)
             t0, t1 = q_off_host[lo], q_off_host[hi]
             sub_terms = q_terms[t0:t1] if t1 > t0 else q_terms[:1]
             sub_off = (q_off[lo:hi + 1] - t0).contiguous()
-            bm = self.sparse.scores(sub_terms.contiguous(), sub_off, max_terms)
+            if fused:
+                e0 = _mark(events)
+                self.sparse.scores_tiled(sub_terms.contiguous(), sub_off, max_terms, bm)
+                e1 = _mark(events)
+                val, idx = ops.dense_mma_fused_topk(self.passages, q_emb[lo:hi].contiguous(), bm, w1, b1, w2, b2,
+                                                    stats, gate_bounds, b_cap, d_hi, min(k, n_local), self.id_base, counters)
+                if events is not None:
+                    events.setdefault("bm25", []).append((e0, e1))
+                    events.setdefault("dense", []).append((e1, _mark(events)))
+                out_s.append(val)
+                out_i.append(idx)
+                continue
+            bm_full = self.sparse.scores(sub_terms.contiguous(), sub_off, max_terms)
             de = ops.dense_scores(self.passages, q_emb[lo:hi].contiguous())
-            _, fused = ops.router_forward(bm, de, w1, b1, w2, b2, stats, 1)
-            val, idx = ops.topk_rows(fused, min(k, fused.shape[1]))
+            _, fused_scores = ops.router_forward(bm_full, de, w1, b1, w2, b2, stats, 1)
+            val, idx = ops.topk_rows(fused_scores, min(k, fused_scores.shape[1]))
             out_s.append(val)
             out_i.append(torch.where(idx >= 0, idx + self.id_base, idx))
         score, ids = torch.cat(out_s), torch.cat(out_i)
         return self._merge(score, ids, score.shape[1])
+
+
+def _mark(events):
+    if events is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e

@@ -133,7 +133,7 @@ def bm25_scores(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tenso
     with torch.cuda.device(dev):
         check(lib.ragb_bm25_scores(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf),
                                    idf.shape[0], k1, dt, stride, dterms, n_dense, _ptr(q_terms), _ptr(q_off), n_q,
-                                   max_query_terms, n_docs, _ptr(out), _stream()))
+                                   max_query_terms, n_docs, _ptr(out), n_docs, 0, _stream()))
     return out
 
 
@@ -187,6 +187,69 @@ def dense_mma_topk(passages: Tensor, queries: Tensor, k: int, id_base: int, vari
 
 @dense_mma_topk.register_fake
 def _(passages, queries, k, id_base, variant):
+    n_q = queries.shape[0]
+    return (queries.new_empty((n_q, k), dtype=torch.float32), queries.new_empty((n_q, k), dtype=torch.int32))
+
+
+SCORE_TILE = 256   # passages per tile of the tiled score matrix (ragb200.h, ragb_bm25_scores tiled = 1)
+
+
+@torch.library.custom_op(f"{NS}::bm25_scores_tiled", mutates_args=("out",), device_types="cuda")
+def bm25_scores_tiled(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
+                      dense_tf: Tensor, dense_terms: Tensor, q_terms: Tensor, q_off: Tensor,
+                      max_query_terms: int, out: Tensor) -> None:
+    """get_scores for a batch written into a caller-owned tiled matrix out[ceil(n_docs / 256), rows >= B, 256] fp32:
+    the layout the full-fusion GEMM epilogue reads.  Columns of the last tile beyond n_docs are left untouched."""
+    term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
+                                                                        q_terms, q_off)
+    n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
+    tiles = -(-n_docs // SCORE_TILE)
+    if (out.dtype != torch.float32 or out.dim() != 3 or not out.is_contiguous() or out.shape[0] < tiles
+            or out.shape[1] < n_q or out.shape[2] != SCORE_TILE):
+        raise ValueError(f"out must be a contiguous float32 [>= {tiles}, >= {n_q}, {SCORE_TILE}] tensor")
+    dt, stride, dterms, n_dense = _dense_table(dense_tf, dense_terms, n_docs)
+    with torch.cuda.device(dev):
+        check(lib.ragb_bm25_scores(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf),
+                                   idf.shape[0], k1, dt, stride, dterms, n_dense, _ptr(q_terms), _ptr(q_off), n_q,
+                                   max_query_terms, n_docs, _ptr(out), out.shape[1], 1, _stream()))
+
+
+@torch.library.custom_op(f"{NS}::dense_mma_fused_topk", mutates_args=("counters",), device_types="cuda")
+def dense_mma_fused_topk(passages: Tensor, queries: Tensor, bm25: Tensor, w1: Tensor, b1: Tensor, w2: Tensor,
+                         b2: Tensor, stats: Tensor, gate_bounds: Tensor, b_cap: float, d_hi: float, k: int, id_base: int,
+                         counters: Tensor) -> Tuple[Tensor, Tensor]:
+    """Full-fusion top-k inside the tcgen05 epilogue (ragb200.h).
+
+    bm25: the tiled fp32 matrix [ceil(N / 256), rows >= B, 256] ``bm25_scores_tiled`` filled; gate_bounds: int32
+    [n_b, n_d], two bf16 (lo, hi) bounds of the gate per cell (``router.full_fusion_bounds``); counters: int64 [2]
+    or empty.
+    """
+    passages, queries = _dense_args(passages, queries)
+    n_q, dev = queries.shape[0], passages.device
+    tiles = -(-passages.shape[0] // SCORE_TILE)
+    if (bm25.dtype != torch.float32 or bm25.dim() != 3 or not bm25.is_contiguous() or bm25.shape[0] < tiles
+            or bm25.shape[1] < n_q or bm25.shape[2] != SCORE_TILE):
+        raise ValueError(f"bm25 must be a contiguous float32 [>= {tiles}, >= {n_q}, {SCORE_TILE}] tiled score matrix")
+    w1, b1, w2, b2, stats = (_need(t, torch.float32, n) for t, n in
+                             ((w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2"), (stats, "stats")))
+    gate_bounds = _need(gate_bounds, torch.int32, "gate_bounds")
+    if gate_bounds.dim() != 2:
+        raise ValueError("gate_bounds must be [n_b, n_d]")
+    score = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.ragb_dense_mma_workspace_bytes(n_q, k), dev)
+    cnt = _ptr(counters) if counters.numel() >= 2 else None
+    with torch.cuda.device(dev):
+        check(lib.ragb_dense_mma_fused_topk(_ptr(passages), passages.shape[0], passages.shape[1], _ptr(queries), n_q, k,
+                                            id_base, _ptr(bm25), bm25.shape[1], _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2),
+                                            _ptr(stats), b1.shape[0], _ptr(gate_bounds), gate_bounds.shape[0],
+                                            gate_bounds.shape[1],
+                                            b_cap, d_hi, _ptr(score), _ptr(ids), cnt, _ptr(ws), ws.numel(), _stream()))
+    return score, ids
+
+
+@dense_mma_fused_topk.register_fake
+def _(passages, queries, bm25, w1, b1, w2, b2, stats, gate_bounds, b_cap, d_hi, k, id_base, counters):
     n_q = queries.shape[0]
     return (queries.new_empty((n_q, k), dtype=torch.float32), queries.new_empty((n_q, k), dtype=torch.int32))
 

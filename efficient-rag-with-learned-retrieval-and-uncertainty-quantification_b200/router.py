@@ -22,6 +22,7 @@ import logging
 from dataclasses import dataclass
 from typing import Any, Dict, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -144,6 +145,18 @@ class RetrievalRouter(nn.Module):
                 "routing_weights": weights.cpu().numpy(),
             }
 
+    def full_fusion_table(self, b_cap: float, d_hi: float, n_b: int = 128, n_d: int = 64) -> torch.Tensor:
+        """Device copy of ``full_fusion_bounds`` for this router, cached until a weight or statistic changes."""
+        tensors = list(self._weights()[:4]) + [self.bm25_mean, self.bm25_std, self.dense_mean, self.dense_std]
+        key = (float(b_cap), float(d_hi), int(n_b), int(n_d), tuple((t.data_ptr(), t._version) for t in tensors))
+        cache = self.__dict__.setdefault("_ff_cache", {})
+        if key not in cache:
+            cache.clear()
+            w1, b1, w2, b2, stats = (t.detach().cpu().numpy() for t in self._weights())
+            cache[key] = torch.from_numpy(full_fusion_bounds(w1, b1, w2, b2, stats, b_cap, d_hi, n_b, n_d)).to(
+                self.scorer[0].weight.device)
+        return cache[key]
+
     # ------------------------------------------------------------------------------------
     def mc_dropout(self, bm25_scores: torch.Tensor, dense_scores: torch.Tensor, n_samples: int = 30,
                    seed: Optional[int] = None, offset: int = 0, torch_layout: bool = False,
@@ -166,6 +179,99 @@ class RetrievalRouter(nn.Module):
         return RouterUncertainty(mean_gate=out[0], std_gate=out[1], mean_fused=out[2], std_fused=out[3],
                                  variance=out[4], consensus=out[5].to(torch.int64), n_samples=int(n_samples),
                                  masks=out[6] if return_samples else None, gates=out[7] if return_samples else None)
+
+
+def full_fusion_gate_range(w1, b1, w2, b2, stats, b_cap: float, d_hi: float, n_b: int = 128, n_d: int = 64,
+                           gate_slack: float = 1e-4) -> Tuple[np.ndarray, np.ndarray]:
+    """Proven bounds (lo, hi), float64 [n_b, n_d], of the running-statistics gate on a grid of cells.
+
+    lo[ib, id] <= gate(b, d) <= hi[ib, id] for every bm25 score b in [ib, ib+1] * b_cap / n_b and every
+    dense score d in -d_hi + [id, id+1] * 2 d_hi / n_d (router.py:130-132, 158-177).
+
+    How: the gate's pre-activation z(b, d) = b2 + sum_j w2_j * relu(A_j b + D_j d + C_j) is continuous
+    and piecewise linear, so over a rectangular cell it takes its extremes at a vertex of the line
+    arrangement: a cell corner, a crossing of a unit's zero line with a cell edge, or a crossing of two
+    zero lines inside the cell.  All of them are enumerated in float64 and sigma is monotone.
+    ``gate_slack`` covers the fp32 evaluation in the kernel.
+    """
+    w1 = np.asarray(w1, dtype=np.float64).reshape(-1, 3)
+    b1 = np.asarray(b1, dtype=np.float64).reshape(-1)
+    w2 = np.asarray(w2, dtype=np.float64).reshape(-1)
+    b2 = float(np.asarray(b2, dtype=np.float64).reshape(-1)[0])
+    st = np.asarray(stats, dtype=np.float32).reshape(4)
+    sb = float(np.float32(st[1] + np.float32(1e-6)))   # the kernel divides by float32(std + 1e-6)
+    sd = float(np.float32(st[3] + np.float32(1e-6)))
+    mb, md = float(st[0]), float(st[2])
+    lo, hi = np.zeros((n_b, n_d)), np.ones((n_b, n_d))
+    if not (np.isfinite(w1).all() and np.isfinite(b1).all() and np.isfinite(w2).all() and np.isfinite(b2)
+            and np.isfinite([sb, sd, mb, md]).all() and sb != 0.0 and sd != 0.0 and b_cap > 0 and d_hi > 0):
+        return lo, hi   # [0, 1] is always valid (bound = max(b, d): prunes little)
+    A = (w1[:, 0] - w1[:, 2]) / sb
+    D = (w1[:, 1] + w1[:, 2]) / sd
+    Cc = b1 - (w1[:, 0] - w1[:, 2]) * mb / sb - (w1[:, 1] + w1[:, 2]) * md / sd
+    wb, wd = b_cap / n_b, 2.0 * d_hi / n_d
+    b_edges = np.arange(n_b + 1, dtype=np.float64) * wb
+    d_edges = -d_hi + np.arange(n_d + 1, dtype=np.float64) * wd
+
+    def z_of(b, d):
+        pre = np.multiply.outer(b, A) + np.multiply.outer(d, D) + Cc
+        return b2 + np.maximum(pre, 0.0) @ w2
+
+    zmin = np.full((n_b, n_d), np.inf)
+    zmax = np.full((n_b, n_d), -np.inf)
+
+    def offer_point(b, d, z):
+        """A vertex belongs to every cell whose closed rectangle contains it (within 1e-6 cells of a grid line: both sides)."""
+        pb, pd = b / wb, (d + d_hi) / wd
+        for ib in (np.floor(pb - 1e-6).astype(np.int64), np.floor(pb + 1e-6).astype(np.int64)):
+            for idx in (np.floor(pd - 1e-6).astype(np.int64), np.floor(pd + 1e-6).astype(np.int64)):
+                ok = (ib >= 0) & (ib < n_b) & (idx >= 0) & (idx < n_d)
+                np.minimum.at(zmin, (ib[ok], idx[ok]), z[ok])
+                np.maximum.at(zmax, (ib[ok], idx[ok]), z[ok])
+
+    gb, gd = np.meshgrid(b_edges, d_edges, indexing="ij")                     # cell corners
+    offer_point(gb.reshape(-1), gd.reshape(-1), z_of(gb.reshape(-1), gd.reshape(-1)))
+    pts_b, pts_d = [], []
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dc = -(np.multiply.outer(b_edges, A) + Cc) / D                        # zero lines x vertical grid lines
+        pts_b.append(np.broadcast_to(b_edges[:, None], dc.shape).reshape(-1))
+        pts_d.append(dc.reshape(-1))
+        bc = -(np.multiply.outer(d_edges, D) + Cc) / A                        # zero lines x horizontal grid lines
+        pts_b.append(bc.reshape(-1))
+        pts_d.append(np.broadcast_to(d_edges[:, None], bc.shape).reshape(-1))
+        i, j = np.triu_indices(A.shape[0], 1)                                 # crossings of two zero lines
+        det = A[i] * D[j] - A[j] * D[i]
+        pts_b.append((-Cc[i] * D[j] + Cc[j] * D[i]) / det)
+        pts_d.append((-A[i] * Cc[j] + A[j] * Cc[i]) / det)
+    bx, dx = np.concatenate(pts_b), np.concatenate(pts_d)
+    ok = np.isfinite(bx) & np.isfinite(dx) & (bx >= 0) & (bx <= b_cap) & (dx >= -d_hi) & (dx <= d_hi)
+    if ok.any():
+        offer_point(bx[ok], dx[ok], z_of(bx[ok], dx[ok]))
+    sig = lambda x: 1.0 / (1.0 + np.exp(-np.clip(x, -700.0, 700.0)))  # noqa: E731
+    return np.clip(sig(zmin) - gate_slack, 0.0, 1.0), np.clip(sig(zmax) + gate_slack, 0.0, 1.0)
+
+
+def _bf16_bits(x: np.ndarray, up: bool) -> np.ndarray:
+    """bfloat16 bit patterns of non-negative float64 values, rounded down (up=False) or up (up=True)."""
+    f = x.astype(np.float32)
+    f = np.where(f.astype(np.float64) > x, np.nextafter(f, np.float32(-1.0)), f) if not up else \
+        np.where(f.astype(np.float64) < x, np.nextafter(f, np.float32(2.0)), f)
+    bits = f.astype(np.float32).view(np.uint32)
+    if up:
+        bits = bits + np.where(bits & 0xFFFF, np.uint32(0x10000), np.uint32(0))
+    return (bits >> 16).astype(np.uint32)
+
+
+def full_fusion_bounds(w1, b1, w2, b2, stats, b_cap: float, d_hi: float, n_b: int = 128, n_d: int = 64) -> np.ndarray:
+    """The gate-bound table ragb_dense_mma_fused_topk takes (include/ragb200.h): int32 [n_b, n_d], bits 0-15 = bf16
+    lower bound (rounded down), bits 16-31 = bf16 upper bound (rounded up) of the gate on each cell; the last bm25
+    row is (0, 1) because it also receives bm25 >= b_cap and bm25 < 0.  The table only prunes gate evaluations
+    (fused = b + g (d - b) <= b + (d <= b ? lo : hi) (d - b)), it never changes results."""
+    lo, hi = full_fusion_gate_range(w1, b1, w2, b2, stats, b_cap, d_hi, n_b, n_d)
+    lo[n_b - 1, :] = 0.0
+    hi[n_b - 1, :] = 1.0
+    packed = (_bf16_bits(hi, True) << 16) | _bf16_bits(lo, False)
+    return packed.astype(np.uint32).view(np.int32)
 
 
 def torch_dropout_increment(n_elements: int, sm_count: int) -> int:

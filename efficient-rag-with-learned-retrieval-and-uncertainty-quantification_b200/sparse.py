@@ -115,6 +115,11 @@ class SparseShard:
         return ops.bm25_score_topk(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1,
                                    self.dense_tf, self.dense_terms, q_terms, q_off, max_terms, self.id_base, k)
 
+    def scores_tiled(self, q_terms: Tensor, q_off: Tensor, max_terms: int, out: Tensor) -> None:
+        """get_scores of a batch written into the tiled matrix ``out[ceil(n_docs / 256), rows >= B, 256]``."""
+        ops.bm25_scores_tiled(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1,
+                              self.dense_tf, self.dense_terms, q_terms, q_off, max_terms, out)
+
     def scores(self, q_terms: Tensor, q_off: Tensor, max_terms: int) -> Tensor:
         return ops.bm25_scores(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1,
                                self.dense_tf, self.dense_terms, q_terms, q_off, max_terms)

@@ -83,13 +83,18 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
                          int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          float* out_score, int32_t* out_id,
                          void* workspace, size_t workspace_bytes, ragb_stream_t stream);
-/* Same arithmetic, full score vectors out_scores[n_queries, n_docs] (get_scores itself). */
+/* Same arithmetic, full score vectors (get_scores itself).
+ * tiled = 0: out_scores[q * out_ld + d], out_ld >= n_docs (row-major).
+ * tiled = 1: out_scores[((d / 256) * out_ld + q) * 256 + d % 256], out_ld >= n_queries: 256-document tiles
+ *            with the query rows of a tile next to each other, ceil(n_docs / 256) * out_ld * 256 floats.
+ *            This is the layout ragb_dense_mma_fused_topk reads (one contiguous piece per GEMM tile). */
 int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf,
                      const float* norm, const float* idf, int64_t vocab, double k1,
                      const uint8_t* dense_tf, int64_t dense_stride,
                      const int32_t* dense_terms, int32_t n_dense,
                      const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
-                     int32_t max_query_terms, int64_t n_docs, float* out_scores, ragb_stream_t stream);
+                     int32_t max_query_terms, int64_t n_docs, float* out_scores, int64_t out_ld,
+                     int32_t tiled, ragb_stream_t stream);
 
 /* ---- dense scoring : DenseIndex.search (rag_uq/streaming_index.py:353-370) -----------
  * Exact inner product of bf16 query rows with bf16 passage rows (unit rows -> cosine,
@@ -111,7 +116,33 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
                         const void* queries_bf16, int32_t n_queries, int32_t k, int64_t id_base,
                         int32_t variant, float* out_score, int32_t* out_id,
                         void* workspace, size_t workspace_bytes, ragb_stream_t stream);
-/* Plain score matrix out[n_queries, n_rows] fp32 (small shapes, tests, full-fusion mode). */
+/* Full-fusion mode: RetrievalRouter.hybrid_rerank (rag_uq/router.py:179-202) evaluated over ALL
+ * passages of the shard inside the epilogue of the tcgen05 GEMM: for every (query, passage)
+ *   fused = gate(bm25, dense) * dense + (1 - gate) * bm25,   gate = RetrievalRouter.forward with
+ * running statistics (stats_initialized == True, router.py:130-132), dense = the accumulator in TMEM,
+ * bm25 = the TILED matrix ragb_bm25_scores(..., tiled = 1) wrote with out_ld = bm25_rows
+ * (32-byte aligned).  Output: the k best fused scores per query and their global ids; neither the
+ * dense nor the fused score matrix ever exists in memory.
+ * gate_bound_table[ib * n_d + id] (n_d a power of two, n_b * n_d <= 8192 cells, staged in shared
+ * memory) packs two bfloat16 numbers, bits 0-15 = lo and bits 16-31 = hi, with lo <= gate(bm25, dense) <= hi over the
+ * cell  bm25 in [ib, ib+1) * b_cap / n_b  x  dense in -d_hi + [id, id+1) * 2 d_hi / n_d; the last
+ * bm25 row (which also receives bm25 >= b_cap and bm25 < 0) must hold lo = 0, hi = 1; d_hi must
+ * bound |dense| for every pair (e.g. max passage norm x max query norm).
+ * The table only prunes gate evaluations (a pair is skipped when
+ * bm25 + (dense <= bm25 ? lo : hi) * (dense - bm25) is below the query's running k-th best fused
+ * score), it never changes results: lo = 0, hi = 1 everywhere is valid (and slow).
+ * rag_uq_b200.router.full_fusion_bounds derives a tight table from the router's weights.
+ * counters: NULL or 2 device uint64 that receive (gate evaluations, list admissions).
+ * Workspace: ragb_dense_mma_workspace_bytes(n_queries, k). */
+int ragb_dense_mma_fused_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
+                              const void* queries_bf16, int32_t n_queries, int32_t k, int64_t id_base,
+                              const float* bm25_scores, int64_t bm25_rows,
+                              const float* w1, const float* b1, const float* w2, const float* b2,
+                              const float* stats, int32_t hidden,
+                              const uint32_t* gate_bound_table, int32_t n_b, int32_t n_d, float b_cap, float d_hi,
+                              float* out_score, int32_t* out_id, unsigned long long* counters,
+                              void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+/* Plain score matrix out[n_queries, n_rows] fp32 (small shapes, tests, un-fused full-fusion mode). */
 int ragb_dense_scores(const void* passages_bf16, int64_t n_rows, int32_t dim,
                       const void* queries_bf16, int32_t n_queries, float* out_scores,
                       ragb_stream_t stream);

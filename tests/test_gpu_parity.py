@@ -349,6 +349,54 @@ def test_full_fusion_mode_c1(rq, dev):
     assert (ids.cpu().long() == want_i).float().mean() > 0.99
 
 
+@pytest.mark.parametrize("n,n_q,k,hidden,scale", [(10_000, 64, 10, 64, 1.0), (33_331, 200, 50, 32, 4.0),
+                                                  (200_000, 384, 10, 64, 1.0), (4099, 130, 100, 128, 10.0)])
+def test_full_fusion_fused_epilogue(rq, dev, n, n_q, k, hidden, scale):
+    """The tcgen05 epilogue with gate + fusion inside equals the un-fused full-fusion path (itself pinned to the
+    oracle in test_full_fusion_mode_c1) and the torch-CPU oracle; the gate-bound table prunes without changing results."""
+    from rag_uq_b200 import synth
+    dim = 768
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    passages = synth.passage_embeddings(0, n, dim, dev)
+    engine = rq.HybridEngine(rq.build_shard(doc_off, doc_tok, vocab).finalize(), passages, id_base=1000)
+    qb = synth.make_queries(n_q, n, dim, cdf, dev)
+    torch.manual_seed(11)
+    router = rq.RetrievalRouter(rq.RouterConfig(hidden_dim=hidden)).to(dev).eval()
+    with torch.no_grad():
+        for p in router.parameters():
+            p.mul_(scale)                      # scale > 1: a gate that swings between 0 and 1 like a trained one
+    router.bm25_mean.fill_(8.0); router.bm25_std.fill_(6.0); router.dense_mean.fill_(0.1); router.dense_std.fill_(0.2)
+    router.stats_initialized = True
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    with torch.no_grad():
+        fs, fi = engine.full_fusion_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, fused=True,
+                                         counters=counters)
+        us, ui = engine.full_fusion_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, fused=False,
+                                         query_chunk=64)
+    # the two paths see dense scores from different fp32 accumulation orders (tensor core vs CUDA cores, ~1e-7);
+    # a steep gate (scale > 1) amplifies that by |dense - bm25| * gate slope
+    tol = 1e-5 * max(1.0, scale * scale)
+    torch.testing.assert_close(fs, us, rtol=tol, atol=tol)
+    same = (fi == ui)
+    assert same.float().mean() > 0.99
+    # where the ids differ the scores must be within rounding of each other (a near-tie swapped)
+    assert bool(((fs - us).abs()[~same] <= tol * us.abs()[~same] + 1e-6).all())
+    evals, admits = (int(v) for v in counters.tolist())
+    assert 0 < admits <= evals <= n_q * n
+    if n >= 100_000:                           # the bound prunes most gate evaluations once the lists have warmed up
+        assert evals < 0.2 * n_q * n           # (a small corpus never leaves warm-up: ~150 passages per list)
+    if n <= 40_000:
+        okapi = bm25_okapi.OkapiCsr(doc_off.cpu().numpy(), doc_tok.cpu().numpy(), vocab)
+        terms = qb.q_terms.view(n_q, -1).cpu().numpy()
+        bm = torch.tensor(np.stack([okapi.get_scores(terms[q]) for q in range(n_q)]), dtype=torch.float32)
+        de = torch.tensor(dense_fusion.dense_scores(passages.float().cpu().numpy(), qb.q_emb.float().cpu().numpy()),
+                          dtype=torch.float32)
+        state = {key: v.detach().cpu() for key, v in router.state_dict().items()}
+        want_s, want_i = router_oracle.hybrid_rerank(bm, de, state, True, k)
+        torch.testing.assert_close(fs.cpu(), want_s, rtol=3 * tol, atol=3 * tol)
+        assert (fi.cpu().long() - 1000 == want_i).float().mean() > 0.98
+
+
 def test_row_sharded_engine_equals_single_engine(rq, dev):
     """Emulate G = 2 on one GPU: local pools per shard, merged exactly as the all-gather path merges."""
     from rag_uq_b200 import synth
