@@ -26,7 +26,7 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
-METRIC = "hybrid top-10 queries/sec over 10Mx768 passages"
+METRIC = "hybrid top-10 queries/sec over 10Mx768 passages"   # BASELINE.json metric; metric_name() relabels other shapes
 UNIT = "queries/s"
 DIM = 768
 
@@ -46,10 +46,23 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--overlap", action="store_true",
                    help="run the BM25 and the dense kernel on two streams (measured: no gain, see engine.local_pools)")
-    p.add_argument("--workload", default="c3", choices=["c3", "c2"],
+    p.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],
                    help="c3 (default, headline): 10M passages, batch 1024, tcgen05 dense.  c2: BASELINE.json configs[1], "
-                        "1M passages, batch-1 GEMV + BM25 (sets --passages 1000000 --batch 1 unless given)")
+                        "1M passages, batch-1 GEMV + BM25 (sets --passages 1000000 --batch 1 unless given).  c4: c3 + "
+                        "MC-Dropout T=30 over the top-100 fused candidates (configs[3]).  c5: 100M passages, 5M-term "
+                        "index, top-100 (configs[4]; needs 8 GPUs)")
+    p.add_argument("--mode", default="pool", choices=["pool", "full-fusion"],
+                   help="pool (default): the reference's hybrid_search semantics (pool-50 union, max-normalised fusion, "
+                        "router rerank of the top-k).  full-fusion: router gate + learned fusion for EVERY (query, "
+                        "passage) pair inside the tcgen05 epilogue (RetrievalRouter.hybrid_rerank over [B, N])")
+    p.add_argument("--mc-samples", type=int, default=0, help="MC-Dropout passes over the fused candidates (c4: 30)")
+    p.add_argument("--candidates", type=int, default=0, help="fused candidates kept per query before the rerank (c4: 100)")
     return p.parse_args()
+
+
+def metric_name(args) -> str:
+    return METRIC if (args.k == 10 and args.passages == 10_000_000) else \
+        f"hybrid top-{args.k} queries/sec over {args.passages / 1e6:g}Mx{DIM} passages"
 
 
 def peaks():
@@ -147,7 +160,7 @@ def run_reference(args):
             values.append(full)
     value = sum(values) / len(values)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / value, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"hybrid top-{args.k} (BM25 pool {args.pool} + exact dense pool {args.pool} + fusion + router), "
@@ -248,6 +261,11 @@ def run_ours(args):
     def step(q_terms, q_off, q_emb, probes=None):
         with torch.no_grad():
             events = {} if probes is not None else None
+            if args.mode == "full-fusion":
+                vals, ids = engine.full_fusion_topk(q_terms, q_off, max_terms, q_emb, router, args.k, events=events)
+                if probes is not None:   # one (start, end) pair per kernel, first to last query chunk
+                    probes.append({name: (ev[0][0], ev[-1][1]) for name, ev in events.items()})
+                return ids, vals
             bs, bi, ds, di = engine.local_pools(q_terms, q_off, max_terms, q_emb, args.pool,
                                                 overlap=args.overlap, events=events)
             if probes is not None:
@@ -260,8 +278,11 @@ def run_ours(args):
                 gi = gi.view(bs.shape[0], world, 2, args.pool)
                 bs, bi = ops.topk_merge(gs[:, :, 0].contiguous(), gi[:, :, 0].contiguous(), args.pool)
                 ds, di = ops.topk_merge(gs[:, :, 1].contiguous(), gi[:, :, 1].contiguous(), args.pool)
-            ids, sb, sd, sh = ops.hybrid_fuse_topk(bs, bi, ds, di, args.k)
+            ids, sb, sd, sh = ops.hybrid_fuse_topk(bs, bi, ds, di, max(args.k, args.candidates))
             vals, order = router.hybrid_rerank(sb, sd, top_k=args.k)
+            if args.mc_samples > 0:   # config C4: T stochastic router passes over the fused candidates
+                unc = router.mc_dropout(sb, sd, n_samples=args.mc_samples)
+                return torch.gather(ids, 1, order.to(torch.int64)), vals, unc.confidence
             return torch.gather(ids, 1, order.to(torch.int64)), vals
 
     def barrier():
@@ -274,18 +295,19 @@ def run_ours(args):
         barrier()
         launches0 = ops.launch_count()
         start, stop = ev(), ev()
+        torch.cuda.nvtx.range_push("bench_timed")   # lets `ncu --nvtx --nvtx-include bench_timed/` list exactly these launches
         start.record()
         out = None
         for s in range(n_steps):
             if from_host:
                 ht, ho, he = host[s % n_sets]
                 qt, qo, qe = ht.to(dev, non_blocking=True), ho.to(dev, non_blocking=True), he.to(dev, non_blocking=True)
-                ids, vals = step(qt, qo, qe)
-                out = (ids.cpu(), vals.cpu())          # device -> host read of the step's result
+                out = tuple(t.cpu() for t in step(qt, qo, qe))   # device -> host read of the step's result
             else:
                 b = batches[s % n_sets]
                 out = step(b.q_terms, b.q_off, b.q_emb, probes)
         stop.record()
+        torch.cuda.nvtx.range_pop()
         barrier()
         ms = start.elapsed_time(stop)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -322,11 +344,16 @@ def run_ours(args):
         toff = engine.sparse.term_off
         sum_df = int((toff[qt[ok] + 1] - toff[qt[ok]]).sum())
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"hybrid top-{args.k}: BM25 pool {args.pool} over CSR + exact dense pool {args.pool} "
-                                   f"({'bf16 GEMV' if args.batch <= 8 else 'tcgen05 variant ' + str(args.variant)}) + fusion + router rerank; {args.passages} passages x {DIM} "
+            "config": {"workload": (f"hybrid top-{args.k}: BM25 pool {args.pool} over CSR + exact dense pool {args.pool} "
+                                    f"({'bf16 GEMV' if args.batch <= 8 else 'tcgen05 variant ' + str(args.variant)}) + fusion + router rerank"
+                                    + (f" + MC-Dropout T={args.mc_samples} over {max(args.k, args.candidates)} candidates" if args.mc_samples else "")
+                                    if args.mode == "pool" else
+                                    f"full-fusion top-{args.k}: BM25 get_scores matrix + tcgen05 GEMM with router gate, learned "
+                                    f"fusion and top-k in the epilogue (every (query, passage) pair)")
+                                   + f"; {args.passages} passages x {DIM} "
                                    f"bf16 row-sharded over {world} GPU(s), batch {args.batch} queries x 8 terms",
                        "l2": "inputs exceed L2 (embedding shard %.1f GB, postings %.1f GB per GPU); 4 rotating query batches"
                              % (n_local * DIM * 2 / 1e9, engine.sparse.nnz * 6 / 1e9),
@@ -355,12 +382,28 @@ def run_ours(args):
                        "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
                        "traffic": None, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
                        "ms_per_launch": dense_avg, "flops_per_launch": flops})
-        bm25_gbs = sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9
+        bm25_bytes = sum_df * 6.0 + (4.0 * n_local * args.batch if args.mode == "full-fusion" else 0.0)
+        bm25_gbs = bm25_bytes / (bm25_avg / 1000.0) / 1e9
         bm25_roof = {"bound": "hbm", "kernel": "bm25_kernel (+ stripe merge)", "achieved": bm25_gbs, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": bm25_gbs / pk["hbm_gbs"], "traffic": None,
                      "peak_source": pk["source"] + " copy bandwidth", "ms_per_launch": bm25_avg,
-                     "bytes_per_launch": sum_df * 6.0,
-                     "note": "algorithmic bytes = 6 B x sum of document frequencies of the batch's query terms"}
+                     "bytes_per_launch": bm25_bytes,
+                     "note": "algorithmic bytes = 6 B x sum of document frequencies of the batch's query terms"
+                             + (" + 4 B x passages x queries for the score matrix" if args.mode == "full-fusion" else "")}
+        # measured DRAM traffic per launch (dram__bytes_read + dram__bytes_write of one ncu --set full capture of this
+        # very command, profiles/traffic_r01.json); only quoted when the workload is the one that was profiled
+        tpath = ROOT / "profiles" / "traffic_r01.json"
+        if tpath.exists():
+            tr = json.loads(tpath.read_text())
+            wl = tr["workload"]
+            if (wl["passages"], wl["batch"], wl["k"], wl["pool"], wl["n_gpus"], wl["mode"]) == \
+                    (args.passages, args.batch, args.k, args.pool, world, args.mode):
+                kb, kd = tr["kernels"].get("bm25_kernel"), tr["kernels"].get("dense_mma_pair_kernel")
+                if kb:
+                    bm25_roof["traffic"] = kb["dram_bytes_read"] + kb["dram_bytes_write"]
+                if kd and not gemv and args.variant == 3:
+                    dense_roof["traffic"] = kd["dram_bytes_read"] + kd["dram_bytes_write"]
+                    dense_roof["traffic_note"] = "algorithmic HBM bytes of this tensor-bound kernel: the embedding shard once = %.3g" % (n_local * DIM * 2.0)
         # the roofline object describes the kernel that takes most of the step
         line["roofline"], line["roofline_secondary"] = (dense_roof, bm25_roof) if dense_avg >= bm25_avg else (bm25_roof, dense_roof)
         if not args.no_cpu_baseline and world == 1:
@@ -380,6 +423,16 @@ if __name__ == "__main__":
             a.passages = 1_000_000
         if "--batch" not in sys.argv:
             a.batch = 1
+    if a.workload == "c4":
+        a.mc_samples = a.mc_samples or 30
+        a.candidates = a.candidates or 100
+    if a.workload == "c5":
+        if "--passages" not in sys.argv:
+            a.passages = 100_000_000
+        if "--k" not in sys.argv:
+            a.k = 100
+        if "--pool" not in sys.argv:
+            a.pool = 100
     if a.impl == "reference":
         run_reference(a)
     else:
