@@ -297,16 +297,28 @@ __device__ __forceinline__ void epilogue_scan(const MmaArgs& a, const uint32_t t
         // room for a whole chunk is guaranteed up front, so the admission loop has no votes in it
         const unsigned full = __ballot_sync(0xffffffffu, st.cnt > LIST_CAP - 32);
         if (full) st = compact_lists<KPL>(warp_lists, full, lane, a.k, st);
-        if (m >= st.thr_score) {
-          const int32_t id0 = static_cast<int32_t>(a.id_base + row0) + c * 32;
-          const int lim = valid - c * 32;
+        // 32 different queries share the warp, so in the warm-up phase (and on small shards for the whole
+        // kernel) some lane has a candidate in almost every chunk.  Walking all 32 columns with a compare,
+        // a bounds test and a predicated append each cost ~25 instructions per column (47% of the samples at
+        // 1.25M rows, k = 50).  Instead every lane records its candidates in a bit mask (2 instructions per
+        // column) and the warp then serves one candidate per lane per round: a register select picks the
+        // score, so nothing is indexed dynamically; the number of rounds is the largest candidate count of
+        // any lane - one or two outside the first chunks of a list.
+        const int32_t id0 = static_cast<int32_t>(a.id_base + row0) + c * 32;
+        const int lim = valid - c * 32;
+        uint32_t pm = 0u;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float s = __uint_as_float(v[i]);
-            if (s >= st.thr_score && i < lim) {
-              const uint64_t key = make_key(s, id0 + i);
-              if (key > st.thr_key) my_list[st.cnt++] = key;
-            }
+        for (int i = 0; i < 32; ++i) pm |= (__uint_as_float(v[i]) >= st.thr_score) ? (1u << i) : 0u;
+        if (lim < 32) pm &= lim <= 0 ? 0u : ((1u << lim) - 1u);
+        while (__any_sync(0xffffffffu, pm != 0u)) {
+          const int sel = __ffs(pm) - 1;
+          float sv = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv = i == sel ? __uint_as_float(v[i]) : sv;
+          if (pm != 0u) {
+            const uint64_t key = make_key(sv, id0 + sel);
+            if (key > st.thr_key) my_list[st.cnt++] = key;
+            pm &= pm - 1u;
           }
         }
       }
@@ -1078,7 +1090,14 @@ static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const 
   return RAGB_OK;
 }
 
-static int mma_list_kpl(int k) { return k <= 32 ? 2 : (k <= 96 ? 4 : 8); }  // capacity 32*KPL >= k + 32
+static int mma_list_kpl(int k) {   // capacity 32*KPL >= k + 32
+  static const int forced = [] {
+    const char* e = getenv("RAGB_MMA_KPL");  // tuning aid only: a larger list is compacted less often
+    return e ? atoi(e) : 0;
+  }();
+  const int kpl = k <= 32 ? 2 : (k <= 96 ? 4 : 8);
+  return (forced == 4 || forced == 8) && forced > kpl ? forced : kpl;
+}
 static size_t mma_list_bytes(int k) {
   return static_cast<size_t>(148) * 2 * MM_BM * (32 * mma_list_kpl(k) + 1) * sizeof(uint64_t);
 }
