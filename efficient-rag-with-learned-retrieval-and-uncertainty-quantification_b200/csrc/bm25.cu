@@ -35,6 +35,8 @@
 // ballot prefix, rare warp-level bitonic merge), so the main loop has no block barrier at all; the
 // 8 warp lists are folded once at the end of the block and the per-block lists of all stripes
 // are merged by topk_merge_kernel.
+#include <cuda_fp16.h>
+
 #include <climits>
 #include <cstdlib>
 
@@ -51,9 +53,11 @@ constexpr int BM_SUPER_DOCS = BM_RANGE * BM_SUPER;
 constexpr int BM_MAX_TERMS = 64;
 constexpr int BM_MAX_DENSE = 1024;  // rows of the dense tf table (term ids sorted ascending)
 constexpr int BM_SEARCH = 4;  // posting lists searched concurrently while placing the cursors
+constexpr int BM_APPROX_MAX = 320;  // fp16 bound pass: fall back to the exact table path when more documents of a super-range pass
 
 // debug counters (RAGB_BM25_DEBUG=1): [0] super-ranges full mode, [1] pruned, [2] pruned with postings,
-// [3] documents scored in pruned mode, [4] queries seeded, [5] queries with seed > table bound
+// [3] documents scored in pruned mode, [4] queries seeded, [5] queries with seed > table bound,
+// [6] super-ranges decided by the fp16 bound pass, [7] bound passes that fell back to the exact table path
 __device__ unsigned long long g_bm25_dbg[8];
 
 struct Bm25Args {
@@ -80,6 +84,8 @@ struct Bm25Args {
   const int32_t* dense_terms;  // [n_dense] term id of each row
   int64_t dense_stride;      // multiple of BM_RANGE, >= n_docs
   int n_dense;
+  const __half* dense_imp;   // optional [n_dense, dense_stride]: fp16 UPPER bound of tf / (tf + norm) per (table term, document)
+  const float* dense_maximp; // optional [n_dense]: row maxima of dense_imp (a term contributes at most weight * maximp)
   float* seed_thr;           // [queries] proven lower bound of each query's k-th best score (0 = none)
   int debug;
 };
@@ -162,6 +168,8 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   if (!DENSE_OUT) sp += sizeof(uint64_t) * a.capacity * BM_WARPS;
   const uint8_t** s_drow = reinterpret_cast<const uint8_t**>(sp) + warp * mt;  // dense-table row of each dense term
   sp += sizeof(uint8_t*) * BM_WARPS * mt;
+  const __half** s_irow = reinterpret_cast<const __half**>(sp) + warp * mt;     // its row of fp16 impact bounds
+  sp += sizeof(__half*) * BM_WARPS * mt;
   float* sacc = reinterpret_cast<float*>(sp) + warp * BM_SUPER_DOCS;  // posting-list contributions of a super-range
   sp += sizeof(float) * BM_WARPS * BM_SUPER_DOCS;
   unsigned* s_bits = reinterpret_cast<unsigned*>(sp) + warp * (BM_SUPER_DOCS / 32);  // documents touched by a posting
@@ -200,6 +208,7 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   const int qb = a.q_off[q];
   const int nt = min(a.q_off[q + 1] - qb, mt);
   int nd = 0, ns = 0;  // dense / sparse term counts (warp-uniform)
+  float ub_lane = 0.0f, ubw_lane = 0.0f;  // this lane's share of the table-term bounds (tight / weights only)
   for (int base = 0; base < nt; base += 32) {
     const int ti = base + lane;
     int t = -1, slot = -1;
@@ -222,7 +231,11 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
     if (live && slot >= 0) {
       const int o = nd + __popc(md & ((1u << lane) - 1));
       s_drow[o] = a.dense_tf + static_cast<int64_t>(slot) * a.dense_stride;
+      s_irow[o] = a.dense_imp != nullptr ? a.dense_imp + static_cast<int64_t>(slot) * a.dense_stride : nullptr;
       s_dwgt[o] = w;
+      const float wp = fmaxf(w, 0.0f);
+      ubw_lane += wp;
+      ub_lane += a.dense_maximp != nullptr ? wp * a.dense_maximp[slot] : wp;
     }
     if (live && slot < 0) s_tmp[ns + __popc(ms & ((1u << lane) - 1))] = t;
     nd += __popc(md);
@@ -234,10 +247,16 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   // of the table terms (tf / (tf + norm) < 1).  Once the warp's k-th best score exceeds that bound,
   // only documents touched by a posting list can still qualify (the "essential lists" of MaxScore):
   // exact, and it turns ~10M evaluations per query into the ~80k documents its rarer terms occur in.
-  float ub_table = 0.0f;
-  for (int i = lane; i < nd; i += 32) ub_table += fmaxf(s_dwgt[i], 0.0f);
+  // With the row maxima of the impact bounds (tf / (tf + norm) <= maximp < 1) the bound is 10-20% tighter.
+  float ub_table = ub_lane, ub_weights = ubw_lane;
 #pragma unroll
-  for (int sh = 16; sh > 0; sh >>= 1) ub_table += __shfl_xor_sync(0xffffffffu, ub_table, sh);
+  for (int sh = 16; sh > 0; sh >>= 1) {
+    ub_table += __shfl_xor_sync(0xffffffffu, ub_table, sh);
+    ub_weights += __shfl_xor_sync(0xffffffffu, ub_weights, sh);
+  }
+  ub_table *= 1.000001f;  // the exact path multiplies by an approximate reciprocal (1 ulp)
+  // fp16 bound pass: every HFMA2 rounds once, |error| <= 2^-11 * (partial sum <= ub_weights)
+  const float approx_slack = static_cast<float>(nd) * ub_weights * (1.0f / 2048.0f) * 1.01f + 1e-3f;
 
   if (a.debug && tid == 0 && blockIdx.y == 0) {
     if (seed_dbg > 0.0f) atomicAdd(&g_bm25_dbg[4], 1ull);
@@ -315,6 +334,28 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   }
   __syncwarp();
 
+  // ---- MaxScore over the posting-list terms.  Rank them by weight (ascending); psum = weight of a term plus
+  // all lighter ones.  While  ub_table + psum(rank j) < thr  the j+1 lightest terms are NON-essential: a document
+  // that only they (and table terms) touch cannot reach thr, so their postings still feed the accumulator but no
+  // longer mark documents for scoring.  The heavy (rare) terms that stay essential have short lists: at 10M
+  // passages this takes the documents scored per query from ~310k to a third of that.
+  // Lane ti < ntv holds rank and psum of term ti; needs ntv <= 32 and no negative weight.
+  int my_rank = 0;
+  float my_psum = INFINITY;
+  bool maxscore = !DENSE_OUT && ntv > 0 && ntv <= 32;
+  if (maxscore) {
+    const float wt = lane < ntv ? s_wgt[lane] : INFINITY;
+    maxscore = !__any_sync(0xffffffffu, lane < ntv && !(wt > 0.0f));
+    float ps = 0.0f;
+    for (int j = 0; j < ntv; ++j) {
+      const float wj = __shfl_sync(0xffffffffu, wt, j);
+      const bool before = wj < wt || (wj == wt && j < lane);   // strict total order, duplicates by position
+      my_rank += before ? 1 : 0;
+      ps += (before || j == lane) ? wj : 0.0f;
+    }
+    if (lane < ntv) my_psum = ps;
+  }
+
   const int j0 = lane * 8;  // the 8 documents of a range this lane owns
   for (int sup = 0; sup < n_super; ++sup) {
     const int64_t s0l = w_begin + static_cast<int64_t>(sup) * BM_SUPER_DOCS;
@@ -332,6 +373,13 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
       } else {
         have_sparse = true;
       }
+    }
+    // non-essential terms of this super-range (the threshold only rises, so the set only grows)
+    // (n_noness > 0 implies thr > ub_table, i.e. the marked-documents path below)
+    int n_noness = 0;
+    if (maxscore) {
+      const float thr_safe = tk.thr_score - 2e-5f * fabsf(tk.thr_score);
+      n_noness = __popc(__ballot_sync(0xffffffffu, lane < ntv && ub_table + my_psum < thr_safe));
     }
     if (have_sparse) {
 #pragma unroll
@@ -351,11 +399,13 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         const int64_t end = s_end[ti];
         const float w = s_wgt[ti];
         int next_doc;
+        // a non-essential term adds to the accumulator but marks nothing
+        unsigned* const mark = (n_noness > 0 && __shfl_sync(0xffffffffu, my_rank, ti & 31) < n_noness) ? nullptr : touched;
         switch (s_dense[ti]) {  // chunks per pass sized to the term's density (warp-uniform)
-          case 0: stream_term<1>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, touched, lane, next_doc); break;
-          case 1: stream_term<2>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, touched, lane, next_doc); break;
-          case 2: stream_term<4>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, touched, lane, next_doc); break;
-          default: stream_term<8>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, touched, lane, next_doc); break;
+          case 0: stream_term<1>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
+          case 1: stream_term<2>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
+          case 2: stream_term<4>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
+          default: stream_term<8>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
         }
         if (lane == 0) {
           s_pos[ti] = pos;
@@ -364,10 +414,67 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         __syncwarp();
       }
     }
-    if (a.debug && lane == 0) atomicAdd(&g_bm25_dbg[(!DENSE_OUT && tk.thr_score > ub_table) ? (have_sparse ? 2 : 1) : 0], 1ull);
-    if (!DENSE_OUT && tk.thr_score > ub_table) {
-      // ---- pruned mode: score only the documents a posting list touched (one bit each)
-      if (have_sparse) {
+    // ---- which documents of this super-range have to be scored exactly?
+    //  * thr > ub_table: only those a posting list touched (the "essential lists" of MaxScore);
+    //  * otherwise, once the threshold is a sizeable fraction of the table bound: an fp16 UPPER bound of
+    //    the table score of every document (one 128-bit load and four HFMA2 per term per 8 documents,
+    //    12x fewer instructions than the exact path) marks the few that may still reach thr; the exact
+    //    arithmetic then runs for the marked and the touched documents only.  Too many marks (the list
+    //    is still warming up): fall through to the exact table path for the whole super-range.
+    bool use_bits = false, bits_valid = have_sparse;
+    if (!DENSE_OUT) {
+      if (tk.thr_score > ub_table) {
+        use_bits = true;
+      } else if (a.dense_imp != nullptr && nd > 0 && tk.thr_score - approx_slack > 0.5f * ub_table) {   // n_noness == 0 here
+        if (!have_sparse) {
+          s_bits[lane] = 0u;
+          __syncwarp();
+        }
+        const __half2 thr2 = __half2half2(__float2half_rd(tk.thr_score - approx_slack));
+#pragma unroll 1
+        for (int r = 0; r < BM_SUPER; ++r) {
+          const int d0 = s0 + r * BM_RANGE;
+          if (d0 >= s1) break;
+          __half2 acc[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = __float2half2_rn(0.0f);
+          const int64_t off = static_cast<int64_t>(d0) + j0;
+          uint4 cur = __ldg(reinterpret_cast<const uint4*>(s_irow[0] + off));
+          for (int i = 0; i < nd; ++i) {
+            const __half2 w2 = __half2half2(__float2half_ru(fmaxf(s_dwgt[i], 0.0f)));
+            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+            if (i + 1 < nd) nxt = __ldg(reinterpret_cast<const uint4*>(s_irow[i + 1] + off));
+            acc[0] = __hfma2(w2, *reinterpret_cast<const __half2*>(&cur.x), acc[0]);
+            acc[1] = __hfma2(w2, *reinterpret_cast<const __half2*>(&cur.y), acc[1]);
+            acc[2] = __hfma2(w2, *reinterpret_cast<const __half2*>(&cur.z), acc[2]);
+            acc[3] = __hfma2(w2, *reinterpret_cast<const __half2*>(&cur.w), acc[3]);
+            cur = nxt;
+          }
+          unsigned m8 = 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const unsigned mk = __hge2_mask(acc[j], thr2);   // 0xFFFF per half that passes
+            m8 |= ((mk & 1u) | ((mk >> 15) & 2u)) << (2 * j);
+          }
+          const int left = s1 - d0 - j0;                    // documents of this lane that exist
+          if (left < 8) m8 &= left <= 0 ? 0u : ((1u << left) - 1u);
+          if (m8) atomicOr(s_bits + r * (BM_RANGE / 32) + (lane >> 2), m8 << ((lane & 3) * 8));
+        }
+        __syncwarp();
+        int marks = __popc(s_bits[lane]);
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) marks += __shfl_xor_sync(0xffffffffu, marks, sh);
+        if (marks <= BM_APPROX_MAX) {
+          use_bits = true;
+          bits_valid = true;
+        }
+        if (a.debug && lane == 0) atomicAdd(&g_bm25_dbg[use_bits ? 6 : 7], 1ull);
+      }
+    }
+    if (a.debug && lane == 0) atomicAdd(&g_bm25_dbg[use_bits ? (have_sparse ? 2 : 1) : 0], 1ull);
+    if (use_bits) {
+      // ---- score only the marked documents (one bit each)
+      if (bits_valid) {
         unsigned word = s_bits[lane];
         if (a.debug) atomicAdd(&g_bm25_dbg[3], static_cast<unsigned long long>(__popc(word)));
         while (__any_sync(0xffffffffu, word != 0u)) {
@@ -384,7 +491,7 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
               const float f = __uint_as_float(0x4B000000u | tfb) - 8388608.0f;
               total = fmaf(s_dwgt[i], f * fast_rcp(f + nrm), total);
             }
-            total += sacc[o];
+            if (have_sparse) total += sacc[o];
           }
           tk.offer(valid && total >= tk.thr_score, make_key(total, static_cast<int32_t>(a.id_base + doc)), lane);
         }
@@ -681,7 +788,7 @@ static size_t bm25_smem_bytes(int max_terms, int capacity, bool dense_out) {
   size_t b = 0;
   b += 2 * sizeof(int64_t) * BM_WARPS * max_terms;
   if (!dense_out) b += sizeof(uint64_t) * capacity * BM_WARPS;
-  b += sizeof(void*) * BM_WARPS * max_terms;
+  b += 2 * sizeof(void*) * BM_WARPS * max_terms;
   b += sizeof(float) * BM_WARPS * BM_SUPER_DOCS;
   b += sizeof(unsigned) * BM_WARPS * (BM_SUPER_DOCS / 32);
   b += (2 * sizeof(float) + 2 * sizeof(int) + 1) * BM_WARPS * max_terms;
@@ -764,7 +871,8 @@ size_t ragb_bm25_topk_workspace_bytes(int32_t n_queries, int64_t n_docs, int32_t
 
 int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
                          const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
-                         const int32_t* dense_terms, int32_t n_dense, const int32_t* q_terms, const int32_t* q_off,
+                         const int32_t* dense_terms, int32_t n_dense, const uint16_t* dense_imp_fp16,
+                         const float* dense_max_imp, const int32_t* q_terms, const int32_t* q_off,
                          int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          float* out_score, int32_t* out_id, void* workspace, size_t workspace_bytes,
                          ragb_stream_t stream_) {
@@ -795,6 +903,12 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   a.dense_terms = dense_terms;
   a.dense_stride = dense_stride;
   a.n_dense = n_dense;
+  RAGB_REQUIRE((dense_imp_fp16 == nullptr) == (dense_max_imp == nullptr), RAGB_EINVAL,
+               "ragb_bm25_score_topk: dense_imp_fp16 and dense_max_imp go together");
+  RAGB_REQUIRE(dense_imp_fp16 == nullptr || (n_dense > 0 && (reinterpret_cast<uintptr_t>(dense_imp_fp16) & 15) == 0),
+               RAGB_EINVAL, "ragb_bm25_score_topk: dense_imp_fp16 needs the dense table and 16-byte alignment");
+  a.dense_imp = reinterpret_cast<const __half*>(dense_imp_fp16);
+  a.dense_maximp = dense_max_imp;
   a.k = k;
   a.capacity = warp_topk_capacity(k);
   a.part_keys = static_cast<uint64_t*>(workspace);

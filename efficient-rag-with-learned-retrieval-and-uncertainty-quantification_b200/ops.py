@@ -98,8 +98,10 @@ def _bm25_args(term_off, post_doc, post_tf, norm, idf, q_terms, q_off):
 
 @torch.library.custom_op(f"{NS}::bm25_score_topk", mutates_args=(), device_types="cuda")
 def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
-                    dense_tf: Tensor, dense_terms: Tensor, q_terms: Tensor, q_off: Tensor, max_query_terms: int,
-                    id_base: int, k: int) -> Tuple[Tensor, Tensor]:
+                    dense_tf: Tensor, dense_terms: Tensor, dense_imp: Tensor, dense_maximp: Tensor, q_terms: Tensor,
+                    q_off: Tensor, max_query_terms: int, id_base: int, k: int) -> Tuple[Tensor, Tensor]:
+    """dense_imp (float16 [n_dense, stride]) / dense_maximp (float32 [n_dense]): optional impact bounds of the table
+    terms (ragb200.h); pass empty tensors to run without them - the results are the same."""
     term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
                                                                         q_terms, q_off)
     n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
@@ -107,16 +109,24 @@ def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: T
     ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
     ws = _workspace(lib.ragb_bm25_topk_workspace_bytes(n_q, n_docs, k), dev)
     dt, stride, dterms, n_dense = _dense_table(dense_tf, dense_terms, n_docs)
+    imp, maximp = None, None
+    if n_dense and dense_imp.numel() and dense_maximp.numel():
+        dense_imp = _need(dense_imp, torch.float16, "dense_imp")
+        dense_maximp = _need(dense_maximp, torch.float32, "dense_maximp")
+        if tuple(dense_imp.shape) != tuple(dense_tf.shape) or dense_maximp.shape[0] != n_dense:
+            raise ValueError("dense_imp must have the shape of dense_tf and dense_maximp one entry per row")
+        imp, maximp = dense_imp.data_ptr(), dense_maximp.data_ptr()
     with torch.cuda.device(dev):
         check(lib.ragb_bm25_score_topk(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf),
-                                       idf.shape[0], k1, dt, stride, dterms, n_dense, _ptr(q_terms), _ptr(q_off), n_q,
+                                       idf.shape[0], k1, dt, stride, dterms, n_dense, imp, maximp, _ptr(q_terms), _ptr(q_off), n_q,
                                        max_query_terms, n_docs, id_base, k, _ptr(score), _ptr(ids), _ptr(ws),
                                        ws.numel(), _stream()))
     return score, ids
 
 
 @bm25_score_topk.register_fake
-def _(term_off, post_doc, post_tf, norm, idf, k1, dense_tf, dense_terms, q_terms, q_off, max_query_terms, id_base, k):
+def _(term_off, post_doc, post_tf, norm, idf, k1, dense_tf, dense_terms, dense_imp, dense_maximp, q_terms, q_off,
+      max_query_terms, id_base, k):
     n_q = q_off.shape[0] - 1
     return norm.new_empty((n_q, k)), norm.new_empty((n_q, k), dtype=torch.int32)
 

@@ -31,6 +31,7 @@ from . import ops
 MAX_DENSE_TERMS = 1024          # rows the kernel's table directory can hold
 DENSE_MIN_FRACTION = int(os.environ.get("RAGB_DENSE_MIN_FRACTION", "16"))  # a term gets a row when df >= N / this ...
 DENSE_TABLE_BYTES = 8 << 30     # ... while the table stays under this many bytes per shard
+IMPACT_TABLE_BYTES = 12 << 30   # the fp16 impact bounds of the table rows are optional: skipped above this size
 
 
 @dataclass
@@ -52,6 +53,8 @@ class SparseShard:
     avgdl: float = 0.0
     dense_tf: Optional[Tensor] = None      # uint8 [n_dense, stride]: tf rows of the most frequent terms
     dense_terms: Optional[Tensor] = None   # int32 [n_dense]
+    dense_imp: Optional[Tensor] = None     # float16 [n_dense, stride]: upper bounds of tf / (tf + norm)
+    dense_maximp: Optional[Tensor] = None  # float32 [n_dense]: their row maxima
     use_dense_table: bool = True
 
     @property
@@ -68,7 +71,31 @@ class SparseShard:
         self.idf = ops.bm25_build_idf(df_global.to(torch.int32), self.corpus_size, self.epsilon)
         self.norm = ops.bm25_build_norm(self.doc_len, self.avgdl, self.k1, self.b)
         self._build_dense_table(df_global, group)
+        self._build_impact_bounds()
         return self
+
+    def _build_impact_bounds(self) -> None:
+        """fp16 upper bounds of tf / (tf + norm) for the table terms and their row maxima (ragb200.h): they let
+        the kernel bound what the table terms can add to a document and mark, in a cheap fp16 pass, the few
+        documents of a super-range that are worth the exact arithmetic.  norm changes with the global
+        statistics, so this runs after every finalize."""
+        dev = self.post_doc.device
+        self.dense_imp = torch.empty(0, dtype=torch.float16, device=dev)
+        self.dense_maximp = torch.empty(0, dtype=torch.float32, device=dev)
+        if self.dense_tf is None or self.dense_tf.numel() == 0 or self.dense_tf.numel() * 2 > IMPACT_TABLE_BYTES:
+            return
+        rows, stride = self.dense_tf.shape
+        norm = torch.ones(stride, dtype=torch.float32, device=dev)
+        norm[:self.n_docs] = self.norm
+        imp = torch.empty((rows, stride), dtype=torch.float16, device=dev)
+        for r in range(rows):
+            tf = self.dense_tf[r].to(torch.float32)
+            exact = tf / (tf + norm) * 1.000002          # the kernel multiplies by an approximate reciprocal
+            h = exact.to(torch.float16)
+            low = h.to(torch.float32) < exact             # rounded down: step to the next fp16 (positive values)
+            imp[r] = torch.where(low, (h.view(torch.int16) + 1).view(torch.float16), h)
+        self.dense_imp = imp
+        self.dense_maximp = imp.to(torch.float32).amax(dim=1).contiguous()
 
     def _build_dense_table(self, df_global: Tensor, group=None) -> None:
         """Dense uint8 tf rows for the terms present in >= 1/64 of ALL documents (capped by memory).
@@ -113,7 +140,8 @@ class SparseShard:
 
     def score_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int):
         return ops.bm25_score_topk(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1,
-                                   self.dense_tf, self.dense_terms, q_terms, q_off, max_terms, self.id_base, k)
+                                   self.dense_tf, self.dense_terms, self.dense_imp, self.dense_maximp, q_terms, q_off,
+                                   max_terms, self.id_base, k)
 
     def scores_tiled(self, q_terms: Tensor, q_off: Tensor, max_terms: int, out: Tensor) -> None:
         """get_scores of a batch written into the tiled matrix ``out[ceil(n_docs / 256), rows >= B, 256]``."""

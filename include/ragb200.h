@@ -70,6 +70,10 @@ int ragb_bm25_build_norm(const int32_t* doc_len, int64_t n_docs, double avgdl, d
  * byte per document beats a posting list; every tf of such a term must be <= 255, and the
  * choice must be the same on every shard).  Their posting lists stay in the CSR but are not
  * read.  dense_stride is a multiple of 256, >= n_docs; n_dense = 0 disables the table.
+ * Optional impact bounds for the table terms (both or neither): dense_imp_fp16[r * dense_stride + d] = an IEEE
+ * fp16 UPPER bound of tf / (tf + norm[d]) (0 where the term is absent; 16-byte aligned), dense_max_imp[r] = the
+ * largest value of row r.  They only prune work (a tighter bound on what the table terms can add, and a cheap
+ * fp16 pass that marks the documents worth scoring exactly); results are identical with and without them.
  * max_query_terms (<= RAGB_MAX_QUERY_TERMS) is the caller's bound on the longest query;
  * it sizes the per-warp cursor table and longer queries are cut to it.
  * score = sum idf[t] * tf * (k1 + 1) / (tf + norm[d]).   Only score > 0 is returned
@@ -79,6 +83,7 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
                          const float* norm, const float* idf, int64_t vocab, double k1,
                          const uint8_t* dense_tf, int64_t dense_stride,
                          const int32_t* dense_terms, int32_t n_dense,
+                         const uint16_t* dense_imp_fp16, const float* dense_max_imp,
                          const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
                          int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          float* out_score, int32_t* out_id,

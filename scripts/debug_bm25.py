@@ -16,9 +16,20 @@ lib.ragb_debug_bm25_counters(out)
 s, i = engine.sparse.score_topk(qb.q_terms, qb.q_off, qb.max_terms, 50)
 torch.cuda.synchronize()
 lib.ragb_debug_bm25_counters(out)
-full, pr0, pr1, docs, seeded, strong = [int(x) for x in out[:6]]
+full, pr0, pr1, docs, seeded, strong, approx_ok, approx_fail = [int(x) for x in out[:8]]
 print(f"table rows {engine.sparse.dense_terms.numel()}  super-ranges: full {full}  pruned-empty {pr0}  pruned-with-postings {pr1}  "
-      f"docs scored in pruned mode {docs} ({docs / max(pr1, 1):.1f} per super-range)  queries seeded {seeded}  seed>bound {strong}")
+      f"docs scored in pruned mode {docs} ({docs / max(pr1, 1):.1f} per super-range)  queries seeded {seeded}  seed>bound {strong}  "
+      f"fp16 bound pass: decided {approx_ok}, fell back {approx_fail}")
+for _ in range(3):
+    engine.sparse.score_topk(qb.q_terms, qb.q_off, qb.max_terms, 50)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    engine.sparse.score_topk(qb.q_terms, qb.q_off, qb.max_terms, 50)
+e1.record()
+torch.cuda.synchronize()
+print(f"bm25 pool-50 x 1024 queries (debug counters on): {e0.elapsed_time(e1) / 5:.2f} ms")
 print("kth scores (first 8 queries):", s[:8, -1].tolist())
 idf = engine.sparse.idf
 terms = qb.q_terms.view(1024, -1)[:8].long().clamp(0, engine.sparse.vocab - 1)

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider -k "bm25 or end_to_end or sharded or large_corpus" > gpurun_out/pytest_bm25.log 2>&1
+echo "== pytest bm25 exit $? =="; tail -n 3 gpurun_out/pytest_bm25.log
+timeout 600 python scripts/bench_bm25.py 10000000 50 2>&1 | tail -2

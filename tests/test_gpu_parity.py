@@ -156,6 +156,33 @@ def test_bm25_scores_and_topk(rq, dev, n, n_q, table):
             assert got == sorted(got, key=lambda c: (-c[1], c[0]))
 
 
+@pytest.mark.parametrize("n,n_q,k", [(300_000, 128, 50), (70_001, 33, 10)])
+def test_bm25_impact_bounds_only_prune(rq, dev, n, n_q, k):
+    """The fp16 impact bounds of the table terms (tighter table bound + marking pass) must not change a single bit of
+    the result: same ids and scores with and without them, and both equal the exhaustive get_scores ranking."""
+    from rag_uq_b200 import synth
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    shard = rq.build_shard(doc_off, doc_tok, vocab).finalize()
+    assert shard.dense_imp.numel() > 0 and shard.dense_maximp.shape[0] == shard.dense_terms.shape[0]
+    # the bounds really are upper bounds of what the exact path computes
+    tf = shard.dense_tf[:, :n].float()
+    exact = tf / (tf + shard.norm[None, :])
+    assert bool((shard.dense_imp[:, :n].float() >= exact).all())
+    assert bool((shard.dense_maximp[:, None] >= exact).all()) and float(shard.dense_maximp.max()) < 1.0
+    qb = synth.make_queries(n_q, n, 64, cdf, dev)
+    with_s, with_i = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+    keep = shard.dense_imp, shard.dense_maximp
+    shard.dense_imp, shard.dense_maximp = keep[0][:0], keep[1][:0]
+    without_s, without_i = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+    shard.dense_imp, shard.dense_maximp = keep
+    assert torch.equal(with_i, without_i) and torch.equal(with_s, without_s)
+    full = shard.scores(qb.q_terms, qb.q_off, qb.max_terms)
+    want_s, want_i = torch.topk(full, k, dim=1)
+    torch.testing.assert_close(with_s, want_s, rtol=0, atol=0)
+    same = with_i.long() == want_i
+    assert bool((same | (with_s == want_s)).all())      # ids may differ only inside exact score ties
+
+
 def test_bm25_edge_queries(rq, dev):
     """empty query, all-OOV query, duplicated terms, a query longer than the corpus is wide."""
     vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, 1000)
