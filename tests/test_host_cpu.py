@@ -212,3 +212,41 @@ def test_confidence_host_math(rq):
     assert res.consensus_answer == "Paris" and 0.0 <= res.confidence <= 1.0
     assert res.uncertainty_score == pytest.approx(min(1.0, res.embedding_variance / 2))
     assert res.metadata["n_samples"] == 6
+
+
+@pytest.mark.parametrize("hidden,scale", [(64, 1.0), (32, 4.0), (128, 1.0), (16, 20.0)])
+def test_full_fusion_gate_bounds_are_proven_bounds(rq, hidden, scale):
+    """router.full_fusion_bounds: lo <= gate <= hi on every cell (checked against the fp32 torch gate on 400k random
+    points), last bm25 row (0, 1), and the fused-score bound the kernel derives from it never undercuts the score."""
+    from rag_uq_b200.router import full_fusion_bounds
+    torch.manual_seed(hidden)
+    lin1, lin2 = torch.nn.Linear(3, hidden), torch.nn.Linear(hidden, 1)
+    w1, b1 = (lin1.weight.detach() * scale).numpy(), (lin1.bias.detach() * scale).numpy()
+    w2, b2 = (lin2.weight.detach() * scale).reshape(-1).numpy(), lin2.bias.detach().numpy()
+    stats = np.array([8.0, 6.0, 0.2, 0.3], dtype=np.float32)
+    b_cap, d_hi, n_b, n_d = 64.0, 1.02, 128, 64
+    table = full_fusion_bounds(w1, b1, w2, b2, stats, b_cap, d_hi, n_b, n_d).view(np.uint32)
+    assert table.shape == (n_b, n_d)
+    lo = (table << 16).view(np.float32)
+    hi = (table & np.uint32(0xFFFF0000)).view(np.float32)
+    assert (lo[-1] == 0).all() and (hi[-1] == 1).all() and (lo <= hi).all() and (lo >= 0).all() and (hi <= 1).all()
+    rng = np.random.default_rng(3)
+    n = 400_000
+    b = rng.uniform(-2.0, b_cap * 1.1, n).astype(np.float32)
+    d = rng.uniform(-d_hi, d_hi, n).astype(np.float32)
+    bt, dt = torch.tensor(b), torch.tensor(d)
+    bn = (bt - stats[0]) / (torch.tensor(stats[1]) + 1e-6)
+    dn = (dt - stats[2]) / (torch.tensor(stats[3]) + 1e-6)
+    feats = torch.stack([bn, dn, dn - bn], -1)
+    gate = torch.sigmoid(torch.relu(feats @ torch.tensor(w1).T + torch.tensor(b1)) @ torch.tensor(w2) + torch.tensor(b2))
+    fused = (gate * dt + (1 - gate) * bt).numpy()
+    gate = gate.numpy()
+    ib = np.floor(b * np.float32(n_b / b_cap)).astype(np.int64)
+    ib = np.where((ib < 0) | (ib > n_b - 1), n_b - 1, ib)           # the kernel's clamp: negative / huge -> last row
+    idx = np.clip(np.floor((d + d_hi) * (n_d / (2 * d_hi))).astype(np.int64), 0, n_d - 1)
+    assert (lo[ib, idx] <= gate).all() and (gate <= hi[ib, idx]).all()
+    bound = b + np.where(d <= b, lo[ib, idx], hi[ib, idx]) * (d - b)
+    assert (bound >= fused - 1e-5 * np.abs(fused) - 1e-6).all()
+    # a degenerate router (NaN weight) yields the always-valid table
+    bad = full_fusion_bounds(w1 * np.nan, b1, w2, b2, stats, b_cap, d_hi, 8, 4).view(np.uint32)
+    assert ((bad << 16).view(np.float32) == 0).all() and ((bad & np.uint32(0xFFFF0000)).view(np.float32) == 1).all()
