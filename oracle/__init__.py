@@ -25,6 +25,10 @@ What is restated here and how it is pinned
   live reference module imported from /root/reference; golden vectors are
   committed under ``tests/golden/router_golden.npz`` by
   ``tests/golden/make_golden.py``.
+* ``hnsw``        - an HNSW index (Malkov & Yashunin; hnswlib conventions, ChromaDB's
+  default parameters) restated to REPORT the recall@k of the reference's approximate
+  dense path against the exact search built here.  **Parity unpinned** (no chromadb /
+  hnswlib in the image, no fixture of their output).
 * ``philox``      - Philox4x32-10 with the curand counter layout, used to check
   the in-kernel dropout masks bit-exactly.
 """

@@ -270,6 +270,28 @@ def test_dense_mma_topk(rq, dev, variant, n, b, k, dim):
     _check_dense(score, ids, want, min(k, n), id_base=7)
 
 
+def test_hnsw_recall_against_exact_search(rq, dev):
+    """The reference's dense path is ChromaDB's approximate HNSW (streaming_index.py:355-359); ours is exact.
+    Report (and sanity-check) the recall@10 of an HNSW with ChromaDB's default parameters against the kernel."""
+    from oracle import hnsw
+    from rag_uq_b200 import synth
+    n, n_q, k = 3000, 48, 10
+    passages = synth.passage_embeddings(0, n, 768, dev)
+    qb = synth.make_queries(n_q, n, 768, synth.zipf_cdf(synth.vocab_size(n), dev), dev)
+    score, ids = rq.ops.dense_gemv_topk(passages, qb.q_emb[:8].contiguous(), k, 0)
+    score2, ids2 = rq.ops.dense_mma_topk(passages, qb.q_emb, k, 0, 3)
+    assert torch.equal(ids, ids2[:8])
+    rep = hnsw.recall_report(passages.float().cpu().numpy(), qb.q_emb.float().cpu().numpy(), ids2.cpu().numpy(), k)
+    print("HNSW recall vs exact:", rep)
+    # the source passage of each query (cosine ~0.9, everything else ~0.0 +- 0.04) is always found ...
+    index = hnsw.HnswCosine(768)
+    index.add(passages.float().cpu().numpy())
+    top1 = [int(index.search(q, 1, 100)[0][0]) for q in qb.q_emb.float().cpu().numpy()]
+    assert np.mean(np.asarray(top1) == ids2[:, 0].cpu().numpy()) > 0.95
+    # ... the other nine are near-random directions in 768-d, where a graph walk is genuinely approximate
+    assert 0.3 < rep["recall@10_search_ef_10"] <= rep["recall@10_search_ef_100"] <= 1.0
+
+
 def test_dense_gemv_equals_mma_bitwise_ids(rq, dev):
     passages, q, want = _dense_case(rq, dev, 20_000, 8)
     gs, gi = rq.ops.dense_gemv_topk(passages, q, 50, 0)

@@ -71,7 +71,8 @@ def test_no_cpu_fallback(rq):
 
 def test_product_package_does_not_import_oracle():
     pkg = ROOT / "efficient-rag-with-learned-retrieval-and-uncertainty-quantification_b200"
-    for path in list(pkg.glob("*.py")) + list(pkg.glob("csrc/*")) + [ROOT / "rag_uq_b200" / "__init__.py"]:
+    for path in (list(pkg.glob("*.py")) + list(pkg.glob("csrc/*")) + [ROOT / "rag_uq_b200" / "__init__.py"]
+                 + list((ROOT / "scripts").glob("*.py"))):
         text = path.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
 

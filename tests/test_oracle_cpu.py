@@ -209,3 +209,23 @@ def test_philox_uniform_and_geometry():
     assert grid == 1184 and inc == ((6553600 - 1) // (256 * 1184 * 4) + 1) * 4
     keep = philox.keep_mask_torch_layout(6400, seed=123, offset=0, keep_prob=0.9, sm_count=148)
     assert keep.shape == (6400,) and 0.85 < keep.mean() < 0.95
+
+
+def test_hnsw_oracle_finds_neighbours_on_clustered_data():
+    """The HNSW restatement behaves like an HNSW: near-perfect recall on low-dimensional clustered vectors with
+    search_ef = 100, lower with ef = 10, deterministic for a fixed seed."""
+    from oracle import hnsw
+    rng = np.random.default_rng(0)
+    centres = rng.normal(size=(12, 24))
+    x = (centres[rng.integers(0, 12, 1200)] + 0.3 * rng.normal(size=(1200, 24))).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = x[:40] + 0.05 * rng.normal(size=(40, 24)).astype(np.float32)
+    exact = np.argsort(-((q / np.linalg.norm(q, axis=1, keepdims=True)) @ x.T), axis=1)[:, :10]
+    rep = hnsw.recall_report(x, q, exact, 10)
+    assert rep["recall@10_search_ef_100"] >= 0.98
+    assert rep["recall@10_search_ef_10"] <= rep["recall@10_search_ef_100"]
+    a, b = hnsw.HnswCosine(24), hnsw.HnswCosine(24)
+    a.add(x[:300]); b.add(x[:300])
+    assert a.links == b.links
+    ids, sims = a.search(x[5], 5)
+    assert ids[0] == 5 and sims[0] == pytest.approx(1.0, abs=1e-5) and list(sims) == sorted(sims, reverse=True)
