@@ -11,6 +11,7 @@ from .confidence import ConfidenceResult, MCDropoutConfidence, RouterUncertainty
 from .engine import HybridEngine, gather_candidates, global_bm25_statistics, shard_rows
 from .retrieval import BM25Index, DenseIndex, Document, HybridRetriever, RetrievalResult, StreamingIndex
 from .router import RetrievalRouter, RouterConfig
+from .shard_io import load_engine, load_shard, save_engine, save_shard
 from .sparse import SegmentedIndex, SparseShard, build_shard, build_shard_blocked
 
 __version__ = "0.1.0"
@@ -18,5 +19,5 @@ __all__ = [
     "RetrievalRouter", "RouterConfig", "MCDropoutConfidence", "ConfidenceResult", "RouterUncertainty",
     "HybridRetriever", "StreamingIndex", "BM25Index", "DenseIndex", "Document", "RetrievalResult",
     "HybridEngine", "SparseShard", "SegmentedIndex", "build_shard", "build_shard_blocked", "shard_rows", "gather_candidates",
-    "global_bm25_statistics",
+    "global_bm25_statistics", "save_shard", "load_shard", "save_engine", "load_engine",
 ]

@@ -732,6 +732,23 @@ def test_incremental_ingest_equals_full_rebuild(rq, dev):
         np.testing.assert_allclose([s for _, s in a], [s for _, s in b], rtol=2e-6)
 
 
+def test_shard_directory_reload_gives_identical_results(rq, dev, tmp_path):
+    """N2: save the engine's shard as raw arrays, load it back (idf / norm / table rows recomputed on the device)
+    and get bit-identical hybrid results."""
+    from rag_uq_b200 import synth
+    n, dim, n_q = 20_000, 768, 40
+    engine, cdf = synth.build_synthetic_engine(n, dim, dev)
+    qb = synth.make_queries(n_q, n, dim, cdf, dev)
+    want = engine.hybrid_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, 10, 50)
+    rq.save_engine(tmp_path / "shard", engine)
+    again = rq.load_engine(tmp_path / "shard", dev)
+    assert torch.equal(again.sparse.idf, engine.sparse.idf) and torch.equal(again.sparse.norm, engine.sparse.norm)
+    assert torch.equal(again.sparse.dense_terms, engine.sparse.dense_terms)
+    got = again.hybrid_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, 10, 50)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
 def test_retrieval_uncertainty(rq, dev):
     g = torch.Generator().manual_seed(9)
     scores = torch.rand(7, 10, generator=g)

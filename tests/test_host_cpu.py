@@ -251,3 +251,35 @@ def test_full_fusion_gate_bounds_are_proven_bounds(rq, hidden, scale):
     # a degenerate router (NaN weight) yields the always-valid table
     bad = full_fusion_bounds(w1 * np.nan, b1, w2, b2, stats, b_cap, d_hi, 8, 4).view(np.uint32)
     assert ((bad << 16).view(np.float32) == 0).all() and ((bad & np.uint32(0xFFFF0000)).view(np.float32) == 1).all()
+
+
+def test_shard_format_round_trip_on_cpu(rq, tmp_path):
+    """N2: the raw-array shard directory reproduces every array bit for bit (memmap read, no parsing); loading
+    without finalize needs no GPU."""
+    g = torch.Generator().manual_seed(5)
+    vocab, n_docs, nnz, dim = 50, 40, 300, 64
+    counts = torch.bincount(torch.randint(0, vocab, (nnz,), generator=g), minlength=vocab)
+    term_off = torch.zeros(vocab + 1, dtype=torch.int64)
+    term_off[1:] = torch.cumsum(counts, 0)
+    shard = rq.SparseShard(term_off, torch.randint(0, n_docs, (nnz,), generator=g, dtype=torch.int32),
+                           torch.randint(1, 900, (nnz,), generator=g, dtype=torch.int16),
+                           torch.randint(20, 300, (n_docs,), generator=g, dtype=torch.int32), counts.to(torch.int32),
+                           n_docs=n_docs, vocab=vocab, id_base=1000, k1=1.2, b=0.6, epsilon=0.3)
+    passages = torch.randn(n_docs, dim, generator=g).to(torch.bfloat16)
+    d = rq.save_shard(tmp_path / "shard0", shard, passages, id_base=1000)
+    meta = json.loads((d / "meta.json").read_text())
+    assert meta["format"] == "rag_uq_b200.shard" and meta["sparse"]["nnz"] == nnz and meta["passages"]["dim"] == dim
+    assert (d / "passages.bin").stat().st_size == n_docs * dim * 2 and (d / "post_tf.bin").stat().st_size == nnz * 2
+    got, emb, base = rq.load_shard(d, "cpu", finalize=False)
+    assert base == 1000 and (got.k1, got.b, got.epsilon, got.n_docs, got.vocab) == (1.2, 0.6, 0.3, n_docs, vocab)
+    for name in ("term_off", "post_doc", "post_tf", "doc_len", "df"):
+        assert torch.equal(getattr(got, name), getattr(shard, name)), name
+    assert torch.equal(emb.view(torch.int16), passages.view(torch.int16))
+    # a dense-only shard and a foreign directory
+    d2 = rq.save_shard(tmp_path / "dense_only", None, passages)
+    sp, emb2, _ = rq.load_shard(d2, "cpu", finalize=False)
+    assert sp is None and torch.equal(emb2.view(torch.int16), passages.view(torch.int16))
+    (tmp_path / "bad").mkdir()
+    (tmp_path / "bad" / "meta.json").write_text(json.dumps({"format": "something else"}))
+    with pytest.raises(ValueError):
+        rq.load_shard(tmp_path / "bad", "cpu")
