@@ -53,7 +53,7 @@ def _read(path: Path, dtype, shape, device, torch_dtype) -> torch.Tensor:
     step = max(1, _CHUNK // mm.dtype.itemsize)
     view = out.view(torch.int16) if torch_dtype in (torch.bfloat16, torch.float16) else out
     for lo in range(0, count, step):
-        chunk = np.ascontiguousarray(mm[lo:lo + step])
+        chunk = np.array(mm[lo:lo + step])   # one copy out of the page cache into writable memory
         if chunk.dtype == np.uint16:
             chunk = chunk.view(np.int16)
         view[lo:lo + step].copy_(torch.from_numpy(chunk), non_blocking=False)
