@@ -86,6 +86,7 @@ struct Bm25Args {
   int n_dense;
   const __half* dense_imp;   // optional [n_dense, dense_stride]: fp16 UPPER bound of tf / (tf + norm) per (table term, document)
   const float* dense_maximp; // optional [n_dense]: row maxima of dense_imp (a term contributes at most weight * maximp)
+  int window_mode;           // > 0: hash-window mode for the pruned phase, aiming at this many postings per window
   float* seed_thr;           // [queries] proven lower bound of each query's k-th best score (0 = none)
   int debug;
 };
@@ -129,7 +130,7 @@ __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc
       if (take) {
         const float f = static_cast<float>(tf[u]);
         const int o = doc[u] - d0;
-        accw[o] += weight * (f * fast_rcp(f + __ldg(norm + doc[u])));
+        accw[o] = fmaf(weight, f * fast_rcp(f + __ldg(norm + doc[u])), accw[o]);   // same expression in stream_term_hash
         if (touched != nullptr) atomicOr(touched + (o >> 5), 1u << (o & 31));
       }
       taken += __popc(__ballot_sync(0xffffffffu, take));
@@ -148,6 +149,84 @@ __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc
     if (peek >= d1) {
       next_doc = peek;
       return;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Window mode (pruned phase).  Once thr > ub_table only documents that a posting list touches matter, and a
+// query's lists touch ~3% of the documents: walking 1024-document super-ranges with a dense accumulator then
+// spends its time on per-visit bookkeeping (~30 postings per visit).  Window mode covers up to 32k documents per
+// visit and keeps the accumulator as an open-addressing hash table (document offset -> partial score) in the SAME
+// 4 KB of shared memory: 512 slots, at most BM_HASH_MAX distinct documents (the window is halved and redone when
+// it would overflow).  Terms are streamed in the same order and with the same fused multiply-add as in the dense
+// accumulator, so every document gets bit-identical sums in both modes (and in any sharding).
+// ---------------------------------------------------------------------------------------
+constexpr int BM_HASH_SLOTS = 512;
+constexpr int BM_HASH_MAX = 352;       // inserts stop being attempted beyond this: 352 + 4 * 32 < 512 keeps probing finite
+constexpr int BM_WINDOW_MAX = 32768;   // documents per window (offsets must also stay well inside int32)
+
+// Returns false when the table would overflow (nothing usable was changed: the caller restores the cursors).
+template <int U>
+__device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ post_doc,
+                                                 const uint16_t* __restrict__ post_tf, int64_t& pos, const int64_t end,
+                                                 const int d0, const int d1, const float weight, int* keys, float* vals,
+                                                 unsigned* flags, const bool essential,
+                                                 const float* __restrict__ norm, const int lane, int& next_doc,
+                                                 int& n_keys) {
+  static_assert(U * 32 + BM_HASH_MAX < BM_HASH_SLOTS, "a pass must fit behind the fill limit");
+  while (true) {
+    if (n_keys > BM_HASH_MAX) return false;
+    int doc[U];
+    unsigned tf[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t idx = pos + u * 32 + lane;
+      const bool in = idx < end;
+      doc[u] = in ? __ldg(post_doc + idx) : INT_MAX;
+      tf[u] = in ? static_cast<unsigned>(__ldg(post_tf + idx)) : 0u;
+    }
+    const int64_t peek_idx = pos + U * 32;
+    int peek = INT_MAX;
+    if (lane == 0 && peek_idx < end) peek = __ldg(post_doc + peek_idx);
+    int taken = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool take = doc[u] < d1;
+      bool fresh = false;
+      if (take) {
+        const float f = static_cast<float>(tf[u]);
+        const float x = f * fast_rcp(f + __ldg(norm + doc[u]));
+        const int key = doc[u] - d0;
+        unsigned slot = (static_cast<unsigned>(key) * 0x9E3779B1u) >> 23;   // 9 bits
+        int prev;
+        while (true) {
+          prev = atomicCAS(keys + slot, -1, key);
+          if (prev == -1 || prev == key) break;
+          slot = (slot + 1) & (BM_HASH_SLOTS - 1);
+        }
+        fresh = prev == -1;
+        // documents of one list are distinct, so no other lane works on this slot's value right now
+        vals[slot] = fmaf(weight, x, fresh ? 0.0f : vals[slot]);
+        if (essential) atomicOr(flags + (slot >> 5), 1u << (slot & 31));
+      }
+      taken += __popc(__ballot_sync(0xffffffffu, take));
+      n_keys += __popc(__ballot_sync(0xffffffffu, fresh));
+    }
+    pos += taken;
+    if (taken < U * 32) {
+      int cand = INT_MAX;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (u == (taken >> 5)) cand = doc[u];
+      next_doc = __shfl_sync(0xffffffffu, cand, taken & 31);
+      return true;
+    }
+    peek = __shfl_sync(0xffffffffu, peek, 0);
+    if (peek >= d1) {
+      next_doc = peek;
+      return true;
     }
     __syncwarp();
   }
@@ -264,6 +343,7 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
   }
   // ---- per-warp cursors: lower_bound(post_doc[term], w_begin) by a 32-ary search, 4 terms at a time
   int ntv = 0;  // sparse terms with a non-empty posting list (warp-uniform)
+  float list_density = 0.0f;  // postings of all list terms per 1024 documents (warp-uniform)
   for (int g = 0; g < ns; g += BM_SEARCH) {
     int64_t lo[BM_SEARCH], hi[BM_SEARCH], te[BM_SEARCH], ts[BM_SEARCH];
     float wg[BM_SEARCH];
@@ -319,13 +399,14 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
         const int64_t cur = lo[j] + __popc(__ballot_sync(0xffffffffu, below));
         int nx = INT_MAX;
         if (cur < te[j]) nx = __ldg(a.post_doc + cur);
+        // expected postings of this term per super-range
+        const double per_range = static_cast<double>(te[j] - ts[j]) * BM_SUPER_DOCS / static_cast<double>(a.n_docs);
+        list_density += static_cast<float>(per_range);
         if (lane == 0) {
           s_pos[ntv] = cur;
           s_end[ntv] = te[j];
           s_wgt[ntv] = wg[j];
           s_nxt[ntv] = nx;
-          // expected postings of this term per super-range
-          const double per_range = static_cast<double>(te[j] - ts[j]) * BM_SUPER_DOCS / static_cast<double>(a.n_docs);
           s_dense[ntv] = per_range < 24.0 ? 0 : (per_range < 56.0 ? 1 : (per_range < 120.0 ? 2 : 3));
         }
         ++ntv;
@@ -356,12 +437,129 @@ __global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
     if (lane < ntv) my_psum = ps;
   }
 
+  // window mode (pruned phase): aim at ~256 postings per window
+  bool window_ok = !DENSE_OUT && a.window_mode != 0 && ntv <= 32;
+  int window = BM_SUPER_DOCS;
+  {
+    const float per_doc = fmaxf(list_density, 1e-3f) / BM_SUPER_DOCS;
+    const int want = static_cast<int>(fminf(static_cast<float>(a.window_mode) / per_doc, static_cast<float>(BM_WINDOW_MAX)));
+    window = max(BM_SUPER_DOCS, want / BM_SUPER_DOCS * BM_SUPER_DOCS);
+  }
+
   const int j0 = lane * 8;  // the 8 documents of a range this lane owns
   for (int sup = 0; sup < n_super; ++sup) {
     const int64_t s0l = w_begin + static_cast<int64_t>(sup) * BM_SUPER_DOCS;
     const int s0 = static_cast<int>(s0l < w_end ? s0l : w_end);
     const int s1 = static_cast<int>(min(w_end, s0l + BM_SUPER_DOCS));
     if (s1 <= s0) break;  // warp-uniform; nothing below synchronises the block
+    if (!DENSE_OUT && window_ok && tk.thr_score > ub_table) {
+      // ================= window mode: the rest of this warp's documents (see stream_term_hash) =================
+      int* const keys = reinterpret_cast<int*>(sacc);
+      float* const vals = sacc + BM_HASH_SLOTS;
+      unsigned* const flags = s_bits;
+      int64_t d0l = s0l;
+      bool fell_back = false;
+      while (d0l < w_end) {
+        const int d0 = static_cast<int>(d0l);
+        const int d1 = static_cast<int>(min(w_end, d0l + window));
+        unsigned act = __ballot_sync(0xffffffffu, lane < ntv && s_nxt[lane] < d1);
+        if (act == 0u) {   // no posting of any list in this window: nothing can reach thr
+          if (a.debug && lane == 0) atomicAdd(&g_bm25_dbg[1], 1ull);
+          d0l += window;
+          continue;
+        }
+        const int64_t save_pos = lane < ntv ? s_pos[lane] : 0;
+        const int save_nxt = lane < ntv ? s_nxt[lane] : 0;
+#pragma unroll
+        for (int i = 0; i < BM_HASH_SLOTS / 128; ++i)
+          reinterpret_cast<int4*>(keys)[i * 32 + lane] = make_int4(-1, -1, -1, -1);
+        if (lane < BM_HASH_SLOTS / 32) flags[lane] = 0u;
+        __syncwarp();
+        int n_noness = 0;
+        if (maxscore) {
+          const float thr_safe = tk.thr_score - 2e-5f * fabsf(tk.thr_score);
+          n_noness = __popc(__ballot_sync(0xffffffffu, lane < ntv && ub_table + my_psum < thr_safe));
+        }
+        int n_keys = 0;
+        bool ok = true;
+        while (act != 0u && ok) {
+          const int ti = __ffs(act) - 1;
+          act &= act - 1u;
+          int64_t pos = s_pos[ti];
+          const int64_t end = s_end[ti];
+          const float w = s_wgt[ti];
+          const bool essential = !(n_noness > 0 && __shfl_sync(0xffffffffu, my_rank, ti) < n_noness);
+          int next_doc = INT_MAX;
+          switch (s_dense[ti]) {  // chunks per pass sized to the term's density (warp-uniform)
+            case 0: ok = stream_term_hash<1>(a.post_doc, a.post_tf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
+            case 1: ok = stream_term_hash<2>(a.post_doc, a.post_tf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
+            default: ok = stream_term_hash<4>(a.post_doc, a.post_tf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
+          }
+          if (ok && lane == 0) {
+            s_pos[ti] = pos;
+            s_nxt[ti] = next_doc;
+          }
+          __syncwarp();
+        }
+        if (!ok) {
+          // too many distinct documents: put the cursors back and redo the window at half the size; a single
+          // super-range that still overflows goes back to the dense accumulator for good
+          if (lane < ntv) {
+            s_pos[lane] = save_pos;
+            s_nxt[lane] = save_nxt;
+          }
+          __syncwarp();
+          if (window == BM_SUPER_DOCS) {
+            fell_back = true;
+            break;
+          }
+          window = max(BM_SUPER_DOCS, (window / 2) / BM_SUPER_DOCS * BM_SUPER_DOCS);
+          continue;
+        }
+        // compact the marked slots to the front of the table (position <= slot, so in place) ...
+        int n_valid = 0;
+        for (int base = 0; base < BM_HASH_SLOTS; base += 32) {
+          const int key = keys[base + lane];
+          const float val = vals[base + lane];
+          const bool valid = key != -1 && ((flags[base >> 5] >> lane) & 1u) != 0u;
+          const unsigned m = __ballot_sync(0xffffffffu, valid);
+          if (valid) {
+            const int j = n_valid + __popc(m & ((1u << lane) - 1u));
+            keys[j] = key;
+            vals[j] = val;
+          }
+          n_valid += __popc(m);
+          __syncwarp();
+        }
+        if (a.debug && lane == 0) {
+          atomicAdd(&g_bm25_dbg[2], 1ull);
+          atomicAdd(&g_bm25_dbg[3], static_cast<unsigned long long>(n_valid));
+        }
+        // ... and score them: table terms first, in query order, then the list part - as in the dense mode
+        for (int i0 = 0; i0 < n_valid; i0 += 32) {
+          const bool valid = i0 + lane < n_valid;
+          float total = 0.0f;
+          int doc = d0;
+          if (valid) {
+            doc = d0 + keys[i0 + lane];
+            const float nrm = __ldg(a.norm + doc);
+            for (int i = 0; i < nd; ++i) {
+              const unsigned tfb = __ldg(s_drow[i] + doc);
+              const float f = __uint_as_float(0x4B000000u | tfb) - 8388608.0f;
+              total = fmaf(s_dwgt[i], f * fast_rcp(f + nrm), total);
+            }
+            total += vals[i0 + lane];
+          }
+          tk.offer(valid && total >= tk.thr_score, make_key(total, static_cast<int32_t>(a.id_base + doc)), lane);
+        }
+        __syncwarp();
+        d0l += window;
+      }
+      if (!fell_back) break;   // this warp is done
+      window_ok = false;
+      sup = static_cast<int>((d0l - w_begin) / BM_SUPER_DOCS) - 1;   // resume the dense-accumulator loop at d0l
+      continue;
+    }
     // ---- posting-list terms: streamed once per super-range into shared memory, and only when
     //      some list actually reaches into it (one ballot decides)
     unsigned active = 0;
@@ -917,6 +1115,9 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   a.seed_thr = reinterpret_cast<float*>(a.part_keys + static_cast<size_t>(n_queries) * stripes * k);
   static const int debug_flag = [] { const char* e = getenv("RAGB_BM25_DEBUG"); return e ? atoi(e) : 0; }();
   a.debug = debug_flag;
+  // postings aimed at per window (0 turns window mode off); tuning aid, the default is what was measured best
+  static const int window_flag = [] { const char* e = getenv("RAGB_BM25_WINDOW"); return e ? atoi(e) : 256; }();
+  a.window_mode = window_flag;
   bm25_seed_kernel<<<n_queries, SEED_THREADS, 0, stream>>>(a);
   RAGB_AFTER_LAUNCH(1);
   const size_t smem = bm25_smem_bytes(a.max_terms, a.capacity, false);

@@ -1,5 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider -k "bm25 or end_to_end or sharded or large_corpus" > gpurun_out/pytest_bm25.log 2>&1
-echo "== pytest bm25 exit $? =="; tail -n 3 gpurun_out/pytest_bm25.log
-timeout 600 python scripts/bench_bm25.py 10000000 50 2>&1 | tail -2
+for w in 128 192 256 320 400; do echo "window target=$w"; RAGB_BM25_WINDOW=$w timeout 600 python scripts/bench_bm25.py 10000000 50 2>&1 | tail -1; done
