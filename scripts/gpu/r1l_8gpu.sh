@@ -1,12 +1,12 @@
 #!/bin/bash
-# 8-GPU (and 4-GPU) runs of the sharded path: headline c3, c4 (MC-Dropout), c5 (100M passages, top-100), full-fusion
+# 8-GPU box: sharded path at 8 / 4 / 2 GPUs (headline c3), c4 (MC-Dropout), c5 (100M passages, top-100), full-fusion
 mkdir -p gpurun_out
 run() { n=$1; name=$2; shift 2; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n "$@" > gpurun_out/$name.log 2>&1; echo "== $name exit $? =="; tail -n 1 gpurun_out/$name.log | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print(d['metric'],'| n',d['n_gpus'],'value',round(d['value']),'e2e',round(d['e2e']['value']),'ms',round(d['ms_per_step'],2),'| bm25',round(d['kernels']['bm25_ms'],2),'dense',round(d['kernels']['dense_ms'],2),'other',round(d['kernels']['other_ms'],2),'build_s',d['config']['build_seconds'])" || tail -n 8 gpurun_out/$name.log; }
-run 8 bench_8gpu_c3 --steps 10 --warmup 3
+run 8 bench_8gpu_c3 --steps 20 --warmup 3
 run 8 bench_8gpu_c5 --workload c5 --steps 5 --warmup 3
 run 8 bench_8gpu_c4 --workload c4 --steps 10 --warmup 3
 run 8 bench_8gpu_ff --mode full-fusion --steps 5 --warmup 3
 run 4 bench_4gpu_c3 --steps 10 --warmup 3
-nvidia-smi topo -m > gpurun_out/topo_8gpu.txt 2>&1
+run 2 bench_2gpu_c3 --steps 10 --warmup 3
