@@ -52,6 +52,12 @@ constexpr int BM_SUPER = 4;            // ranges per super-range: posting lists 
 constexpr int BM_SUPER_DOCS = BM_RANGE * BM_SUPER;
 constexpr int BM_MAX_TERMS = 64;
 constexpr int BM_MAX_DENSE = 1024;  // rows of the dense tf table (term ids sorted ascending)
+#ifndef RAGB_BM_MIN_BLOCKS
+#define RAGB_BM_MIN_BLOCKS 3
+#endif
+// Resident blocks per SM the register budget is sized for.  4 (64 registers) spilled 80 bytes in the window loop and
+// only 23 of its 32 warps were resident on average anyway; 3 (80 registers, no spills): 14.0 -> 11.6 ms at 10M x 1024.
+constexpr int BM_MIN_BLOCKS = RAGB_BM_MIN_BLOCKS;
 constexpr int BM_SEARCH = 4;  // posting lists searched concurrently while placing the cursors
 constexpr int BM_APPROX_MAX = 320;  // fp16 bound pass: fall back to the exact table path when more documents of a super-range pass
 
@@ -233,7 +239,7 @@ __device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ pos
 }
 
 template <bool DENSE_OUT>
-__global__ void __launch_bounds__(BM_THREADS, 4) bm25_kernel(const Bm25Args a) {
+__global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm25_kernel(const Bm25Args a) {   // get_scores streams: occupancy first
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = a.max_terms;
