@@ -330,10 +330,11 @@ def test_hybrid_fuse_topk_vs_oracle(rq, dev):
         assert (ids[q, len(want):] == -1).all() and (oh[q, len(want):] == 0).all()
 
 
-@pytest.mark.parametrize("n_q", [64, 4])
-def test_hybrid_engine_end_to_end_c1(rq, dev, n_q):
+@pytest.mark.parametrize("n_q,k,pool", [(64, 10, 50), (4, 10, 50), (40, 100, 100)])
+def test_hybrid_engine_end_to_end_c1(rq, dev, n_q, k, pool):
+    """Config C1 end to end against the oracle; (40, 100, 100) is the top-100 / pool-100 shape of config C5."""
     from rag_uq_b200 import synth
-    n, dim, k, pool = 10_000, 768, 10, 50
+    n, dim = 10_000, 768
     vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
     passages = synth.passage_embeddings(0, n, dim, dev)
     shard = rq.build_shard(doc_off, doc_tok, vocab).finalize()
@@ -352,7 +353,7 @@ def test_hybrid_engine_end_to_end_c1(rq, dev, n_q):
         np.testing.assert_allclose(sh[q, :len(want)], [w[3] for w in want], rtol=2e-5, atol=1e-6)
         exact += got == [w[0] for w in want]
         assert set(got) == set(w[0] for w in want) or abs(want[-1][3] - sh[q, len(want) - 1]) < 1e-5
-    assert exact >= n_q - 1          # a pool-boundary tie may flip at most very rarely
+    assert exact >= n_q - max(1, n_q // 20)   # a pool-boundary (near-)tie may flip at most very rarely
     # router-in-the-loop + confidence (run_evaluation.py:165-196) on the same batch
     torch.manual_seed(7)
     router = rq.RetrievalRouter().to(dev).eval()
