@@ -43,7 +43,7 @@ constexpr int MM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MM_A_STAGE_BYTES = MM_BM * MM_BK * 2;  // 16 KB
 constexpr int MM_MAX_STAGES = 16;
 constexpr int MM_MAX_SMEM = 227 * 1024;
-constexpr int MM_PACE_TILES = 8;         // how far a block may run ahead of the slowest slab of its group
+constexpr int MM_PACE_TILES = 4;         // how far a block may run ahead of the slowest slab of its group
 constexpr int MM_PROGRESS_BYTES = 4096;  // head of the workspace: progress counters (<= 148 blocks)
 
 struct MmaArgs {
@@ -62,6 +62,8 @@ struct MmaArgs {
   int* progress;        // [n_groups, n_slabs] tiles issued so far (soft pacing between the slabs of a group)
   uint64_t* lists;      // [blocks, 128, list capacity + 1] per-thread candidate lists
   int stage_limit;
+  int pace_tiles;       // how far (in tiles) a block may run ahead of the slowest slab of its passage group
+  int pace_mask;        // a block publishes its position and checks the others every (pace_mask + 1) tiles
   // ---- full-fusion epilogue only (FUSED kernels) ----
   const float* bm25;    // [ceil(n_rows / 256), bm25_rows, 256] fp32 BM25 scores of this shard's rows, 256-passage tiles
   int64_t bm25_ld;      // query rows per tile (>= n_queries)
@@ -650,12 +652,12 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
         // and HBM traffic multiplies (measured 3.4x).  Every 4 tiles a block publishes its position
         // and briefly waits for the slowest slab; the wait is bounded, so it can never deadlock.
         const int it = tile - tile_begin;
-        if (n_slabs > 1 && (it & 3) == 0) {
+        if (n_slabs > 1 && (it & a.pace_mask) == 0) {
           group_progress[slab] = it;
           for (int spins = 0; spins < 256; ++spins) {
             int slowest = it;
             for (int sl = 0; sl < n_slabs; ++sl) slowest = min(slowest, group_progress[sl]);
-            if (it - slowest <= MM_PACE_TILES) break;
+            if (it - slowest <= a.pace_tiles) break;
             __nanosleep(256);
           }
         }
@@ -864,12 +866,12 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_pair_kernel(const __g
       volatile int* group_progress = a.progress + group * n_pairs_slab;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int it = tile - tile_begin;
-        if (leader && n_pairs_slab > 1 && (it & 3) == 0) {   // soft pacing between the pairs of a group
+        if (leader && n_pairs_slab > 1 && (it & a.pace_mask) == 0) {   // soft pacing between the pairs of a group
           group_progress[pair % n_pairs_slab] = it;
           for (int spins = 0; spins < 256; ++spins) {
             int slowest = it;
             for (int sl = 0; sl < n_pairs_slab; ++sl) slowest = min(slowest, group_progress[sl]);
-            if (it - slowest <= MM_PACE_TILES) break;
+            if (it - slowest <= a.pace_tiles) break;
             __nanosleep(256);
           }
         }
@@ -969,6 +971,23 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int dim, in
   return RAGB_OK;
 }
 
+static int mma_pace_mask() {
+  static const int v = [] {
+    const char* e = getenv("RAGB_MMA_PUBLISH");  // tuning aid: 1, 2 or 4 tiles between position updates
+    const int n = e ? atoi(e) : 4;
+    return n <= 1 ? 0 : (n == 2 ? 1 : 3);
+  }();
+  return v;
+}
+
+static int mma_pace_tiles() {
+  static const int v = [] {
+    const char* e = getenv("RAGB_MMA_PACE");  // tuning aid
+    return e ? atoi(e) : MM_PACE_TILES;
+  }();
+  return v;
+}
+
 // fused: null (dense-only top-k) or the full-fusion fields of MmaArgs (bm25, router, bound table)
 static void copy_fused_fields(MmaArgs& a, const MmaArgs* fused) {
   if (fused == nullptr) return;
@@ -1016,6 +1035,8 @@ static int launch_mma(const void* passages, int64_t n_rows, int dim, const void*
   a.progress = progress;
   a.lists = lists;
   copy_fused_fields(a, fused);
+  a.pace_tiles = mma_pace_tiles();
+  a.pace_mask = mma_pace_mask();
   RAGB_CUDA(cudaMemsetAsync(progress, 0, MM_PROGRESS_BYTES, stream));
   // Ring depth: everything shared memory offers (RAGB_MMA_STAGES caps it, e.g. to leave room for
   // blocks of another kernel on the same SM when experimenting with two-stream overlap).
@@ -1063,6 +1084,8 @@ static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const 
   a.progress = progress;
   a.lists = lists;
   copy_fused_fields(a, fused);
+  a.pace_tiles = mma_pace_tiles();
+  a.pace_mask = mma_pace_mask();
   RAGB_CUDA(cudaMemsetAsync(progress, 0, MM_PROGRESS_BYTES, stream));
   constexpr int TABLE_BYTES = FUSED ? FF_TABLE_CELLS * static_cast<int>(sizeof(uint32_t)) : 0;
   int stages = (MM_MAX_SMEM - 1024 - 256 - TABLE_BYTES) / MM2_STAGE_BYTES;

@@ -1,8 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -k "full_fusion" > gpurun_out/pytest_ff.log 2>&1
-echo "== pytest ff exit $? =="; tail -n 5 gpurun_out/pytest_ff.log
-for d in 0 2; do
+for d in 0 4; do
 RAGB_FF_DEBUG=$d timeout 600 python scripts/bench_full_fusion.py 10000000 1024 10 > gpurun_out/ff_dbg$d.log 2>&1; echo "== dbg $d exit $? =="; tail -n 1 gpurun_out/ff_dbg$d.log | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('fused_gemm_ms','bm25_scores_ms','gate_evaluations','full_fusion_ms')})"
 done

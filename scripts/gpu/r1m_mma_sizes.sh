@@ -1,5 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -k "dense or end_to_end or sharded or large_corpus" > gpurun_out/pytest_dense.log 2>&1
-echo "== pytest dense exit $? =="; tail -n 3 gpurun_out/pytest_dense.log
-MMA_VARIANTS=3 timeout 900 python scripts/bench_mma.py 1250000 10000000 > gpurun_out/mma_sizes.log 2>&1; echo "exit $?"; cat gpurun_out/mma_sizes.log
+for pub in 4 2 1; do for p in 4 3; do echo "publish $pub pace $p"; RAGB_MMA_PUBLISH=$pub RAGB_MMA_PACE=$p MMA_VARIANTS=3 MMA_KS=50 timeout 600 python scripts/bench_mma.py 10000000 2>&1 | tail -1; done; done
+RAGB_MMA_PUBLISH=2 MMA_VARIANTS=3 MMA_KS=50 timeout 600 python scripts/bench_mma.py 1250000 2>&1 | tail -1
+MMA_VARIANTS=3 MMA_KS=50 timeout 600 python scripts/bench_mma.py 1250000 2>&1 | tail -1
