@@ -7,6 +7,8 @@ identical modulo ties; integer work (CSR, ids, masks) bit-exact.
 import json
 import math
 
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
@@ -181,6 +183,45 @@ def test_bm25_impact_bounds_only_prune(rq, dev, n, n_q, k):
     torch.testing.assert_close(with_s, want_s, rtol=0, atol=0)
     same = with_i.long() == want_i
     assert bool((same | (with_s == want_s)).all())      # ids may differ only inside exact score ties
+
+
+_WINDOW_STRESS = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+import rag_uq_b200 as rq
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(3)
+n, vocab, per_doc = 60_000, 96, 12                      # every term occurs in ~12% of the documents
+doc_tok = torch.randint(0, vocab, (n * per_doc,), generator=g, dtype=torch.int32).to(dev)
+doc_off = (torch.arange(n + 1, dtype=torch.int64) * per_doc).to(dev)
+shard = rq.build_shard(doc_off, doc_tok, vocab)
+shard.use_dense_table = False                           # all terms stream their posting lists: ub_table = 0, pruned from the start
+shard.finalize()
+n_q, k = 24, 20
+q_terms = torch.randint(0, vocab, (n_q * 30,), generator=g, dtype=torch.int32).to(dev)   # 30 dense lists per query
+q_off = (torch.arange(n_q + 1, dtype=torch.int32) * 30).to(dev)
+score, ids = shard.score_topk(q_terms, q_off, 30, k)
+full = shard.scores(q_terms, q_off, 30)
+want_s, want_i = torch.topk(full, k, dim=1)
+assert torch.equal(score, want_s), (score - want_s).abs().max()
+assert bool(((ids.long() == want_i) | (score == want_s)).all())
+print("window stress ok")
+"""
+
+
+@pytest.mark.parametrize("target", ["100000", "256", "0"])
+def test_bm25_window_mode_overflow_and_fallback(rq, dev, target):
+    """Window mode under stress: 30 dense posting lists per query overflow the 512-slot hash table at any window size
+    (halving down to one super-range, then back to the dense accumulator); an absurd posting target starts every
+    window at 32k documents.  The results must equal the exhaustive ranking bit for bit in every setting
+    (RAGB_BM25_WINDOW is read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, RAGB_BM25_WINDOW=target)
+    root = str(Path(__file__).resolve().parent.parent)
+    out = subprocess.run([sys.executable, "-c", _WINDOW_STRESS, root], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "window stress ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
 def test_bm25_edge_queries(rq, dev):
