@@ -522,12 +522,15 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
           window = max(BM_SUPER_DOCS, (window / 2) / BM_SUPER_DOCS * BM_SUPER_DOCS);
           continue;
         }
-        // compact the marked slots to the front of the table (position <= slot, so in place) ...
+        // compact the marked slots to the front of the table (position <= slot, so in place) ...  A marked
+        // document whose list part plus everything the table terms could add stays below thr is dropped here,
+        // before any of its table bytes is gathered (most marked documents match a single light list term).
+        const float need = (tk.thr_score - 2e-5f * fabsf(tk.thr_score)) - ub_table;
         int n_valid = 0;
         for (int base = 0; base < BM_HASH_SLOTS; base += 32) {
           const int key = keys[base + lane];
           const float val = vals[base + lane];
-          const bool valid = key != -1 && ((flags[base >> 5] >> lane) & 1u) != 0u;
+          const bool valid = key != -1 && ((flags[base >> 5] >> lane) & 1u) != 0u && val >= need;
           const unsigned m = __ballot_sync(0xffffffffu, valid);
           if (valid) {
             const int j = n_valid + __popc(m & ((1u << lane) - 1u));
