@@ -48,12 +48,16 @@ def gather_candidates(score: Tensor, ids: Tensor, group=None) -> Tuple[Tensor, T
     if world == 1:
         return score.unsqueeze(1), ids.unsqueeze(1)
     b, k = score.shape
-    all_s = torch.empty((world * b, k), dtype=score.dtype, device=score.device)   # rank-major concatenation
-    all_i = torch.empty((world * b, k), dtype=ids.dtype, device=ids.device)
-    dist.all_gather_into_tensor(all_s, score.contiguous(), group=group)
-    dist.all_gather_into_tensor(all_i, ids.contiguous(), group=group)
-    return (all_s.view(world, b, k).permute(1, 0, 2).contiguous(),
-            all_i.view(world, b, k).permute(1, 0, 2).contiguous())
+    # ONE collective: fp32 scores travel as their int32 bit pattern next to the int32 ids ([B, 2, k] per rank; the
+    # message is latency-bound - 800 KB per rank at B = 1024, two pools of 50 - so one launch instead of two matters)
+    if score.dtype != torch.float32 or ids.dtype != torch.int32:
+        raise TypeError("gather_candidates expects float32 scores and int32 ids")
+    packed = torch.stack([score.contiguous().view(torch.int32), ids.contiguous()], dim=1)
+    flat = torch.empty((world * b, 2, k), dtype=torch.int32, device=score.device)   # rank-major concatenation
+    dist.all_gather_into_tensor(flat, packed, group=group)
+    gathered = flat.view(world, b, 2, k)
+    return (gathered[:, :, 0].permute(1, 0, 2).contiguous().view(torch.float32),
+            gathered[:, :, 1].permute(1, 0, 2).contiguous())
 
 
 class HybridEngine:
