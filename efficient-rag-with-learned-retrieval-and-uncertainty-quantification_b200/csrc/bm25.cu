@@ -9,32 +9,40 @@
 //   norm[N] float32 = k1*(1-b+b*len/avgdl), idf[V] float32.
 // Algorithmic bytes per posting: 4 (doc) + 2 (tf) = 6, plus 4 per document per range for norm.
 //
-// Kernel shape.  grid = (queries, stripes); a block of 8 warps owns one stripe of
-// consecutive documents for one query, each WARP owns a contiguous eighth of it and walks
-// it in ranges of 256 documents (8 per lane).  Two ways a term reaches the accumulator:
-//  * the terms that occur in more than 1/64 of all documents (a few hundred; they carry >95% of
-//    all postings) are ALSO stored as a dense row of uint8 term frequencies; a lane
-//    loads its 8 bytes with one 64-bit load per term and accumulates in registers - no document
-//    ids, no cursor, no compare, ~12x fewer instructions per posting than list streaming;
-//  * every other term streams its posting list: lists are sorted by document, so a warp
-//    continues reading where it stopped (one cursor per term, placed once by a 32-ary search),
-//    128-byte coalesced, 1 to 8 independent 32-posting chunks per pass sized to the list's
-//    density, into a shared-memory accumulator that covers a super-range of 4 ranges (1024
-//    documents): these lists are sparse, so walking them once per kilodocument instead of once
-//    per range cuts their bookkeeping four-fold.  All documents inside one chunk are distinct,
-//    so the update is a plain read-modify-write: no atomics anywhere.  Terms whose next posting
-//    lies beyond the super-range are skipped with one ballot.
-// Which terms use the table is decided from GLOBAL document frequencies, so every shard makes
-// the same choice and the fp32 accumulation order (table terms in query order, then list terms
-// in query order) does not depend on how the corpus is sharded.
-// Pruning (exact): a document with no posting-list term can score at most the sum of the table
-// terms' weights; once a warp's k-th best exceeds that bound it only scores the documents its
-// posting lists touched in the super-range (bitmap + byte gathers from the table), which is what
-// the rarer query terms leave of 10M documents: ~80k per query.
+// Kernel shape.  grid = (queries, stripes), enough stripes for ~64 blocks per SM (queries differ widely in
+// cost once pruning works, fine stripes balance the SMs); a block of 8 warps owns one stripe of consecutive
+// documents for one query, each WARP owns a contiguous eighth of it.  A warp goes through up to three phases:
+//
+//  1. Dense accumulator (1024-document super-ranges, the only phase of the get_scores variant).  Two ways a
+//     term reaches the accumulator:
+//     * the terms that occur in more than 1/16 of all documents (~150; they carry >95% of all postings) are
+//       ALSO stored as a dense row of uint8 term frequencies; a lane loads its 8 bytes with one 64-bit load
+//       per term and accumulates in registers - no document ids, no cursor, no compare;
+//     * every other term streams its posting list: lists are sorted by document, so a warp continues reading
+//       where it stopped (one cursor per term, placed once by a 32-ary search), 128-byte coalesced, 1 to 8
+//       independent 32-posting chunks per pass sized to the list's density, into a shared-memory accumulator
+//       that covers the super-range.  All documents inside one chunk are distinct, so the update is a plain
+//       read-modify-write: no atomics on scores.  Terms whose next posting lies beyond the super-range are
+//       skipped with one ballot.
+//  2. fp16 bound pass (top-k variant, while thr is a sizeable fraction of what the table terms can add):
+//     an fp16 UPPER bound of every document's table score (one 128-bit load + four HFMA2 per term per 8
+//     documents) marks the few documents that may still reach thr; only those and the ones a posting list
+//     touched get the exact arithmetic.  With it the exact table path of phase 1 is never taken at 10M x 1024.
+//  3. Window mode (once thr exceeds the table bound): only documents a posting list touches matter - ~3% of
+//     the corpus per query - so the warp covers up to 32k documents per visit and keeps the accumulator as an
+//     open-addressing hash table in the same 4 KB of shared memory (see stream_term_hash).  MaxScore marks
+//     only documents of essential (heavy, rare) lists, and marked documents whose list part plus the table bound
+//     cannot reach thr are dropped before any table byte is gathered.
+//
+// Which terms use the table is decided from GLOBAL document frequencies, so every shard makes the same
+// choice, and all phases accumulate with the same fused multiply-adds in the same order (table terms in query
+// order, then list terms in query order): a document's score does not depend on the phase that computed it
+// nor on how the corpus is sharded.  Every pruning step is exact (proven bounds only).
 // Selection is warp-private too (WarpTopK in topk.cuh: threshold in a register, appends through a
 // ballot prefix, rare warp-level bitonic merge), so the main loop has no block barrier at all; the
 // 8 warp lists are folded once at the end of the block and the per-block lists of all stripes
-// are merged by topk_merge_kernel.
+// are merged by topk_merge_kernel.  bm25_seed_kernel proves a lower bound of each query's k-th best score
+// from its posting lists so that most queries start directly in phase 3.
 #include <cuda_fp16.h>
 
 #include <climits>
