@@ -283,3 +283,25 @@ def test_shard_format_round_trip_on_cpu(rq, tmp_path):
     (tmp_path / "bad" / "meta.json").write_text(json.dumps({"format": "something else"}))
     with pytest.raises(ValueError):
         rq.load_shard(tmp_path / "bad", "cpu")
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` needs no GPU: it times the oracle port of the reference's per-query path on the
+    host cores and prints ONE JSON line with the keys the driver reads (same metric / unit / config as our arm)."""
+    import sys
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample-docs", "300"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
+    assert d["metric"] == "hybrid top-10 queries/sec over 10Mx768 passages" and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["steps"] == 1 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "passages" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 stay silent under torchrun
+    env = dict(**__import__("os").environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=60, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
