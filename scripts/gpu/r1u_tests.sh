@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider -k "window_mode or bm25" > gpurun_out/pytest_win.log 2>&1
-echo "== pytest exit $? =="; tail -n 25 gpurun_out/pytest_win.log
+timeout 200 python -m pytest tests -m gpu -q --timeout 150 -p no:cacheprovider -k "random_small_corpora" > gpurun_out/pytest_rand.log 2>&1
+echo "== pytest exit $? =="; tail -n 30 gpurun_out/pytest_rand.log | cut -c1-220

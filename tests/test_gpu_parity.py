@@ -224,6 +224,46 @@ def test_bm25_window_mode_overflow_and_fallback(rq, dev, target):
     assert out.returncode == 0 and "window stress ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_bm25_random_small_corpora_vs_oracle(rq, dev, seed):
+    """Differential test on odd shapes: random tiny / ragged corpora (empty documents, vocabularies from 3 to 5000
+    terms, with and without the byte table), random k, queries with duplicates and out-of-vocabulary ids - top-k
+    scores must equal the float64 oracle within 1e-5 and the exhaustive GPU ranking bit for bit."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    n = int(torch.randint(1, 3000, (1,), generator=g))
+    vocab = int(torch.randint(3, 5000, (1,), generator=g))
+    lens = torch.randint(0, 40, (n,), generator=g)
+    if seed % 3 == 0:
+        lens[torch.randint(0, n, (max(1, n // 7),), generator=g)] = 0          # empty documents
+    doc_off = torch.zeros(n + 1, dtype=torch.int64)
+    doc_off[1:] = torch.cumsum(lens, 0)
+    skew = torch.rand(int(doc_off[-1]), generator=g) ** (2 + seed % 4)          # a few very frequent terms
+    doc_tok = (skew * vocab).to(torch.int32).clamp_(max=vocab - 1)
+    shard = rq.build_shard(doc_off.to(dev), doc_tok.to(dev), vocab)
+    shard.use_dense_table = seed % 2 == 0
+    shard.finalize()
+    n_q = int(torch.randint(1, 40, (1,), generator=g))
+    q_len = torch.randint(0, 12, (n_q,), generator=g)
+    q_off = torch.zeros(n_q + 1, dtype=torch.int32)
+    q_off[1:] = torch.cumsum(q_len, 0).to(torch.int32)
+    q_terms = torch.randint(-2, vocab + 3, (max(1, int(q_off[-1])),), generator=g, dtype=torch.int32)   # some OOV ids
+    k = int(torch.randint(1, 120, (1,), generator=g))
+    max_terms = max(1, int(q_len.max()))
+    score, ids = shard.score_topk(q_terms.to(dev), q_off.to(dev), max_terms, k)
+    full = shard.scores(q_terms.to(dev), q_off.to(dev), max_terms)
+    kk = min(k, n)
+    want_s, want_i = torch.topk(full, kk, dim=1)
+    want_s = torch.where(want_s > 0, want_s, torch.zeros_like(want_s))          # only positive scores are returned
+    assert torch.equal(score[:, :kk], want_s)
+    assert bool((score[:, kk:] == 0).all()) and bool((ids[:, kk:] == -1).all())
+    assert bool(((ids[:, :kk].long() == want_i) | (want_s == 0) | (score[:, :kk] == want_s)).all())
+    assert bool((ids[:, :kk][want_s == 0] == -1).all())
+    ref = bm25_okapi.OkapiCsr(doc_off.numpy(), doc_tok.numpy(), vocab)
+    for q in range(n_q):
+        terms = q_terms[int(q_off[q]):int(q_off[q + 1])].tolist()
+        np.testing.assert_allclose(full[q].cpu().numpy(), ref.get_scores(terms), rtol=1e-5, atol=1e-9)
+
+
 def test_bm25_edge_queries(rq, dev):
     """empty query, all-OOV query, duplicated terms, a query longer than the corpus is wide."""
     vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, 1000)
