@@ -528,6 +528,41 @@ def test_full_fusion_fused_epilogue(rq, dev, n, n_q, k, hidden, scale):
         assert (fi.cpu().long() - 1000 == want_i).float().mean() > 0.98
 
 
+@pytest.mark.parametrize("seed", list(range(6)))
+def test_full_fusion_fused_epilogue_random_shapes(rq, dev, seed):
+    """Differential test of the fused epilogue against the un-fused path on odd shapes: ragged tile tails, one and many
+    query slabs, k from 1 to 100, hidden 16-128, gates of any steepness, statistics that put the gate anywhere."""
+    from rag_uq_b200 import synth
+    g = torch.Generator().manual_seed(77 + seed)
+    n = int(torch.randint(300, 6000, (1,), generator=g))
+    n_q = int(torch.randint(9, 300, (1,), generator=g))
+    k = int(torch.randint(1, 101, (1,), generator=g))
+    hidden = [16, 32, 64, 128, 64, 48][seed]
+    scale = [1.0, 3.0, 0.3, 12.0, 1.0, 6.0][seed]
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    passages = synth.passage_embeddings(0, n, 768, dev)
+    engine = rq.HybridEngine(rq.build_shard(doc_off, doc_tok, vocab).finalize(), passages, id_base=seed * 1000)
+    qb = synth.make_queries(n_q, n, 768, cdf, dev)
+    torch.manual_seed(seed)
+    router = rq.RetrievalRouter(rq.RouterConfig(hidden_dim=hidden)).to(dev).eval()
+    with torch.no_grad():
+        for p in router.parameters():
+            p.mul_(scale)
+    stats = torch.rand(4, generator=g)
+    router.bm25_mean.fill_(float(stats[0]) * 20 - 2); router.bm25_std.fill_(float(stats[1]) * 10 + 0.1)
+    router.dense_mean.fill_(float(stats[2]) - 0.5); router.dense_std.fill_(float(stats[3]) * 0.5 + 0.02)
+    router.stats_initialized = True
+    with torch.no_grad():
+        fs, fi = engine.full_fusion_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, fused=True)
+        us, ui = engine.full_fusion_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, fused=False, query_chunk=64)
+    assert fs.shape == us.shape == (n_q, min(k, n))
+    tol = 1e-5 * max(1.0, scale * scale) * max(1.0, 0.2 / float(router.dense_std))
+    torch.testing.assert_close(fs, us, rtol=tol, atol=tol)
+    same = fi == ui
+    assert same.float().mean() > 0.98
+    assert bool(((fs - us).abs()[~same] <= tol * us.abs()[~same] + tol).all())
+
+
 def test_row_sharded_engine_equals_single_engine(rq, dev):
     """Emulate G = 2 on one GPU: local pools per shard, merged exactly as the all-gather path merges."""
     from rag_uq_b200 import synth
