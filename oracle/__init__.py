@@ -10,16 +10,21 @@ What is restated here and how it is pinned
 * ``bm25_okapi``  - rank_bm25 0.2.2 ``BM25Okapi`` (PyPI dependency of the
   reference, ``requirements.txt:8``; NOT vendored under /root/reference and not
   installable in this image) + ``BM25Index.search``
-  (``rag_uq/streaming_index.py:150-179``).  **Parity unpinned**: the reference
-  has no test, fixture or golden vector touching ``streaming_index.py``; the
-  restatement is anchored on the published rank_bm25 algorithm and on the
-  hand-derived known-answer vectors in ``tests/golden/bm25_known_answers.json``.
+  (``rag_uq/streaming_index.py:150-179``).  ``BM25Index.search`` is **pinned**: the
+  live class runs in ``tests/golden/make_retrieval_golden.py`` (its missing third-party
+  ``BM25Okapi`` bound to ``OkapiLiteral``) -> ``tests/golden/retrieval_golden.json``.
+  The rank_bm25 ARITHMETIC stays **parity unpinned** (package not installable, no
+  reference fixture): anchored on the published algorithm and the hand-derived
+  known-answer vectors in ``tests/golden/bm25_known_answers.json``.
 * ``dense``       - exact cosine scoring that stands in for ChromaDB's
   approximate HNSW (``rag_uq/streaming_index.py:338-370``).  **Parity
   unpinned** (chromadb not installable; no reference test).
 * ``fusion``      - ``HybridRetriever.hybrid_search`` /
-  ``get_scores_for_router`` (``rag_uq/streaming_index.py:464-557``).  **Parity
-  unpinned** (no reference test).
+  ``get_scores_for_router`` (``rag_uq/streaming_index.py:464-557``).  **Pinned**:
+  the live ``HybridRetriever`` runs in ``make_retrieval_golden.py`` with stubbed
+  pools (disjoint pools, an empty / all-zero side, negative and all-negative
+  cosines, ids without a stored document, short pools, pool cuts) and the oracle
+  reproduces its output bit for bit.
 * ``router``      - ``RetrievalRouter`` forward / hybrid_rerank / MC-Dropout
   (``rag_uq/router.py:100-202``).  **Pinned**: checked bit-for-bit against the
   live reference module imported from /root/reference; golden vectors are

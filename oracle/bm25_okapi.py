@@ -7,9 +7,16 @@ Follows
   * ``BM25Index._tokenize``  ``rag_uq/streaming_index.py:118-120``
   * ``BM25Index.search``     ``rag_uq/streaming_index.py:150-179``
 
-PARITY UNPINNED: the reference holds no test / golden vector for this path; the
-known answers in ``tests/golden/bm25_known_answers.json`` were derived by hand
-from the published Okapi formula and are reproduced by both classes below.
+PINNED (``BM25Index.search`` around the scoring call): ``tests/golden/make_retrieval_golden.py``
+runs the LIVE ``rag_uq.streaming_index.BM25Index`` from /root/reference (tokeniser, duplicate
+skipping, rebuild per add, ``np.argsort(...)[::-1][:top_k]``, the ``> 0`` filter, row -> doc id)
+with the module's missing ``BM25Okapi`` bound to ``OkapiLiteral`` and stores its results in
+``tests/golden/retrieval_golden.json``; ``index_search`` / ``tokenize`` are checked against it.
+PARITY UNPINNED (the rank_bm25 arithmetic itself): the package cannot be installed here and the
+reference holds no golden vector for it; the known answers in
+``tests/golden/bm25_known_answers.json`` were derived by hand from the published Okapi formula
+ and are reproduced by both classes below and by an independent scalar
+implementation in ``tests/golden/make_golden.py``.
 
 Two implementations, checked against each other in ``tests/test_oracle_cpu.py``:
   ``OkapiLiteral``  - per-document dict-of-counts, one Python pass over every

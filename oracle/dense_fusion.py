@@ -8,8 +8,14 @@ Follows
   * ``HybridRetriever.hybrid_search``      ``rag_uq/streaming_index.py:464-523``
   * ``HybridRetriever.get_scores_for_router`` ``rag_uq/streaming_index.py:525-557``
 
-PARITY UNPINNED for all three: the reference has no test or fixture for
-``streaming_index.py`` and chromadb is not installable in this image.
+PINNED (fusion): ``tests/golden/make_retrieval_golden.py`` runs the LIVE
+``rag_uq.streaming_index.HybridRetriever`` from /root/reference with its two
+``*_search`` methods replaced by fixed pools and stores what ``hybrid_search`` and
+``get_scores_for_router`` return (``tests/golden/retrieval_golden.json``);
+``tests/test_oracle_cpu.py`` checks the two functions below against it bit for bit
+(and against the live class on random pools whenever /root/reference is mounted).
+PARITY UNPINNED (dense scoring only): chromadb is not installable in this image,
+so the exact cosine is anchored on its definition, not on ChromaDB output.
 """
 from __future__ import annotations
 
@@ -37,17 +43,19 @@ def topk_desc(scores: np.ndarray, k: int, positive_only: bool = False) -> List[L
 
 
 def hybrid_search(bm25_pool: Sequence[Tuple[int, float]], dense_pool: Sequence[Tuple[int, float]],
-                  top_k: int = 10) -> List[Tuple[int, float, float, float]]:
+                  top_k: int = 10, known_ids=None) -> List[Tuple[int, float, float, float]]:
     """Pool fusion, streaming_index.py:484-523.  Returns (id, bm25, dense, hybrid) rows.
 
-    Union of the two pools, a score missing from one pool is 0.0 (:498-499), each
+    Union of the two pools, ids the retriever holds no document for are skipped
+    BEFORE the maxima are taken (:494-496; ``known_ids`` = container of the ids it
+    holds, None = all), a score missing from one pool is 0.0 (:498-499), each
     score divided by the pool-union maximum - ``max(...) or 1`` (:513-514) -
     averaged (:517-519), sorted descending (:521), cut to top_k (:523).  Tie order
     in the reference depends on set iteration order; we fix it to id ascending.
     """
     b: Dict[int, float] = dict(bm25_pool)
     d: Dict[int, float] = dict(dense_pool)
-    ids = sorted(set(b) | set(d))
+    ids = sorted(i for i in (set(b) | set(d)) if known_ids is None or i in known_ids)
     if not ids:
         return []
     rows = [(i, b.get(i, 0.0), d.get(i, 0.0)) for i in ids]
@@ -58,10 +66,11 @@ def hybrid_search(bm25_pool: Sequence[Tuple[int, float]], dense_pool: Sequence[T
     return fused[:top_k]
 
 
-def scores_for_router(bm25_pool, dense_pool, num_passages: int = 20):
+def scores_for_router(bm25_pool, dense_pool, num_passages: int = 20, known_ids=None):
     """streaming_index.py:537-557: hybrid_search(top_k=num_passages) split into aligned
-    lists and padded with 0.0 / id -1 (the reference pads ids with "")."""
-    rows = hybrid_search(bm25_pool, dense_pool, top_k=num_passages)
+    lists and padded with 0.0 / id -1 (the reference pads ids with "").  The caller hands
+    in pools of (at most) 50: get_scores_for_router does not forward a pool size (:537)."""
+    rows = hybrid_search(bm25_pool, dense_pool, top_k=num_passages, known_ids=known_ids)
     bm = [r[1] for r in rows]
     de = [r[2] for r in rows]
     ids = [r[0] for r in rows]

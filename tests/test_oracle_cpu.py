@@ -100,6 +100,150 @@ def test_topk_desc_ties():
     assert [i for i, _ in dense_fusion.topk_desc(s, 10, positive_only=True)[0]] == [1, 2, 4, 0]
 
 
+# ------------------------------------------------- fusion + BM25Index.search vs the LIVE reference's outputs
+@pytest.fixture(scope="module")
+def retrieval_gold(golden_dir):
+    with open(golden_dir / "retrieval_golden.json") as fh:
+        return json.load(fh)
+
+
+def tie_groups(rows, score_of):
+    """[[ids of equal score...], ...] in rank order: the reference's order INSIDE a group is set-iteration /
+    introsort dependent, the groups themselves and their order are not."""
+    groups = []
+    for r in rows:
+        if groups and score_of(r) == groups[-1][0]:
+            groups[-1][1].add(r[0])
+        else:
+            groups.append((score_of(r), {r[0]}))
+    return [g for _, g in groups]
+
+
+def _number_pools(case, number):
+    pool = case["retrieval_pool_size"]
+    return ([(number(i), s) for i, s in case["bm25_pool"][:pool]], [(number(i), s) for i, s in case["dense_pool"][:pool]])
+
+
+def test_fusion_oracle_matches_live_reference_golden(retrieval_gold):
+    """oracle.dense_fusion.hybrid_search / scores_for_router == HybridRetriever.hybrid_search /
+    get_scores_for_router of /root/reference (streaming_index.py:464-557) on every stored case, bit for bit."""
+    hy = retrieval_gold["hybrid"]
+    known = {d: i for i, d in enumerate(hy["document_ids"])}
+    ghosts = {}
+
+    def number(doc_id):
+        return known[doc_id] if doc_id in known else ghosts.setdefault(doc_id, 10_000 + len(ghosts))
+
+    assert len(hy["cases"]) >= 20
+    for case in hy["cases"]:
+        bpool, dpool = _number_pools(case, number)
+        got = dense_fusion.hybrid_search(bpool, dpool, case["top_k"], known_ids=set(known.values()))
+        want = [(number(r[0]), r[1], r[2], r[3]) for r in case["hybrid_search"]]
+        assert len(got) == len(want), case["name"]
+        assert tie_groups(got, lambda r: r[3]) == tie_groups(want, lambda r: r[3]), case["name"]
+        by_id = {r[0]: r for r in want}
+        for r in got:                                   # same Python-float arithmetic: exact equality
+            assert r == by_id[r[0]], (case["name"], r, by_id[r[0]])
+        # get_scores_for_router always pools 50 (:537) and pads with 0.0 / ""
+        n = case["num_passages"]
+        b50 = [(number(i), s) for i, s in case["bm25_pool"][:50]]
+        d50 = [(number(i), s) for i, s in case["dense_pool"][:50]]
+        ob, od, oi = dense_fusion.scores_for_router(b50, d50, n, known_ids=set(known.values()))
+        ref = case["scores_for_router"]
+        assert len(ob) == len(od) == len(oi) == n == len(ref["bm25"]) == len(ref["ids"]) == len(ref["texts"])
+        ref_rows = [(number(i) if i != "" else -1, b, d) for i, b, d in zip(ref["ids"], ref["bm25"], ref["dense"])]
+        assert sorted(zip(oi, ob, od)) == sorted(ref_rows), case["name"]
+        n_real = sum(1 for i in ref["ids"] if i != "")
+        assert oi[n_real:] == [-1] * (n - n_real) and ob[n_real:] == [0.0] * (n - n_real) and od[n_real:] == [0.0] * (n - n_real)
+        assert all(t == (f"text of {i}" if i else "") for i, t in zip(ref["ids"], ref["texts"]))
+
+
+def test_index_search_oracle_matches_live_reference_golden(retrieval_gold):
+    """oracle.bm25_okapi.tokenize + index_search == BM25Index.search of /root/reference (:150-179): argsort cut,
+    the > 0 filter, top_k > N, row -> doc id, duplicate documents skipped on add."""
+    n_cases = 0
+    for corpus in retrieval_gold["bm25_index_search"]:
+        docs = [bm25_okapi.tokenize(t) for t in corpus["texts"]]
+        lit = bm25_okapi.OkapiLiteral(docs, k1=corpus["k1"], b=corpus["b"])
+        vocab = {}
+        ids = [[vocab.setdefault(w, len(vocab)) for w in d] for d in docs]
+        off = np.concatenate([[0], np.cumsum([len(d) for d in ids])])
+        csr = bm25_okapi.OkapiCsr(off, np.concatenate(ids), len(vocab), k1=corpus["k1"], b=corpus["b"])
+        for case in corpus["cases"]:
+            toks = bm25_okapi.tokenize(case["query"])
+            got = bm25_okapi.index_search(lit.get_scores(toks), case["top_k"])
+            want = [(corpus["doc_ids"].index(d), s) for d, s in case["result"]]
+            assert len(got) == len(want), (corpus["name"], case["query"])
+            assert tie_groups(got, lambda r: r[1]) == tie_groups(want, lambda r: r[1]), (corpus["name"], case["query"])
+            assert dict(got) == dict(want)              # identical float64 scores
+            got_csr = bm25_okapi.index_search(csr.get_scores([vocab.get(w, -1) for w in toks]), case["top_k"])
+            assert [i for i, _ in got_csr] == [i for i, _ in got] or tie_groups(got_csr, lambda r: round(r[1], 9)) == \
+                tie_groups(got, lambda r: round(r[1], 9))
+            np.testing.assert_allclose([s for _, s in got_csr], [s for _, s in got], rtol=1e-12)
+            n_cases += 1
+    assert n_cases >= 20
+
+
+@pytest.mark.skipif(not REFERENCE.exists(), reason="live reference only exists in the build container")
+def test_fusion_and_index_search_oracle_match_live_reference_random():
+    """300 random pool pairs and 40 random corpora through the live classes (not only the stored cases)."""
+    sys.path.insert(0, str(REFERENCE))
+    try:
+        import rag_uq.streaming_index as ref
+    finally:
+        sys.path.remove(str(REFERENCE))
+    rng = np.random.default_rng(77)
+    names = [f"doc{i}" for i in range(150)]
+    for trial in range(300):
+        r = ref.HybridRetriever()
+        held = set(rng.choice(150, size=int(rng.integers(100, 151)), replace=False).tolist())
+        for i in held:
+            r.documents[names[i]] = ref.Document(id=names[i], text=f"t{i}")
+        nb, nd = int(rng.integers(0, 61)), int(rng.integers(0, 61))
+        lo_d = float(rng.choice([-1.0, -0.2, 0.0, 0.3]))
+        bp = [(int(i), float(s)) for i, s in zip(rng.choice(150, nb, replace=False), np.sort(rng.uniform(0.01, 25, nb))[::-1])]
+        dp = [(int(i), float(s)) for i, s in zip(rng.choice(150, nd, replace=False), np.sort(rng.uniform(lo_d, lo_d + 1, nd))[::-1])]
+        if trial % 9 == 0:
+            dp = [(i, 0.0) for i, _ in dp]
+        pool, top_k = int(rng.integers(1, 70)), int(rng.integers(1, 40))
+        r.bm25_search = lambda q, k=20, bp=bp: [(names[i], s) for i, s in bp[:k]]
+        r.dense_search = lambda q, k=20, dp=dp: [(names[i], s) for i, s in dp[:k]]
+        everything = r.hybrid_search("q", 10 ** 6, pool)
+        hs = [x.hybrid_score for x in everything]
+        if top_k < len(hs) and hs[top_k - 1] == hs[top_k]:
+            continue                                     # cut inside a tie group: membership is set-order dependent
+        live = [(names.index(x.doc_id), x.bm25_score, x.dense_score, x.hybrid_score) for x in everything[:top_k]]
+        got = dense_fusion.hybrid_search(bp[:pool], dp[:pool], top_k, known_ids=held)
+        assert tie_groups(got, lambda x: x[3]) == tie_groups(live, lambda x: x[3])
+        assert sorted(got) == sorted(live)
+    saved = getattr(ref, "BM25Okapi", None)
+    ref.BM25Okapi = bm25_okapi.OkapiLiteral      # the un-vendored third-party class (see make_retrieval_golden.py)
+    try:
+        words = [f"w{i}" for i in range(40)]
+        for trial in range(40):
+            n = int(rng.integers(1, 60))
+            texts = [" ".join(rng.choice(words, size=int(rng.integers(1, 25))).tolist()) for _ in range(n)]
+            index = ref.BM25Index()
+            index.add_documents([ref.Document(id=f"d{i}", text=t) for i, t in enumerate(texts)])
+            lit = bm25_okapi.OkapiLiteral([bm25_okapi.tokenize(t) for t in texts])
+            for _ in range(5):
+                q = " ".join(rng.choice(words + ["oov"], size=int(rng.integers(1, 6))).tolist())
+                k = int(rng.integers(1, 2 * n + 2))
+                scores = lit.get_scores(bm25_okapi.tokenize(q))
+                ranked = np.sort(scores)[::-1]
+                if k < n and ranked[k - 1] == ranked[k] and ranked[k - 1] > 0:
+                    continue
+                live = [(int(d[1:]), s) for d, s in index.search(q, k)]
+                got = bm25_okapi.index_search(scores, k)
+                assert tie_groups(got, lambda x: x[1]) == tie_groups(live, lambda x: x[1])
+                assert dict(got) == dict(live)
+    finally:
+        if saved is None:
+            del ref.BM25Okapi
+        else:
+            ref.BM25Okapi = saved
+
+
 # ---------------------------------------------------------------------------------- router
 @pytest.fixture(scope="module")
 def gold(golden_dir):
