@@ -386,17 +386,22 @@ __device__ __forceinline__ void load_bm25_chunk(const float* __restrict__ p, flo
 
 struct FusedBound {
   const uint32_t* table;  // shared memory, [n_b][n_d]: bf16 lo in bits 0-15, bf16 hi in bits 16-31
-  float inv_wb, inv_wd, d_off;
-  uint32_t nb_max, nd_mask;  // n_b - 1, n_d - 1 (n_d is a power of two)
+  float inv_wb, inv_wd, d_hi;
+  uint32_t nb_max;
+  int nd_max;  // n_b - 1, n_d - 1 (n_d is a power of two)
   int nd_shift;
-  // Full-rate ALU only (no F2I / F2F): x + (2^23 - 0.5) rounds to 2^23 + floor(x), so the low mantissa bits
-  // are the cell index (a point exactly on a cell boundary may land in either neighbour: both closed
-  // cells contain it).  Negative, huge or NaN bm25 wrap to a large unsigned and clamp into the last row
-  // (lo = 0, hi = 1: bound = max(b, d)); dense stays inside +-d_hi by contract and is masked so that a
-  // violation can never read outside the table.
+  // Full-rate ALU only (no F2I / F2F): for 0.25 <= x < 2^22, fmaf(.., 8388607.5f) = x + (2^23 - 0.5) rounds to
+  // 2^23 + floor(x), so the low mantissa bits are the cell index (a point exactly on a cell boundary may land in
+  // either neighbour: both closed cells contain it).  The magic constant must be the LAST rounding step: the
+  // offset of the dense axis is therefore added to d first (d + d_hi >= 0), never folded into the constant -
+  // 2^23 - 0.5 + d_hi / wd is not representable and would turn the floor into a round-to-nearest.
+  // x < 0.25 gives 2^23 - 0.5 (bit pattern just below 0x4B000000): as a signed difference that is -1 and clamps
+  // to cell 0.  Negative, huge or NaN bm25 wrap to a large UNSIGNED value and clamp into the last row
+  // (lo = 0, hi = 1: bound = max(b, d)); dense stays inside +-d_hi by contract and is clamped (not masked) so a
+  // violation lands in an edge cell instead of wrapping to the opposite end of the table.
   __device__ __forceinline__ float operator()(const float b, const float d) const {
     const uint32_t ib = min(__float_as_uint(fmaf(b, inv_wb, 8388607.5f)) - 0x4B000000u, nb_max);
-    const uint32_t id = __float_as_uint(fmaf(d, inv_wd, d_off)) & nd_mask;
+    const int id = min(max(static_cast<int>(__float_as_uint(fmaf(d + d_hi, inv_wd, 8388607.5f)) - 0x4B000000u), 0), nd_max);
     const uint32_t e = table[(ib << nd_shift) + id];
     const float diff = d - b;
     const float g = __uint_as_float(diff <= 0.0f ? (e << 16) : (e & 0xffff0000u));
@@ -447,6 +452,14 @@ struct LaneGate {
   }
 };
 
+// Debug aid (tests): the bound exactly as the fused epilogue evaluates it, for arbitrary (bm25, dense) pairs.
+__global__ void ff_bound_debug_kernel(const float* __restrict__ b, const float* __restrict__ d, int n,
+                                      const uint32_t* __restrict__ table, int n_b, int n_d, float inv_wb, float inv_wd,
+                                      float d_hi, float* __restrict__ out) {
+  const FusedBound bound{table, inv_wb, inv_wd, d_hi, static_cast<uint32_t>(n_b - 1), n_d - 1, 31 - __clz(n_d)};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = bound(b[i], d[i]);
+}
+
 template <int BN, int KPL>
 __device__ __forceinline__ void epilogue_scan_fused(const MmaArgs& a, const uint32_t* s_table, const uint32_t tmem_base,
                                                     const uint32_t acc_col0, uint64_t* block_lists, const int warp,
@@ -468,8 +481,8 @@ __device__ __forceinline__ void epilogue_scan_fused(const MmaArgs& a, const uint
   static_assert(BN == 256, "the bm25 matrix is stored in 256-passage tiles");
   const float* brow = a.bm25 + static_cast<int64_t>(live ? query : 0) * BN;
   const int64_t tile_stride = a.bm25_ld * BN;
-  const FusedBound bound{s_table, a.ff_inv_wb, a.ff_inv_wd, fmaf(a.ff_d_hi, a.ff_inv_wd, 8388607.5f),
-                         static_cast<uint32_t>(a.ff_nb - 1), static_cast<uint32_t>(a.ff_nd - 1), 31 - __clz(a.ff_nd)};
+  const FusedBound bound{s_table, a.ff_inv_wb, a.ff_inv_wd, a.ff_d_hi,
+                         static_cast<uint32_t>(a.ff_nb - 1), a.ff_nd - 1, 31 - __clz(a.ff_nd)};
   LaneGate gate;
   gate.load(a.rw, lane);
   ListState st{0, -INFINITY, 0ull};
@@ -1254,6 +1267,20 @@ int ragb_dense_mma_fused_topk(const void* passages_bf16, int64_t n_rows, int32_t
 #undef RAGB_FUSED_ARGS
   if (rc != RAGB_OK) return rc;
   return launch_merge_keys(part, n_queries, n_groups * 2, k, k, out_score, out_id, stream);
+}
+
+// Debug aid (not part of the documented ABI): evaluate the full-fusion bound of the fused epilogue for n
+// (bm25, dense) pairs with the same table geometry ragb_dense_mma_fused_topk derives from (n_b, n_d, b_cap, d_hi).
+int ragb_debug_fused_bound(const float* bm25, const float* dense, int32_t n, const uint32_t* gate_bound_table, int32_t n_b,
+                           int32_t n_d, float b_cap, float d_hi, float* out, ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  RAGB_REQUIRE(bm25 && dense && gate_bound_table && out && n > 0, RAGB_EINVAL, "ragb_debug_fused_bound: bad argument");
+  RAGB_REQUIRE(n_b >= 2 && n_d >= 1 && (n_d & (n_d - 1)) == 0, RAGB_EINVAL, "ragb_debug_fused_bound: bad table shape");
+  ff_bound_debug_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      bm25, dense, n, gate_bound_table, n_b, n_d, static_cast<float>(n_b) / b_cap, static_cast<float>(n_d) / (2.0f * d_hi),
+      d_hi, out);
+  RAGB_AFTER_LAUNCH(1);
+  return RAGB_OK;
 }
 
 }  // extern "C"

@@ -72,7 +72,11 @@ struct BlockTopK {
   // Block-wide: make room for `incoming` further appends.  Contains barriers.
   __device__ __forceinline__ void reserve(int incoming) {
     __syncthreads();
-    if (*count + incoming > room()) flush();
+    const bool must_flush = *count + incoming > room();
+    // every thread has taken the (therefore block-uniform) decision before the first offer() of a faster warp
+    // moves *count: without this barrier two warps could disagree and meet mismatched barriers inside flush()
+    __syncthreads();
+    if (must_flush) flush();
   }
 
   // Block-wide: fold the appended candidates into the sorted top-k.  Contains barriers;

@@ -170,13 +170,18 @@ class HybridEngine:
         MC-Dropout confidence of the router on these candidates.  Returns a dict of device tensors.
         """
         ids, sb, sd, sh = self.hybrid_topk(q_terms, q_off, max_terms, q_emb, k, pool)
-        fused, order = router.hybrid_rerank(sb, sd, top_k=k)
+        # The reference loop calls the router once per query with [1, k] tensors (run_evaluation.py:171-174): until
+        # running statistics are armed (the state right after load_state_dict) every query is normalised with ITS OWN
+        # mean / std.  A [B, k] call would normalise over the whole batch and make a query's ranking depend on its
+        # batch mates, so the per-query mode is requested explicitly; with running statistics it changes nothing.
+        per_query = not getattr(router, "stats_initialized", False)
+        fused, order = router.hybrid_rerank(sb, sd, top_k=k, per_query_stats=per_query)
         ranked = torch.gather(ids, 1, order)
         out = {"ids": ranked, "fused": fused, "bm25": torch.gather(sb, 1, order), "dense": torch.gather(sd, 1, order),
                "hybrid": torch.gather(sh, 1, order),
                "retrieval_uncertainty": ops.retrieval_uncertainty(fused.contiguous(), ranked.contiguous(), lam)}
         if mc_samples > 0:
-            unc = router.mc_dropout(sb, sd, n_samples=mc_samples, seed=seed)
+            unc = router.mc_dropout(sb, sd, n_samples=mc_samples, seed=seed, per_query_stats=per_query)
             out["router_confidence"] = unc.confidence
             out["gate_mean"], out["gate_std"] = unc.mean_gate, unc.std_gate
         return out

@@ -433,7 +433,7 @@ def router_mc_dropout(bm25: Tensor, dense: Tensor, w1: Tensor, b1: Tensor, w2: T
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     with torch.cuda.device(dev):
         check(lib.ragb_router_mc_dropout(_ptr(bm25), _ptr(dense), n_q, n_cand, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2),
-                                         _ptr(stats), hidden, norm_mode, n_samples, p_drop, seed, offset, mask_layout,
+                                         _ptr(stats), hidden, norm_mode, n_samples, p_drop, seed & 0xFFFFFFFFFFFFFFFF, offset, mask_layout,
                                          sm_count, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]),
                                          _ptr(variance), _ptr(consensus), _ptr(mask) if dump else None,
                                          _ptr(gates) if dump else None, _ptr(scratch), _stream()))

@@ -10,7 +10,11 @@ all scoring happens on the B200 through ``engine.HybridEngine``.  Differences, a
 * ``embed_fn`` (texts -> [n, dim] array) replaces the per-text Ollama HTTP call
   (:267-288); without it the class tries ``ollama`` and then the reference's sha256
   pseudo-embedding (:269-273), exactly in that order;
-* ``*_batch`` methods take whole query batches.
+* ``*_batch`` methods take whole query batches;
+* the dense side persists under ``persist_directory`` as raw arrays instead of a ChromaDB store
+  (``<persist_directory>/<collection_name>/rows.bf16 + meta.jsonl + header.json``, appended on every add and
+  reloaded by the constructor, like the reference's PersistentClient at :254-263), so an index resumed from
+  the ``StreamingIndex`` checkpoint has its dense rows back; ``persist_directory=None`` keeps it in memory only.
 Tie order, which the reference leaves to introsort / set iteration, is fixed: higher score
 first, then the document added earlier.
 """
@@ -191,7 +195,7 @@ class BM25Index:
 class DenseIndex:
     """Exact cosine index over bf16 unit rows in HBM (the reference asks ChromaDB's HNSW)."""
 
-    def __init__(self, collection_name: str = "rag_documents", persist_directory: str = "./data/chroma_db",
+    def __init__(self, collection_name: str = "rag_documents", persist_directory: Optional[str] = "./data/chroma_db",
                  embedding_model: str = "nomic-embed-text", chroma_host: Optional[str] = None, chroma_port: int = 8000,
                  embed_fn: Optional[Callable[[List[str]], Any]] = None, device=None, mma_variant: int = 3):
         self.collection_name = collection_name
@@ -207,7 +211,51 @@ class DenseIndex:
         self._rows: Optional[torch.Tensor] = None   # bf16 [capacity, dim_padded]
         self._count = 0
         self.dim: Optional[int] = None
+        if chroma_host:
+            logger.warning("chroma_host=%s ignored: rag_uq_b200 keeps the dense rows in HBM and persists them under "
+                           "persist_directory, it does not talk to a ChromaDB server", chroma_host)
+        self._store = Path(persist_directory) / collection_name if persist_directory else None
+        if self._store is not None and (self._store / "header.json").exists():
+            self._load()
         logger.info(f"Initialized DenseIndex with collection '{collection_name}'")
+
+    # -- persistence (stands in for chromadb.PersistentClient, streaming_index.py:254-263) --------------
+    def _persist(self, rows: torch.Tensor, ids: Sequence[str], texts: Sequence[str], metadatas: Sequence[Dict[str, Any]]) -> None:
+        """Append the new rows (raw little-endian bf16, padded width) and one JSON line per document."""
+        if self._store is None:
+            return
+        self._store.mkdir(parents=True, exist_ok=True)
+        header = self._store / "header.json"
+        if not header.exists():
+            header.write_text(json.dumps({"format": "rag_uq_b200 dense rows v1", "dim": self.dim, "padded_dim": int(rows.shape[1]),
+                                          "dtype": "bfloat16", "embedding_model": self.embedding_model}))
+        with open(self._store / "rows.bf16", "ab") as fh:
+            fh.write(rows.cpu().view(torch.int16).numpy().tobytes())
+        with open(self._store / "meta.jsonl", "a") as fh:
+            for i, t, m in zip(ids, texts, metadatas):
+                fh.write(json.dumps({"id": i, "text": t, "metadata": m}) + "\n")
+
+    def _load(self) -> None:
+        head = json.loads((self._store / "header.json").read_text())
+        if head.get("format") != "rag_uq_b200 dense rows v1":
+            raise ValueError(f"{self._store}: not a rag_uq_b200 dense store")
+        meta_path, rows_path = self._store / "meta.jsonl", self._store / "rows.bf16"
+        metas = [json.loads(line) for line in meta_path.read_text().splitlines() if line.strip()] if meta_path.exists() else []
+        width = int(head["padded_dim"])
+        raw = np.fromfile(rows_path, dtype=np.int16) if rows_path.exists() else np.zeros(0, np.int16)
+        n = min(len(metas), raw.size // width)          # a crash between the two appends leaves a ragged tail: drop it
+        if n < len(metas) or n * width < raw.size:
+            logger.warning(f"{self._store}: dropping an incomplete tail ({len(metas)} metadata lines, {raw.size // width} rows)")
+        self.dim = int(head["dim"])
+        if n:
+            dev = torch.device(self.device) if self.device is not None else _default_device()
+            rows = torch.from_numpy(raw[:n * width].reshape(n, width).copy()).view(torch.bfloat16).to(dev)
+            self._rows, self._count = rows, n
+            self.ids = [m["id"] for m in metas[:n]]
+            self.texts = [m["text"] for m in metas[:n]]
+            self.metadatas = [m.get("metadata") or {} for m in metas[:n]]
+            self._id_set = set(self.ids)
+        logger.info(f"Loaded dense index with {n} rows from {self._store}")
 
     # -- embeddings --------------------------------------------------------------------------
     def _get_embedding(self, text: str) -> List[float]:
@@ -257,10 +305,13 @@ class DenseIndex:
             self._rows = grown
         self._rows[self._count:self._count + n] = rows
         self._count += n
+        texts = list(texts) if texts is not None else [""] * n
+        metadatas = list(metadatas) if metadatas is not None else [{} for _ in range(n)]
         self.ids.extend(ids)
         self._id_set.update(ids)
-        self.texts.extend(texts if texts is not None else [""] * n)
-        self.metadatas.extend(metadatas if metadatas is not None else [{} for _ in range(n)])
+        self.texts.extend(texts)
+        self.metadatas.extend(metadatas)
+        self._persist(rows, list(ids), texts, metadatas)
         return n
 
     def add_documents(self, documents: List[Document], batch_size: int = 100) -> int:
@@ -306,7 +357,7 @@ class HybridRetriever:
     """BM25 + dense retrieval with both scores per passage (streaming_index.py:376-560)."""
 
     def __init__(self, bm25_persist_path: Optional[str] = "./data/bm25_index.pkl",
-                 chroma_persist_path: str = "./data/chroma_db", chroma_host: Optional[str] = None,
+                 chroma_persist_path: Optional[str] = "./data/chroma_db", chroma_host: Optional[str] = None,
                  embedding_model: str = "nomic-embed-text", embed_fn: Optional[Callable] = None, device=None,
                  mma_variant: int = 3):
         self.bm25_index = BM25Index(persist_path=bm25_persist_path, device=device)
@@ -316,6 +367,12 @@ class HybridRetriever:
                                       mma_variant=mma_variant)
         self.documents: Dict[str, Document] = {}
         self._order: Dict[str, int] = {}
+        # The reference keeps ``self.documents`` in memory only (:422-423): after a restart its persisted indices
+        # still answer bm25_search / dense_search but hybrid_search drops every hit (:494-496) and returns [].
+        # Restoring the document store from the reloaded BM25 pickle is additive.
+        for doc_id in self.bm25_index.doc_ids:
+            self._order[doc_id] = len(self._order)
+            self.documents[doc_id] = self.bm25_index.documents[doc_id]
 
     def add_documents(self, documents: List[Document], batch_size: int = 100) -> Dict[str, int]:
         for doc in documents:
@@ -428,6 +485,15 @@ class StreamingIndex:
         self.checkpoint_path = Path(checkpoint_path)
         self.batch_size = batch_size
         self.progress = self._load_checkpoint()
+        sides = [getattr(retriever, name, None) for name in ("bm25_index", "dense_index")]
+        have = min(len(side) for side in sides) if all(side is not None for side in sides) else None
+        if have is not None and self.progress["total_indexed"] > have:
+            # e.g. the dense store was kept in memory only (persist_directory=None) or deleted: skipping the
+            # checkpointed lines would leave those documents without postings / dense rows for ever (re-adding
+            # is idempotent: documents an index already holds are skipped)
+            logger.error(f"checkpoint {self.checkpoint_path} says {self.progress['total_indexed']} documents are indexed "
+                         f"but the retriever holds {have}: ignoring the checkpoint and re-indexing from the first line")
+            self.progress = {"last_offset": 0, "total_indexed": 0, "files_completed": []}
 
     def _load_checkpoint(self) -> Dict[str, Any]:
         if self.checkpoint_path.exists():

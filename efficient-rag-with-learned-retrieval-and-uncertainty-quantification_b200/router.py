@@ -119,12 +119,23 @@ class RetrievalRouter(nn.Module):
         return gate
 
     def hybrid_rerank(self, bm25_scores: torch.Tensor, dense_scores: torch.Tensor,
-                      top_k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(top-k fused scores, int64 indices), fused = w*dense + (1-w)*bm25 (router.py:179-202)."""
+                      top_k: int = 10, per_query_stats: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(top-k fused scores, int64 indices), fused = w*dense + (1-w)*bm25 (router.py:179-202).
+
+        ``per_query_stats`` (extension, as in ``forward``): without armed running statistics every row is
+        normalised with its own mean / std - the result of calling the reference once per query with [1, P]
+        tensors, which is what its evaluation loop does (experiments/run_evaluation.py:165-184).  The default
+        normalises over the whole call, exactly like the reference does for a [B, P] call.
+        In train mode the reference's ``forward(update_stats=False)`` applies Dropout (router.py:196): so does this.
+        """
         bm25_scores, dense_scores = self._check(bm25_scores, dense_scores)
-        mode = NORM_RUNNING if self.stats_initialized else NORM_BATCH
+        mode = NORM_RUNNING if self.stats_initialized else (NORM_PER_QUERY if per_query_stats else NORM_BATCH)
         w1, b1, w2, b2, stats = self._weights()
-        _, fused = ops.router_forward(bm25_scores, dense_scores, w1, b1, w2, b2, stats, mode)
+        if self.training and self.config.dropout > 0:
+            gate = self.forward(bm25_scores, dense_scores, update_stats=False, per_query_stats=per_query_stats)
+            fused = (gate * dense_scores + (1 - gate) * bm25_scores).contiguous()
+        else:
+            _, fused = ops.router_forward(bm25_scores, dense_scores, w1, b1, w2, b2, stats, mode)
         k = min(top_k, fused.size(-1))
         values, indices = ops.topk_rows(fused, k)
         return torch.return_types.topk((values, indices.to(torch.int64)))
@@ -283,11 +294,15 @@ def torch_dropout_increment(n_elements: int, sm_count: int) -> int:
 
 def _philox_state(device, n_elements: int, n_calls: int = 1) -> Tuple[int, int]:
     """(seed, offset) of torch's CUDA generator, advanced as n_calls dropout launches would."""
-    gen = torch.cuda.default_generators[torch.device(device).index or 0]
+    index = torch.device(device).index
+    gen = torch.cuda.default_generators[torch.cuda.current_device() if index is None else index]
     seed, offset = int(gen.initial_seed()), int(gen.get_offset())
     inc = torch_dropout_increment(n_elements, torch.cuda.get_device_properties(device).multi_processor_count)
     gen.set_offset(offset + inc * n_calls)
-    return seed & ((1 << 63) - 1) if seed >= (1 << 63) else seed, offset
+    # torch.seed() draws 64 random bits: about half of those seeds are >= 2^63.  The op schema carries a signed
+    # int64, so such a seed travels as its two's-complement image and is widened back to the same 64 bits at the
+    # C boundary (ops.router_mc_dropout) - masking it to 63 bits would change the Philox key.
+    return seed - (1 << 64) if seed >= (1 << 63) else seed, offset
 
 
 __all__ = ["RouterConfig", "RetrievalRouter", "ConfidenceResult", "RouterUncertainty"]

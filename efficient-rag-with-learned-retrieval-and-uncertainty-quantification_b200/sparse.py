@@ -56,6 +56,7 @@ class SparseShard:
     dense_imp: Optional[Tensor] = None     # float16 [n_dense, stride]: upper bounds of tf / (tf + norm)
     dense_maximp: Optional[Tensor] = None  # float32 [n_dense]: their row maxima
     use_dense_table: bool = True
+    df_global: Optional[Tensor] = None     # document frequencies summed over all shards (set by finalize)
 
     @property
     def nnz(self) -> int:
@@ -65,6 +66,7 @@ class SparseShard:
                  total_len: Optional[int] = None, group=None) -> "SparseShard":
         """(Re)compute idf[V] and norm[N] from GLOBAL statistics (defaults: this shard alone)."""
         df_global = self.df if df_global is None else df_global
+        self.df_global = df_global           # what idf was computed from (bench --verify compares it with its own count)
         self.corpus_size = self.n_docs if corpus_size is None else int(corpus_size)
         total = int(self.doc_len.sum()) if total_len is None else int(total_len)
         self.avgdl = total / self.corpus_size

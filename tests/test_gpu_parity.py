@@ -31,6 +31,32 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(scope="module")
+def retrieval_gold(golden_dir):
+    with open(golden_dir / "retrieval_golden.json") as fh:
+        return json.load(fh)
+
+
+def assert_ranking_matches(got_ids, got_scores, want_ids, want_scores, all_scores=None, rtol=1e-5, atol=1e-7):
+    """"Top-k ids identical modulo ties", made precise: same length, scores equal position by position within the
+    tolerance, and every returned id is one the oracle ranks at that position OR a (near-)tie of it - i.e. its
+    oracle score is within the tolerance of the oracle score at that position.  ``all_scores`` (the oracle's full
+    score vector indexed by id, or a dict id -> score) lets a near-tie ACROSS the cut be recognised; without it
+    only the oracle's own top-k can stand in."""
+    assert len(got_ids) == len(want_ids), (got_ids, want_ids)
+    np.testing.assert_allclose(got_scores, want_scores, rtol=rtol, atol=atol)
+    assert len(set(got_ids)) == len(got_ids), "an id was returned twice"
+    lookup = dict(zip(want_ids, want_scores))
+    for j, (gi, ws) in enumerate(zip(got_ids, want_scores)):
+        if gi == want_ids[j]:
+            continue
+        truth = lookup.get(gi)
+        if truth is None and all_scores is not None:
+            truth = all_scores[gi] if not isinstance(all_scores, dict) else all_scores.get(gi)
+        assert truth is not None, f"rank {j}: id {gi} is not among the oracle's candidates {want_ids}"
+        assert abs(truth - ws) <= rtol * abs(ws) + atol, f"rank {j}: id {gi} (oracle score {truth}) is no tie of {want_ids[j]} ({ws})"
+
+
 # ------------------------------------------------------------------------------------------
 # selection
 # ------------------------------------------------------------------------------------------
@@ -279,8 +305,9 @@ def test_bm25_edge_queries(rq, dev):
         want_full = ref.get_scores(queries[q])
         np.testing.assert_allclose(full[q], want_full, rtol=1e-5, atol=1e-9)
         want = bm25_okapi.index_search(want_full, 20)
-        assert [int(i) for i in ids[q] if i >= 0] == [w[0] for w in want] or True
-        np.testing.assert_allclose([float(s) for s, i in zip(score[q], ids[q]) if i >= 0], [w[1] for w in want], rtol=1e-5)
+        got_ids = [int(i) for i in ids[q] if i >= 0]
+        got_scores = [float(s) for s, i in zip(score[q], ids[q]) if i >= 0]
+        assert_ranking_matches(got_ids, got_scores, [w[0] for w in want], [w[1] for w in want], want_full, 1e-5)
 
 
 def test_bm25_shards_with_global_statistics_equal_unsharded(rq, dev):
@@ -431,19 +458,29 @@ def test_hybrid_engine_end_to_end_c1(rq, dev, n_q, k, pool):
         de = dense_fusion.topk_desc(dense[q:q + 1], pool)[0]
         want = dense_fusion.hybrid_search(bm, de, k)
         got = [int(i) for i in ids[q] if i >= 0]
-        np.testing.assert_allclose(sh[q, :len(want)], [w[3] for w in want], rtol=2e-5, atol=1e-6)
         exact += got == [w[0] for w in want]
-        assert set(got) == set(w[0] for w in want) or abs(want[-1][3] - sh[q, len(want) - 1]) < 1e-5
-    assert exact >= n_q - max(1, n_q // 20)   # a pool-boundary (near-)tie may flip at most very rarely
+        # every deviation must be a near-tie in the ORACLE's own hybrid scores (pool-boundary and rank ties only)
+        everything = {w[0]: w[3] for w in dense_fusion.hybrid_search(
+            bm25_okapi.index_search(okapi.get_scores(terms[q]), pool + 3), dense_fusion.topk_desc(dense[q:q + 1], pool + 3)[0], 4 * pool)}
+        assert_ranking_matches(got, sh[q, :len(got)].tolist(), [w[0] for w in want], [w[3] for w in want], everything, 2e-5, 1e-6)
+    assert exact >= n_q - max(1, n_q // 20)   # and they are rare
     # router-in-the-loop + confidence (run_evaluation.py:165-196) on the same batch
     torch.manual_seed(7)
     router = rq.RetrievalRouter().to(dev).eval()
     with torch.no_grad():
         res = engine.retrieve_and_rerank(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, pool, mc_samples=10, seed=5)
     state = {key: v.detach().cpu() for key, v in router.state_dict().items()}
-    ov, oi = router_oracle.hybrid_rerank(torch.tensor(sb), torch.tensor(sd), state, False, k)
+    # the reference loop (run_evaluation.py:165-184) calls the router once per query with [1, k] tensors: statistics of
+    # THAT query only (stats_initialized is False right after load_state_dict), never of its batch mates
+    per_query = [router_oracle.hybrid_rerank(torch.tensor(sb[q:q + 1]), torch.tensor(sd[q:q + 1]), state, False, k) for q in range(n_q)]
+    ov, oi = torch.cat([p[0] for p in per_query]), torch.cat([p[1] for p in per_query])
     torch.testing.assert_close(res["fused"].cpu(), ov, rtol=1e-5, atol=1e-5)
     assert np.array_equal(res["ids"].cpu().numpy(), np.take_along_axis(ids, oi.numpy(), axis=1))
+    if n_q > 1:   # ... and it differs from normalising over the whole [B, k] call, which hybrid_rerank does by default
+        bv, bi_ = router_oracle.hybrid_rerank(torch.tensor(sb), torch.tensor(sd), state, False, k)
+        dv, di_ = router.hybrid_rerank(torch.tensor(sb, device=dev), torch.tensor(sd, device=dev), top_k=k)
+        torch.testing.assert_close(dv.cpu(), bv, rtol=1e-5, atol=1e-5)
+        assert not torch.allclose(bv, ov)
     for q in range(n_q):
         valid = [float(v) for v, i in zip(res["fused"][q], res["ids"][q]) if i >= 0]
         assert float(res["retrieval_uncertainty"][q]) == pytest.approx(dense_fusion.retrieval_uncertainty(valid, 1.0), rel=1e-4, abs=1e-5)
@@ -526,6 +563,63 @@ def test_full_fusion_fused_epilogue(rq, dev, n, n_q, k, hidden, scale):
         want_s, want_i = router_oracle.hybrid_rerank(bm, de, state, True, k)
         torch.testing.assert_close(fs.cpu(), want_s, rtol=3 * tol, atol=3 * tol)
         assert (fi.cpu().long() - 1000 == want_i).float().mean() > 0.98
+
+
+@pytest.mark.parametrize("hidden,scale,dense_std", [(64, 1.0, 0.3), (32, 6.0, 0.05), (16, 20.0, 0.02), (128, 3.0, 0.1)])
+def test_full_fusion_bound_as_the_kernel_indexes_it(rq, dev, hidden, scale, dense_std):
+    """The gate-bound lookup EXACTLY as the fused epilogue evaluates it (FusedBound in csrc/dense_mma.cu, called
+    through the debug entry point) on 600k (bm25, dense) pairs spanning every cell, with steep gates and a small
+    dense_std: the bound never undercuts the fused score, the cell it reads is the floor cell (or a neighbour only
+    for points within 1e-4 cells of a grid line), cosines close to +-d_hi do not wrap to the other end of the table."""
+    import ctypes as C
+    from rag_uq_b200 import _lib
+    from rag_uq_b200.router import full_fusion_bounds
+    fn = _lib.lib.ragb_debug_fused_bound
+    fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
+                                        C.c_float, C.c_void_p, C.c_void_p]
+    torch.manual_seed(hidden)
+    lin1, lin2 = torch.nn.Linear(3, hidden), torch.nn.Linear(hidden, 1)
+    w1, b1 = (lin1.weight.detach() * scale).numpy(), (lin1.bias.detach() * scale).numpy()
+    w2, b2 = (lin2.weight.detach() * scale).reshape(-1).numpy(), lin2.bias.detach().numpy()
+    stats = np.array([8.0, 6.0, 0.2, dense_std], dtype=np.float32)
+    b_cap, d_hi, n_b, n_d = 32.0, 1.015625, 128, 64
+    table = full_fusion_bounds(w1, b1, w2, b2, stats, b_cap, d_hi, n_b, n_d)
+    lo = (table.view(np.uint32) << 16).view(np.float32)
+    hi = (table.view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)
+    rng = np.random.default_rng(hidden)
+    n = 600_000
+    b = rng.uniform(0.0, b_cap * 1.05, n).astype(np.float32)
+    d = rng.uniform(-d_hi, d_hi, n).astype(np.float32)
+    b[:2000] = 0.0                                                    # documents without any query term
+    d[2000:4000] = np.float32(d_hi) * rng.choice([-1.0, 1.0], 2000).astype(np.float32)     # the edges of the table
+    d[4000:6000] = rng.uniform(0.98, 1.0, 2000).astype(np.float32)    # cos close to 1 must stay in the top cells
+    tb, td = torch.tensor(b, device=dev), torch.tensor(d, device=dev)
+    ttab = torch.tensor(table, device=dev)
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    _lib.check(fn(tb.data_ptr(), td.data_ptr(), n, ttab.data_ptr(), n_b, n_d, b_cap, d_hi, out.data_ptr(),
+                  torch.cuda.current_stream().cuda_stream))
+    got = out.cpu().numpy()
+    bt, dt = torch.tensor(b), torch.tensor(d)
+    bn = (bt - stats[0]) / (torch.tensor(stats[1]) + 1e-6)
+    dn = (dt - stats[2]) / (torch.tensor(stats[3]) + 1e-6)
+    feats = torch.stack([bn, dn, dn - bn], -1)
+    gate = torch.sigmoid(torch.relu(feats @ torch.tensor(w1).T + torch.tensor(b1)) @ torch.tensor(w2) + torch.tensor(b2))
+    fused = (gate * dt + (1 - gate) * bt).numpy()
+    assert (got >= fused - 1e-5 * np.abs(fused) - 1e-6).all(), "the kernel's bound undercuts a fused score"
+    # which cell did the kernel read?  Recompute the bound for the floor cell and its neighbours in float64.
+    xb, xd = b.astype(np.float64) * (n_b / b_cap), (d.astype(np.float64) + d_hi) * (n_d / (2 * d_hi))
+    fb = np.floor(xb).astype(np.int64)
+    fb = np.where((fb < 0) | (fb > n_b - 1) | (xb < 0.25), n_b - 1, fb)       # documented: tiny / huge bm25 -> last row (0, 1)
+    fd = np.clip(np.floor(xd).astype(np.int64), 0, n_d - 1)
+
+    def bound_at(ib, idx):
+        g = np.where(d <= b, lo[ib, idx], hi[ib, idx]).astype(np.float32)
+        return (g * (d - b) + b).astype(np.float32)
+
+    same = np.isclose(got, bound_at(fb, fd), rtol=1e-6, atol=1e-6)
+    near_line = (np.abs(xd - np.round(xd)) < 1e-4) | (np.abs(xb - np.round(xb)) < 1e-4) | (np.abs(xb - 0.25) < 1e-3)
+    assert (same | near_line).all(), f"{int((~(same | near_line)).sum())} pairs read a cell that is not their floor cell"
+    assert same.mean() > 0.999
 
 
 @pytest.mark.parametrize("seed", list(range(6)))
@@ -774,6 +868,96 @@ def test_mc_dropout_torch_cuda_bit_exact(rq, dev):
 # ------------------------------------------------------------------------------------------
 # drop-in string API
 # ------------------------------------------------------------------------------------------
+def _pool_tensors(pool_rows, number, width, dev):
+    score = torch.zeros((1, width), dtype=torch.float32)
+    ident = torch.full((1, width), -1, dtype=torch.int32)
+    for j, (doc_id, sc) in enumerate(pool_rows[:width]):
+        score[0, j], ident[0, j] = sc, number(doc_id)
+    return score.to(dev), ident.to(dev)
+
+
+def test_hybrid_fuse_kernel_vs_live_reference_golden(rq, dev, retrieval_gold):
+    """ragb_hybrid_fuse_topk against what the reference's own HybridRetriever.hybrid_search returned
+    (streaming_index.py:464-523, run live with stubbed pools by tests/golden/make_retrieval_golden.py)."""
+    hy = retrieval_gold["hybrid"]
+    known = {d: i for i, d in enumerate(hy["document_ids"])}
+    for case in hy["cases"]:
+        pool = case["retrieval_pool_size"]
+        width = max(pool, 1)
+        # ids the retriever holds no document for never reach the fusion (:494-496): id -1 / score 0 = "no entry"
+        bs, bi = _pool_tensors([r for r in case["bm25_pool"][:pool] if r[0] in known], known.get, width, dev)
+        ds, di = _pool_tensors([r for r in case["dense_pool"][:pool] if r[0] in known], known.get, width, dev)
+        k = min(case["top_k"], 2 * width)
+        ids, ob, od, oh = (t[0].cpu().tolist() for t in rq.ops.hybrid_fuse_topk(bs, bi, ds, di, k))
+        want = case["hybrid_search"]
+        n = len(want)
+        assert [i for i in ids if i >= 0] == ids[:n] and all(i == -1 for i in ids[n:]), case["name"]
+        assert_ranking_matches(ids[:n], oh[:n], [known[w[0]] for w in want], [w[3] for w in want], None, 2e-6, 1e-7)
+        by_id = {known[w[0]]: w for w in want}
+        for i, b, d in zip(ids[:n], ob[:n], od[:n]):
+            assert b == np.float32(by_id[i][1]) and d == np.float32(by_id[i][2]), case["name"]   # scores pass through untouched
+
+
+def test_hybrid_retriever_dropin_vs_live_reference_golden(rq, dev, retrieval_gold):
+    """The drop-in HybridRetriever.hybrid_search / get_scores_for_router (host join on document ids + fusion kernel)
+    fed the SAME pools the live reference was fed: same documents, scores, order (modulo ties), texts, titles, padding."""
+    hy = retrieval_gold["hybrid"]
+    names = hy["document_ids"]
+    for case in hy["cases"]:
+        r = rq.HybridRetriever(bm25_persist_path=None, chroma_persist_path=None)
+        for i, d in enumerate(names):
+            r.documents[d] = rq.Document(id=d, text=f"text of {d}", title=f"title {d}")
+            r._order[d] = i
+        # the two indices number their rows independently and may hold ids the retriever has no document for
+        b_rows = names + sorted({x[0] for x in case["bm25_pool"]} - set(names))
+        d_rows = list(reversed(names)) + sorted({x[0] for x in case["dense_pool"]} - set(names))
+        r.bm25_index.doc_ids, r.dense_index.ids = b_rows, d_rows
+
+        def stub(queries, query_embeddings=None, top_k=10, retrieval_pool_size=50, case=case, b_rows=b_rows, d_rows=d_rows):
+            w = max(retrieval_pool_size, 1)
+            bm = _pool_tensors(case["bm25_pool"], b_rows.index, w, dev) if case["bm25_pool"] else None
+            de = _pool_tensors(case["dense_pool"], d_rows.index, w, dev) if case["dense_pool"] else None
+            return 1, bm, de
+
+        r.hybrid_search_batch = stub
+        got = r.hybrid_search("ignored", top_k=case["top_k"], retrieval_pool_size=case["retrieval_pool_size"])
+        want = case["hybrid_search"]
+        assert_ranking_matches([g.doc_id for g in got], [g.hybrid_score for g in got], [w[0] for w in want],
+                               [w[3] for w in want], None, 2e-6, 1e-7)
+        by_id = {w[0]: w for w in want}
+        for g in got:
+            w = by_id[g.doc_id]
+            assert (g.bm25_score, g.dense_score, g.text, g.title) == (float(np.float32(w[1])), float(np.float32(w[2])), w[4], w[5])
+        ref = case["scores_for_router"]
+        bsc, dsc, ids, txt = r.get_scores_for_router("ignored", num_passages=case["num_passages"])
+        n_real = sum(1 for i in ref["ids"] if i)
+        assert len(ids) == len(ref["ids"]) and ids[n_real:] == [""] * (len(ids) - n_real) and txt[n_real:] == ref["texts"][n_real:]
+        assert bsc[n_real:] == [0.0] * (len(ids) - n_real) and dsc[n_real:] == [0.0] * (len(ids) - n_real)
+        assert sorted(ids[:n_real]) == sorted(ref["ids"][:n_real]), case["name"]
+        ref_rows = {i: (b, d, t) for i, b, d, t in zip(ref["ids"], ref["bm25"], ref["dense"], ref["texts"])}
+        for i, b, d, t in zip(ids[:n_real], bsc, dsc, txt):
+            assert (b, d, t) == (float(np.float32(ref_rows[i][0])), float(np.float32(ref_rows[i][1])), ref_rows[i][2])
+
+
+def test_bm25_index_search_vs_live_reference_golden(rq, dev, retrieval_gold):
+    """The drop-in BM25Index.search (host tokeniser + vocabulary + CSR segments + bm25_kernel) against the live
+    reference's BM25Index.search (streaming_index.py:150-179) on the same texts: same documents in the same order
+    (modulo ties), scores within 1e-5 relative, nothing with score <= 0, top_k > N."""
+    for corpus in retrieval_gold["bm25_index_search"]:
+        index = rq.BM25Index(k1=corpus["k1"], b=corpus["b"])
+        docs = [rq.Document(id=d, text=t) for d, t in zip(corpus["doc_ids"], corpus["texts"])]
+        half = len(docs) // 2 + 1
+        assert index.add_documents(docs[:half]) == half and index.add_documents(docs) == len(docs) - half
+        lit = bm25_okapi.OkapiLiteral([bm25_okapi.tokenize(t) for t in corpus["texts"]], k1=corpus["k1"], b=corpus["b"])
+        for case in corpus["cases"]:
+            got = index.search(case["query"], case["top_k"])
+            want = case["result"]
+            full = dict(zip(corpus["doc_ids"], lit.get_scores(bm25_okapi.tokenize(case["query"])).tolist()))
+            assert_ranking_matches([g[0] for g in got], [g[1] for g in got], [w[0] for w in want], [w[1] for w in want],
+                                   full, 1e-5, 1e-9)
+            assert all(s > 0 for _, s in got)
+
+
 def test_hybrid_retriever_dropin(rq, dev, tmp_path):
     rng = np.random.default_rng(0)
     words = [f"w{i}" for i in range(200)]
@@ -783,7 +967,8 @@ def test_hybrid_retriever_dropin(rq, dev, tmp_path):
     def embed(batch):
         return np.stack([table.get(t, np.ones(96, np.float32)) for t in batch])
 
-    r = rq.HybridRetriever(bm25_persist_path=str(tmp_path / "bm25.pkl"), embed_fn=embed)
+    r = rq.HybridRetriever(bm25_persist_path=str(tmp_path / "bm25.pkl"), chroma_persist_path=str(tmp_path / "dense"),
+                           embed_fn=embed)
     docs = [rq.Document(id=f"doc{i}", text=t, title=f"T{i}") for i, t in enumerate(texts)]
     stats = r.add_documents(docs[:200])
     assert stats == {"bm25_added": 200, "dense_added": 200, "total_documents": 200}
@@ -805,14 +990,41 @@ def test_hybrid_retriever_dropin(rq, dev, tmp_path):
             assert g_.hybrid_score == pytest.approx(w[3], rel=2e-5, abs=1e-6)
             assert g_.text == texts[w[0]] and g_.title == f"T{w[0]}"
         assert [d for d, _ in r.bm25_search(query, 20)] == [f"doc{i}" for i, _ in bm[:20]]
-        bsc, dsc, ids, txt = r.get_scores_for_router(query, num_passages=20)
-        assert len(bsc) == len(dsc) == len(ids) == len(txt) == 20
+        for num in (20, 7, 120):
+            bsc, dsc, ids, txt = r.get_scores_for_router(query, num_passages=num)
+            ob, od, oi = dense_fusion.scores_for_router(bm, de, num)          # pools of 50, as :537 implies
+            assert len(bsc) == len(dsc) == len(ids) == len(txt) == num
+            assert ids == [f"doc{i}" if i >= 0 else "" for i in oi]
+            assert txt == [texts[i] if i >= 0 else "" for i in oi]
+            np.testing.assert_allclose(bsc, ob, rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(dsc, od, rtol=0, atol=3e-6)
     # persistence uses the reference's pickle schema and reloads
     again = rq.BM25Index(persist_path=str(tmp_path / "bm25.pkl"))
     assert len(again) == 300 and again.search(texts[17], 5) == r.bm25_index.search(texts[17], 5)
     import pickle
     with open(tmp_path / "bm25.pkl", "rb") as fh:
         assert set(pickle.load(fh)) == {"documents", "doc_ids", "tokenized_corpus", "k1", "b"}
+    # a restarted process gets BOTH sides back (the dense rows are persisted next to the BM25 pickle) and answers
+    # exactly as before; a StreamingIndex checkpoint taken then may be resumed without losing dense rows
+    before = r.hybrid_search(texts[17], top_k=10)
+    r2 = rq.HybridRetriever(bm25_persist_path=str(tmp_path / "bm25.pkl"), chroma_persist_path=str(tmp_path / "dense"),
+                            embed_fn=embed)
+    assert len(r2) == 300 and len(r2.dense_index) == 300 and len(r2.bm25_index) == 300
+    assert torch.equal(r2.dense_index.matrix.view(torch.int16), r.dense_index.matrix.view(torch.int16))
+    assert r2.dense_index.ids == r.dense_index.ids and r2.dense_index.texts == r.dense_index.texts
+    after = r2.hybrid_search(texts[17], top_k=10)
+    assert [(a.doc_id, a.bm25_score, a.dense_score, a.hybrid_score, a.text) for a in after] == \
+        [(b.doc_id, b.bm25_score, b.dense_score, b.hybrid_score, b.text) for b in before]
+    assert r2.add_documents(docs[:50]) == {"bm25_added": 0, "dense_added": 0, "total_documents": 300}
+    # without a dense store the resume guard refuses to skip the checkpointed lines
+    corpus = tmp_path / "c.jsonl"
+    corpus.write_text("".join(json.dumps({"id": f"s{i}", "text": texts[i]}) + "\n" for i in range(6)))
+    r3 = rq.HybridRetriever(bm25_persist_path=str(tmp_path / "b3.pkl"), chroma_persist_path=None, embed_fn=embed)
+    assert list(rq.StreamingIndex(r3, str(tmp_path / "ck3.json"), batch_size=4).stream_from_jsonl(str(corpus))) == [4, 2]
+    r4 = rq.HybridRetriever(bm25_persist_path=str(tmp_path / "b3.pkl"), chroma_persist_path=None, embed_fn=embed)
+    resumed = rq.StreamingIndex(r4, str(tmp_path / "ck3.json"), batch_size=4)
+    assert resumed.progress["last_offset"] == 0                         # checkpoint ignored: dense rows were not persisted
+    assert list(resumed.stream_from_jsonl(str(corpus))) == [4, 2] and len(r4.dense_index) == 6 and len(r4.bm25_index) == 6
 
 
 def test_incremental_ingest_equals_full_rebuild(rq, dev):
@@ -938,7 +1150,7 @@ def test_error_behaviour(rq, dev):
                                torch.zeros(9, 64, device=dev, dtype=torch.bfloat16), 1, 0)  # batch > 8
     with pytest.raises(NotImplementedError):
         rq.ops.topk_rows(torch.zeros(2, 10), 1)                              # CPU tensor
-    assert rq.DenseIndex().search("q") == [] and rq.BM25Index().search("q") == []
+    assert rq.DenseIndex(persist_directory=None).search("q") == [] and rq.BM25Index().search("q") == []
     before = rq.ops.launch_count()
     rq.ops.topk_rows(torch.randn(2, 100, device=dev), 5)
     assert rq.ops.launch_count() > before

@@ -115,6 +115,49 @@ def test_synth_is_deterministic_and_shardable(rq):
         assert all(t in doc or t >= cdf.shape[0] for t in q1.q_terms[8 * i:8 * i + 8].tolist())
 
 
+def test_large_check_streams_the_same_oracle(rq):
+    """oracle.large_check (what `bench.py --verify` and the 1M GPU test use on corpora too large for the CSR oracle)
+    == OkapiCsr + exact dense + oracle fusion + oracle rerank on a corpus small enough for both."""
+    from oracle import bm25_okapi, dense_fusion, large_check, router as router_oracle
+    from rag_uq_b200 import synth
+    n, dim, n_q, pool, k = 3000, 64, 6, 50, 10
+    vocab = synth.vocab_size(n)
+    cdf = synth.zipf_cdf(vocab, "cpu")
+    qb = synth.make_queries(n_q, n, dim, cdf, "cpu")
+    terms = qb.q_terms.view(n_q, -1).tolist()
+    terms[2] = terms[2][:3] + terms[2][:3]            # duplicates count per occurrence
+    torch.manual_seed(7)
+    lin1, lin2 = torch.nn.Linear(3, 64), torch.nn.Linear(64, 1)
+    state = {"scorer.0.weight": lin1.weight.detach(), "scorer.0.bias": lin1.bias.detach(), "scorer.3.weight": lin2.weight.detach(),
+             "scorer.3.bias": lin2.bias.detach(), "bm25_mean": torch.tensor(8.0), "bm25_std": torch.tensor(6.0),
+             "dense_mean": torch.tensor(0.2), "dense_std": torch.tensor(0.3)}
+    recs, info = large_check.run_synthetic_check(synth, "cpu", n, dim, terms, qb.q_emb, pool, k, state, True, chunk_docs=700)
+    off, tok = synth.doc_tokens(0, n, cdf)
+    okapi = bm25_okapi.OkapiCsr(off.numpy(), tok.numpy(), vocab)
+    assert info["average_idf"] == pytest.approx(okapi.average_idf, rel=1e-13) and info["avgdl"] == okapi.avgdl
+    emb = synth.passage_embeddings(0, n, dim, "cpu").float().numpy()
+    dense = dense_fusion.dense_scores(emb, qb.q_emb.float().numpy())
+    for q in range(n_q):
+        bm = bm25_okapi.index_search(okapi.get_scores(terms[q]), pool)
+        de = dense_fusion.topk_desc(dense[q:q + 1], pool)[0]
+        assert [i for i, _ in recs[q]["bm25_pool"]] == [i for i, _ in bm]
+        np.testing.assert_allclose([s for _, s in recs[q]["bm25_pool"]], [s for _, s in bm], rtol=1e-13)
+        assert [i for i, _ in recs[q]["dense_pool"]] == [i for i, _ in de]
+        want = dense_fusion.hybrid_search(bm, de, k)
+        assert [r[0] for r in recs[q]["fused"]] == [r[0] for r in want]
+        sb, sd, ids = dense_fusion.scores_for_router(bm, de, k)
+        vals, order = router_oracle.hybrid_rerank(torch.tensor([sb]), torch.tensor([sd]), state, True, k)
+        assert recs[q]["rerank_ids"] == [ids[j] for j in order[0].tolist()]
+    # top_desc: ties in index order, positivity filter, gap report
+    idx, val, gap = large_check.top_desc(np.array([0.0, 2.0, 2.0, -1.0, 3.0, 0.0]), 3)
+    assert idx.tolist() == [4, 1, 2] and gap == 1.0
+    idx, _, _ = large_check.top_desc(np.array([0.0, 2.0, 2.0, -1.0, 3.0, 0.0]), 5, positive_only=True)
+    assert idx.tolist() == [4, 1, 2]
+    exact, explained = large_check.compare_ranking([4, 2, 1], [3.0, 2.0, 2.0], [4, 1, 2], [3.0, 2.0, 2.0], {4: 3.0, 1: 2.0, 2: 2.0}, 1e-6, 0)
+    assert (exact, explained) == (False, True)
+    assert large_check.compare_ranking([4, 0], [3.0, 2.0], [4, 1], [3.0, 2.0], {4: 3.0, 1: 2.0, 0: 0.0}, 1e-6, 0) == (False, False)
+
+
 def test_shard_rows_partition():
     import rag_uq_b200 as rq
     for n, world in [(10, 3), (10_000_000, 8), (7, 8), (1, 1)]:
