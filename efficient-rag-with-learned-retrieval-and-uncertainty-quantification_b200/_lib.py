@@ -50,6 +50,9 @@ SIGNATURES = {
     "ragb_bm25_idf_scratch_bytes": (_sz, [_i64]),
     "ragb_bm25_build_idf": (C.c_int, [_p, _i64, _i64, _f64, _p, _p, _sz, _p]),
     "ragb_bm25_build_norm": (C.c_int, [_p, _i64, _f64, _f64, _f64, _p, _p]),
+    "ragb_bm25_term_max_tf": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
+    "ragb_bm25_build_dense_table": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _p, _i64, _p]),
+    "ragb_bm25_build_impact_bounds": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p]),
     "ragb_bm25_topk_workspace_bytes": (_sz, [_i32, _i64, _i32]),
     "ragb_bm25_score_topk": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _p, _p, _i32, _i32,
                                        _i64, _i64, _i32, _p, _p, _p, _sz, _p]),

@@ -995,6 +995,69 @@ __global__ void norm_kernel(const int32_t* __restrict__ doc_len, int64_t n_docs,
   if (i < n_docs) norm_out[i] = static_cast<float>(k1 * (1.0 - b + b * static_cast<double>(doc_len[i]) / avgdl));
 }
 
+// ---------------------------------------------------------------------------------------
+// Builders of the dense tf table and its fp16 impact bounds (used by SparseShard.finalize).
+// ---------------------------------------------------------------------------------------
+constexpr int TB_THREADS = 256;
+constexpr int TB_SPLIT = 64;   // blocks per term: grid = (TB_SPLIT, n_terms)
+
+// max_tf[i] = largest term frequency in the posting list of terms[i] (0 for an empty list); max_tf is zeroed by the caller
+__global__ void __launch_bounds__(TB_THREADS) term_max_tf_kernel(const int64_t* __restrict__ term_off,
+                                                                 const uint16_t* __restrict__ post_tf,
+                                                                 const int32_t* __restrict__ terms, int32_t* __restrict__ max_tf) {
+  const int t = terms[blockIdx.y];
+  const int64_t lo = term_off[t], hi = term_off[t + 1];
+  int best = 0;
+  for (int64_t i = lo + static_cast<int64_t>(blockIdx.x) * TB_THREADS + threadIdx.x; i < hi; i += static_cast<int64_t>(TB_SPLIT) * TB_THREADS)
+    best = max(best, static_cast<int>(__ldg(post_tf + i)));
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, sh));
+  if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(max_tf + blockIdx.y, best);
+}
+
+// table[i][doc] = tf for every posting of terms[i]; the table was zeroed by the caller (0 = term absent)
+__global__ void __launch_bounds__(TB_THREADS) dense_table_fill_kernel(const int64_t* __restrict__ term_off,
+                                                                      const int32_t* __restrict__ post_doc,
+                                                                      const uint16_t* __restrict__ post_tf,
+                                                                      const int32_t* __restrict__ terms, uint8_t* __restrict__ table,
+                                                                      int64_t stride) {
+  const int t = terms[blockIdx.y];
+  const int64_t lo = term_off[t], hi = term_off[t + 1];
+  uint8_t* row = table + static_cast<int64_t>(blockIdx.y) * stride;
+  for (int64_t i = lo + static_cast<int64_t>(blockIdx.x) * TB_THREADS + threadIdx.x; i < hi; i += static_cast<int64_t>(TB_SPLIT) * TB_THREADS)
+    row[__ldg(post_doc + i)] = static_cast<uint8_t>(__ldg(post_tf + i));
+}
+
+// imp[r][d] = smallest fp16 >= tf / (tf + norm[d]) * (1 + 2e-6)  (the scoring kernels multiply by an approximate
+// reciprocal: the factor keeps the bound above what they compute); max_imp[r] = row maximum (zeroed by the caller;
+// non-negative floats order like their bit patterns, so one atomicMax on the bits per block suffices).
+__global__ void __launch_bounds__(TB_THREADS) impact_bounds_kernel(const uint8_t* __restrict__ table, const float* __restrict__ norm,
+                                                                   int64_t n_docs, int64_t stride, __half* __restrict__ imp,
+                                                                   float* __restrict__ max_imp) {
+  const int r = blockIdx.y;
+  const uint8_t* row = table + static_cast<int64_t>(r) * stride;
+  __half* out = imp + static_cast<int64_t>(r) * stride;
+  float best = 0.0f;
+  // 8 documents per thread per step: one 64-bit load of tf bytes, one 128-bit store of fp16 bounds (stride % 256 == 0)
+  for (int64_t d0 = (static_cast<int64_t>(blockIdx.x) * TB_THREADS + threadIdx.x) * 8; d0 < stride;
+       d0 += static_cast<int64_t>(gridDim.x) * TB_THREADS * 8) {
+    const uint2 bytes = __ldg(reinterpret_cast<const uint2*>(row + d0));
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f = static_cast<float>(((j < 4 ? bytes.x : bytes.y) >> (8 * (j & 3))) & 0xffu);
+      const float nrm = (d0 + j) < n_docs ? __ldg(norm + d0 + j) : 1.0f;
+      const float exact = __fmul_rn(__fdiv_rn(f, __fadd_rn(f, nrm)), 1.000002f);
+      h[j] = __float2half_ru(exact);
+      best = fmaxf(best, __half2float(h[j]));
+    }
+    *reinterpret_cast<uint4*>(out + d0) = *reinterpret_cast<const uint4*>(h);
+  }
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, sh));
+  if ((threadIdx.x & 31) == 0 && best > 0.0f) atomicMax(reinterpret_cast<unsigned*>(max_imp + r), __float_as_uint(best));
+}
+
 static int bm25_stripes(int n_queries, int64_t n_docs, int64_t* stripe_docs_out) {
   const int64_t unit = static_cast<int64_t>(BM_WARPS) * BM_SUPER_DOCS;
   static const int64_t per_sm = [] {
@@ -1087,6 +1150,55 @@ int ragb_bm25_build_norm(const int32_t* doc_len, int64_t n_docs, double avgdl, d
   RAGB_REQUIRE(doc_len && norm_out, RAGB_EINVAL, "ragb_bm25_build_norm: null pointer");
   RAGB_REQUIRE(n_docs > 0 && avgdl > 0.0, RAGB_EINVAL, "ragb_bm25_build_norm: empty shape");
   norm_kernel<<<static_cast<unsigned>(ceil_div64(n_docs, 256)), 256, 0, stream>>>(doc_len, n_docs, avgdl, k1, b, norm_out);
+  RAGB_AFTER_LAUNCH(1);
+  return RAGB_OK;
+}
+
+int ragb_bm25_term_max_tf(const int64_t* term_off, const uint16_t* post_tf, const int32_t* terms, int32_t n_terms,
+                          int32_t* max_tf_out, ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(term_off && post_tf && terms && max_tf_out, RAGB_EINVAL, "ragb_bm25_term_max_tf: null pointer");
+  RAGB_REQUIRE(n_terms > 0 && n_terms <= 65535, RAGB_ELIMIT, "ragb_bm25_term_max_tf: n_terms=%d outside [1,65535]", n_terms);
+  RAGB_CUDA(cudaMemsetAsync(max_tf_out, 0, sizeof(int32_t) * n_terms, stream));
+  term_max_tf_kernel<<<dim3(TB_SPLIT, n_terms), TB_THREADS, 0, stream>>>(term_off, post_tf, terms, max_tf_out);
+  RAGB_AFTER_LAUNCH(1);
+  return RAGB_OK;
+}
+
+int ragb_bm25_build_dense_table(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf,
+                                const int32_t* terms, int32_t n_terms, int64_t n_docs, uint8_t* table_out, int64_t stride,
+                                ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(term_off && post_doc && post_tf && terms && table_out, RAGB_EINVAL, "ragb_bm25_build_dense_table: null pointer");
+  RAGB_REQUIRE(n_terms > 0 && n_terms <= BM_MAX_DENSE, RAGB_ELIMIT, "ragb_bm25_build_dense_table: n_terms=%d outside [1,%d]",
+               n_terms, BM_MAX_DENSE);
+  RAGB_REQUIRE(stride >= n_docs && stride % BM_RANGE == 0, RAGB_EINVAL,
+               "ragb_bm25_build_dense_table: stride must be a multiple of %d covering n_docs", BM_RANGE);
+  RAGB_CUDA(cudaMemsetAsync(table_out, 0, static_cast<size_t>(n_terms) * stride, stream));
+  dense_table_fill_kernel<<<dim3(TB_SPLIT, n_terms), TB_THREADS, 0, stream>>>(term_off, post_doc, post_tf, terms, table_out, stride);
+  RAGB_AFTER_LAUNCH(1);
+  return RAGB_OK;
+}
+
+int ragb_bm25_build_impact_bounds(const uint8_t* dense_tf, int64_t dense_stride, int32_t n_dense, const float* norm,
+                                  int64_t n_docs, uint16_t* dense_imp_fp16_out, float* dense_max_imp_out,
+                                  ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(dense_tf && norm && dense_imp_fp16_out && dense_max_imp_out, RAGB_EINVAL, "ragb_bm25_build_impact_bounds: null pointer");
+  RAGB_REQUIRE(n_dense > 0 && n_dense <= BM_MAX_DENSE, RAGB_ELIMIT, "ragb_bm25_build_impact_bounds: n_dense=%d outside [1,%d]",
+               n_dense, BM_MAX_DENSE);
+  RAGB_REQUIRE(dense_stride >= n_docs && dense_stride % BM_RANGE == 0, RAGB_EINVAL,
+               "ragb_bm25_build_impact_bounds: dense_stride must be a multiple of %d covering n_docs", BM_RANGE);
+  RAGB_REQUIRE(((reinterpret_cast<uintptr_t>(dense_tf) | reinterpret_cast<uintptr_t>(dense_imp_fp16_out)) & 15) == 0, RAGB_EINVAL,
+               "ragb_bm25_build_impact_bounds: tables must be 16-byte aligned");
+  RAGB_CUDA(cudaMemsetAsync(dense_max_imp_out, 0, sizeof(float) * n_dense, stream));
+  int64_t blocks = ceil_div64(dense_stride, static_cast<int64_t>(TB_THREADS) * 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  impact_bounds_kernel<<<dim3(static_cast<unsigned>(blocks), n_dense), TB_THREADS, 0, stream>>>(
+      dense_tf, norm, n_docs, dense_stride, reinterpret_cast<__half*>(dense_imp_fp16_out), dense_max_imp_out);
   RAGB_AFTER_LAUNCH(1);
   return RAGB_OK;
 }

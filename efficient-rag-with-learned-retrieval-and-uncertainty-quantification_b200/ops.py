@@ -72,6 +72,58 @@ def _(doc_len, avgdl, k1, b):
     return doc_len.new_empty(doc_len.shape, dtype=torch.float32)
 
 
+@torch.library.custom_op(f"{NS}::bm25_term_max_tf", mutates_args=(), device_types="cuda")
+def bm25_term_max_tf(term_off: Tensor, post_tf: Tensor, terms: Tensor) -> Tensor:
+    """Largest term frequency in the posting list of each of ``terms`` (int32 [n])."""
+    term_off, post_tf, terms = _need(term_off, torch.int64, "term_off"), _need(post_tf, torch.int16, "post_tf"), \
+        _need(terms, torch.int32, "terms")
+    out = torch.empty(terms.shape[0], dtype=torch.int32, device=terms.device)
+    with torch.cuda.device(terms.device):
+        check(lib.ragb_bm25_term_max_tf(_ptr(term_off), _ptr(post_tf), _ptr(terms), terms.shape[0], _ptr(out), _stream()))
+    return out
+
+
+@bm25_term_max_tf.register_fake
+def _(term_off, post_tf, terms):
+    return terms.new_empty(terms.shape)
+
+
+@torch.library.custom_op(f"{NS}::bm25_build_dense_table", mutates_args=(), device_types="cuda")
+def bm25_build_dense_table(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, terms: Tensor, n_docs: int,
+                           stride: int) -> Tensor:
+    """uint8 [n_terms, stride] tf rows of ``terms`` (0 = absent)."""
+    term_off, post_doc, post_tf, terms = _need(term_off, torch.int64, "term_off"), _need(post_doc, torch.int32, "post_doc"), \
+        _need(post_tf, torch.int16, "post_tf"), _need(terms, torch.int32, "terms")
+    table = torch.empty((terms.shape[0], stride), dtype=torch.uint8, device=terms.device)
+    with torch.cuda.device(terms.device):
+        check(lib.ragb_bm25_build_dense_table(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(terms), terms.shape[0],
+                                              n_docs, _ptr(table), stride, _stream()))
+    return table
+
+
+@bm25_build_dense_table.register_fake
+def _(term_off, post_doc, post_tf, terms, n_docs, stride):
+    return terms.new_empty((terms.shape[0], stride), dtype=torch.uint8)
+
+
+@torch.library.custom_op(f"{NS}::bm25_build_impact_bounds", mutates_args=(), device_types="cuda")
+def bm25_build_impact_bounds(dense_tf: Tensor, norm: Tensor) -> Tuple[Tensor, Tensor]:
+    """-> (fp16 [n_dense, stride] upper bounds of tf / (tf + norm), fp32 [n_dense] row maxima)."""
+    dense_tf, norm = _need(dense_tf, torch.uint8, "dense_tf"), _need(norm, torch.float32, "norm")
+    rows, stride = dense_tf.shape
+    imp = torch.empty((rows, stride), dtype=torch.float16, device=dense_tf.device)
+    maximp = torch.empty(rows, dtype=torch.float32, device=dense_tf.device)
+    with torch.cuda.device(dense_tf.device):
+        check(lib.ragb_bm25_build_impact_bounds(_ptr(dense_tf), stride, rows, _ptr(norm), norm.shape[0], _ptr(imp),
+                                                _ptr(maximp), _stream()))
+    return imp, maximp
+
+
+@bm25_build_impact_bounds.register_fake
+def _(dense_tf, norm):
+    return dense_tf.new_empty(dense_tf.shape, dtype=torch.float16), norm.new_empty((dense_tf.shape[0],))
+
+
 def _dense_table(dense_tf: Tensor, dense_terms: Tensor, n_docs: int):
     """(ptr, stride, terms ptr, rows) of the optional dense tf table; an empty tensor disables it."""
     if dense_tf.numel() == 0 or dense_terms.numel() == 0:

@@ -86,18 +86,7 @@ class SparseShard:
         self.dense_maximp = torch.empty(0, dtype=torch.float32, device=dev)
         if self.dense_tf is None or self.dense_tf.numel() == 0 or self.dense_tf.numel() * 2 > IMPACT_TABLE_BYTES:
             return
-        rows, stride = self.dense_tf.shape
-        norm = torch.ones(stride, dtype=torch.float32, device=dev)
-        norm[:self.n_docs] = self.norm
-        imp = torch.empty((rows, stride), dtype=torch.float16, device=dev)
-        for r in range(rows):
-            tf = self.dense_tf[r].to(torch.float32)
-            exact = tf / (tf + norm) * 1.000002          # the kernel multiplies by an approximate reciprocal
-            h = exact.to(torch.float16)
-            low = h.to(torch.float32) < exact             # rounded down: step to the next fp16 (positive values)
-            imp[r] = torch.where(low, (h.view(torch.int16) + 1).view(torch.float16), h)
-        self.dense_imp = imp
-        self.dense_maximp = imp.to(torch.float32).amax(dim=1).contiguous()
+        self.dense_imp, self.dense_maximp = ops.bm25_build_impact_bounds(self.dense_tf, self.norm)
 
     def _build_dense_table(self, df_global: Tensor, group=None) -> None:
         """Dense uint8 tf rows for the terms present in >= 1/64 of ALL documents (capped by memory).
@@ -124,21 +113,15 @@ class SparseShard:
         if cand.numel() > rows_max:
             top = torch.topk(df_global[cand].to(torch.int64), rows_max).indices
             cand = cand[top].sort().values
-        lo, hi = self.term_off[cand].tolist(), self.term_off[cand + 1].tolist()
-        fits = torch.ones(cand.numel(), dtype=torch.int32, device=dev)
-        for i, (a, b) in enumerate(zip(lo, hi)):
-            if b > a and int((self.post_tf[a:b].to(torch.int32) & 0xFFFF).max()) > 255:
-                fits[i] = 0
+        # every tf of a table term must fit a byte on EVERY shard (one kernel + one MIN all-reduce, no host loop)
+        fits = (ops.bm25_term_max_tf(self.term_off, self.post_tf, cand.to(torch.int32)) <= 255).to(torch.int32)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=group)
         cand = cand[fits.bool()]
         if cand.numel() == 0:
             return
-        table = torch.zeros((cand.numel(), stride), dtype=torch.uint8, device=dev)
-        for i, t in enumerate(cand.tolist()):
-            a, b = int(self.term_off[t]), int(self.term_off[t + 1])
-            table[i, self.post_doc[a:b].to(torch.int64)] = self.post_tf[a:b].to(torch.uint8)
-        self.dense_tf, self.dense_terms = table, cand.to(torch.int32)
+        self.dense_terms = cand.to(torch.int32).contiguous()
+        self.dense_tf = ops.bm25_build_dense_table(self.term_off, self.post_doc, self.post_tf, self.dense_terms, self.n_docs, stride)
 
     def score_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int):
         return ops.bm25_score_topk(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1,

@@ -59,6 +59,23 @@ int ragb_bm25_build_idf(const int32_t* df, int64_t vocab, int64_t corpus_size, d
 int ragb_bm25_build_norm(const int32_t* doc_len, int64_t n_docs, double avgdl, double k1, double b,
                          float* norm_out, ragb_stream_t stream);
 
+/* ---- builders of the optional dense tf table and its impact bounds (what BM25Okapi.__init__ keeps as one
+ *      dict per document, rank_bm25 _initialize, reached from rag_uq/streaming_index.py:142,220) ------------
+ * ragb_bm25_term_max_tf: max_tf_out[i] = largest term frequency among the postings of terms[i] (0 = empty list);
+ *   a term qualifies for a table row only if this is <= 255 on EVERY shard.
+ * ragb_bm25_build_dense_table: table_out[i * stride + d] = tf of terms[i] in local document d, 0 where absent
+ *   (the table is cleared first); stride % 256 == 0, >= n_docs; n_terms <= 1024.
+ * ragb_bm25_build_impact_bounds: dense_imp_fp16_out[r * stride + d] = the smallest IEEE fp16 >=
+ *   tf / (tf + norm[d]) * (1 + 2e-6), dense_max_imp_out[r] = the maximum of row r (see ragb_bm25_score_topk). */
+int ragb_bm25_term_max_tf(const int64_t* term_off, const uint16_t* post_tf, const int32_t* terms, int32_t n_terms,
+                          int32_t* max_tf_out, ragb_stream_t stream);
+int ragb_bm25_build_dense_table(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf,
+                                const int32_t* terms, int32_t n_terms, int64_t n_docs, uint8_t* table_out,
+                                int64_t stride, ragb_stream_t stream);
+int ragb_bm25_build_impact_bounds(const uint8_t* dense_tf, int64_t dense_stride, int32_t n_dense, const float* norm,
+                                  int64_t n_docs, uint16_t* dense_imp_fp16_out, float* dense_max_imp_out,
+                                  ragb_stream_t stream);
+
 /* ---- BM25 scoring : rank_bm25 BM25Okapi.get_scores + BM25Index.search
  *      (rag_uq/streaming_index.py:165-179) --------------------------------------------
  * Term-major CSR over the LOCAL shard: postings of term t are

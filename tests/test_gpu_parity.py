@@ -1090,6 +1090,44 @@ def test_retrieval_uncertainty(rq, dev):
         assert float(got[q]) == pytest.approx(dense_fusion.retrieval_uncertainty(valid, 0.5), rel=1e-5, abs=1e-6)
 
 
+def _check_against_streamed_oracle(rq, dev, engine, cdf, n, first_query, n_q, k, pool, router, tag):
+    """Hybrid top-k + router rerank of n_q queries against oracle/large_check.py streamed over the WHOLE corpus."""
+    from oracle import large_check
+    from rag_uq_b200 import synth
+    qb = synth.make_queries(n_q, n, 768, cdf, dev, first_query=first_query)
+    with torch.no_grad():
+        res = engine.retrieve_and_rerank(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, pool)
+    state = {key: v.detach().cpu() for key, v in router.state_dict().items()}
+    recs, info = large_check.run_synthetic_check(synth, dev, n, 768, qb.q_terms.view(n_q, -1).cpu().tolist(), qb.q_emb, pool, k,
+                                                 state, True, df_expect=engine.sparse.df_global)
+    assert info["df_matches_product"] is True
+    ids, vals = res["ids"].cpu().tolist(), res["fused"].cpu().tolist()
+    exact = 0
+    for q, rec in enumerate(recs):
+        ex, ok = large_check.compare_ranking(ids[q], vals[q], rec["rerank_ids"], rec["rerank_vals"], rec["rerank_all"], 2e-5, 1e-6)
+        # a pool cut that fp32 and fp64 may place differently changes which documents are fused at all: not a kernel error
+        assert ok or min(rec["bm25_gap"], rec["dense_gap"]) < 1e-5, (tag, q, ids[q], rec["rerank_ids"])
+        exact += ex
+    assert exact >= n_q - 1, (tag, exact)
+    return exact
+
+
+def test_c2_shape_1m_batch1_against_streamed_oracle(rq, dev):
+    """BASELINE configs[1] at full size: 1M passages, batch-1 queries through the GEMV + BM25 path, top-10, checked
+    against the float64 oracle over all 1M passages (ids identical modulo proven ties, scores 2e-5); then the same
+    corpus through the batched tcgen05 path (16 queries)."""
+    from rag_uq_b200 import synth
+    n = 1_000_000
+    engine, cdf = synth.build_synthetic_engine(n, 768, dev)
+    torch.manual_seed(7)
+    router = rq.RetrievalRouter().to(dev).eval()
+    router.bm25_mean.fill_(8.0); router.bm25_std.fill_(6.0); router.dense_mean.fill_(0.2); router.dense_std.fill_(0.3)
+    router.stats_initialized = True
+    for first in (0, 1, 2):                               # three separate batch-1 calls (GEMV path)
+        _check_against_streamed_oracle(rq, dev, engine, cdf, n, first, 1, 10, 50, router, f"b1-{first}")
+    _check_against_streamed_oracle(rq, dev, engine, cdf, n, 100, 16, 10, 50, router, "b16-mma")
+
+
 @pytest.mark.parametrize("n,n_q", [(2_000_000, 256)])
 def test_large_corpus_properties(rq, dev, n, n_q):
     """Size-independent properties at a corpus the CPU oracle cannot score: the pruned / seeded top-k
