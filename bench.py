@@ -360,7 +360,7 @@ def run_ours(args):
     n_local = engine.passages.shape[0]
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    dense_ms, bm25_ms = [], []
+    dense_ms, bm25_ms, exch_ms = [], [], []
 
     def step(q_terms, q_off, q_emb, probes=None):
         with torch.no_grad():
@@ -426,6 +426,8 @@ def run_ours(args):
     for evs in probes:
         bm25_ms.append(evs["bm25"][0].elapsed_time(evs["bm25"][1]))
         dense_ms.append(evs["dense"][0].elapsed_time(evs["dense"][1]))
+        if "seed_exchange" in evs:
+            exch_ms.append(evs["seed_exchange"][0].elapsed_time(evs["seed_exchange"][1]))
     timed(max(1, args.warmup // 2), True)
     e2e_ms, _, _, last = timed(args.steps, True)
 
@@ -488,6 +490,7 @@ def run_ours(args):
                         "bm25_posting_gbs": sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9,
                         "bm25_frac_of_hbm_peak": sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9 / pk["hbm_gbs"],
                         "dense_ms": dense_avg,
+                        "seed_exchange_ms": (sum(exch_ms) / len(exch_ms)) if exch_ms else None,
                         "other_ms": ms / args.steps - (max(dense_avg, bm25_avg) if (args.overlap and args.batch > 8)
                                                        else dense_avg + bm25_avg)},
         }

@@ -55,13 +55,16 @@ SIGNATURES = {
     "ragb_bm25_build_impact_bounds": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p]),
     "ragb_bm25_topk_workspace_bytes": (_sz, [_i32, _i64, _i32]),
     "ragb_bm25_score_topk": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _p, _p, _i32, _i32,
-                                       _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
+                                       _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "ragb_bm25_seed": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _i32, _i32, _i64, _i32, _p, _p]),
     "ragb_bm25_scores": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _i32, _i32, _i64,
                                    _p, _i64, _i32, _p]),
     "ragb_dense_gemv_workspace_bytes": (_sz, [_i32, _i32]),
     "ragb_dense_gemv_topk": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _p, _p, _p, _sz, _p]),
     "ragb_dense_mma_workspace_bytes": (_sz, [_i32, _i32]),
     "ragb_dense_mma_topk": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "ragb_dense_mma_sample": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _i32, _p, _p, _sz, _p]),
+    "ragb_dense_mma_seeded": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "ragb_dense_mma_fused_topk": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _p, _i64, _p, _p, _p, _p, _p, _i32,
                                             _p, _i32, _i32, C.c_float, C.c_float, _p, _p, _p, _p, _sz, _p]),
     "ragb_dense_scores": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _p]),

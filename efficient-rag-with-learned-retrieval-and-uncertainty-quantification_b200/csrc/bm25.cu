@@ -460,12 +460,23 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
     window = max(BM_SUPER_DOCS, want / BM_SUPER_DOCS * BM_SUPER_DOCS);
   }
 
+  // The admission threshold is shared between all blocks of a query through seed_thr[q] in L2: every block that
+  // finishes publishes the k-th best score of its stripe (atomicMax below) - a proven lower bound of the query's
+  // final k-th best - and every warp picks the current value up once per visit.  Blocks of later stripes therefore
+  // start where the best earlier stripe ended instead of warming their own top-k up from the seed.  The value is
+  // requested one visit ahead so its L2 latency hides behind the work of the visit.  It only prunes: results do
+  // not depend on which blocks ran first.
+  float pending_thr = 0.0f;
   const int j0 = lane * 8;  // the 8 documents of a range this lane owns
   for (int sup = 0; sup < n_super; ++sup) {
     const int64_t s0l = w_begin + static_cast<int64_t>(sup) * BM_SUPER_DOCS;
     const int s0 = static_cast<int>(s0l < w_end ? s0l : w_end);
     const int s1 = static_cast<int>(min(w_end, s0l + BM_SUPER_DOCS));
     if (s1 <= s0) break;  // warp-uniform; nothing below synchronises the block
+    if (!DENSE_OUT) {
+      tk.raise(pending_thr);
+      pending_thr = __ldcg(a.seed_thr + q);
+    }
     if (!DENSE_OUT && window_ok && tk.thr_score > ub_table) {
       // ================= window mode: the rest of this warp's documents (see stream_term_hash) =================
       int* const keys = reinterpret_cast<int*>(sacc);
@@ -476,6 +487,8 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
       while (d0l < w_end) {
         const int d0 = static_cast<int>(d0l);
         const int d1 = static_cast<int>(min(w_end, d0l + window));
+        tk.raise(pending_thr);
+        pending_thr = __ldcg(a.seed_thr + q);
         unsigned act = __ballot_sync(0xffffffffu, lane < ntv && s_nxt[lane] < d1);
         if (act == 0u) {   // no posting of any list in this window: nothing can reach thr
           if (a.debug && lane == 0) atomicAdd(&g_bm25_dbg[1], 1ull);
@@ -819,6 +832,11 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
     bitonic_sort_desc<BM_THREADS>(all_keys, n);
     uint64_t* dst = a.part_keys + (static_cast<int64_t>(q) * gridDim.y + blockIdx.y) * a.k;
     for (int i = tid; i < a.k; i += BM_THREADS) dst[i] = all_keys[i];
+    // publish this stripe's k-th best score (positive floats order like their bit patterns)
+    if (tid == 0 && all_keys[a.k - 1] != 0ull) {
+      const float kth = key_score(all_keys[a.k - 1]);
+      if (kth > 0.0f) atomicMax(reinterpret_cast<int*>(a.seed_thr + q), __float_as_int(kth));
+    }
   }
 }
 
@@ -1210,13 +1228,48 @@ size_t ragb_bm25_topk_workspace_bytes(int32_t n_queries, int64_t n_docs, int32_t
   return static_cast<size_t>(n_queries) * stripes * k * sizeof(uint64_t) + static_cast<size_t>(n_queries) * sizeof(float);
 }
 
+int ragb_bm25_seed(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
+                   const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
+                   const int32_t* dense_terms, int32_t n_dense, const int32_t* q_terms, const int32_t* q_off,
+                   int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int32_t k, float* seed_out,
+                   ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = bm25_common_checks("ragb_bm25_seed", term_off, post_doc, post_tf, norm, idf, vocab, q_terms, q_off, n_queries,
+                              n_docs, max_query_terms, dense_tf, dense_stride, dense_terms, n_dense);
+  if (rc != RAGB_OK) return rc;
+  RAGB_REQUIRE(seed_out, RAGB_EINVAL, "ragb_bm25_seed: null pointer");
+  RAGB_REQUIRE(k > 0 && k <= RAGB_MAX_TOPK, RAGB_ELIMIT, "ragb_bm25_seed: k=%d outside [1,%d]", k, RAGB_MAX_TOPK);
+  Bm25Args a{};
+  a.term_off = term_off;
+  a.post_doc = post_doc;
+  a.post_tf = post_tf;
+  a.norm = norm;
+  a.idf = idf;
+  a.q_terms = q_terms;
+  a.q_off = q_off;
+  a.vocab = vocab;
+  a.n_docs = n_docs;
+  a.k1p1 = static_cast<float>(k1 + 1.0);
+  a.max_terms = max_query_terms;
+  a.dense_tf = dense_tf;
+  a.dense_terms = dense_terms;
+  a.dense_stride = dense_stride;
+  a.n_dense = n_dense;
+  a.k = k;
+  a.seed_thr = seed_out;
+  bm25_seed_kernel<<<n_queries, SEED_THREADS, 0, stream>>>(a);
+  RAGB_AFTER_LAUNCH(1);
+  return RAGB_OK;
+}
+
 int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
                          const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
                          const int32_t* dense_terms, int32_t n_dense, const uint16_t* dense_imp_fp16,
                          const float* dense_max_imp, const int32_t* q_terms, const int32_t* q_off,
                          int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
-                         float* out_score, int32_t* out_id, void* workspace, size_t workspace_bytes,
-                         ragb_stream_t stream_) {
+                         const float* seed_thr, float* out_score, int32_t* out_id, void* workspace,
+                         size_t workspace_bytes, ragb_stream_t stream_) {
   RAGB_ENTRY();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = bm25_common_checks("ragb_bm25_score_topk", term_off, post_doc, post_tf, norm, idf, vocab, q_terms, q_off,
@@ -1261,8 +1314,14 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   // postings aimed at per window (0 turns window mode off); tuning aid, the default is what was measured best
   static const int window_flag = [] { const char* e = getenv("RAGB_BM25_WINDOW"); return e ? atoi(e) : 256; }();
   a.window_mode = window_flag;
-  bm25_seed_kernel<<<n_queries, SEED_THREADS, 0, stream>>>(a);
-  RAGB_AFTER_LAUNCH(1);
+  if (seed_thr != nullptr) {
+    // bounds proven elsewhere (ragb_bm25_seed, possibly raised to the maximum over all shards): the kernel keeps
+    // raising its private copy, the caller's array stays untouched
+    RAGB_CUDA(cudaMemcpyAsync(a.seed_thr, seed_thr, sizeof(float) * n_queries, cudaMemcpyDeviceToDevice, stream));
+  } else {
+    bm25_seed_kernel<<<n_queries, SEED_THREADS, 0, stream>>>(a);
+    RAGB_AFTER_LAUNCH(1);
+  }
   const size_t smem = bm25_smem_bytes(a.max_terms, a.capacity, false);
   RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   bm25_kernel<false><<<dim3(n_queries, stripes), BM_THREADS, smem, stream>>>(a);

@@ -46,6 +46,12 @@ void note_launch(int n = 1);
 // select.cu: merge [n_queries, n_lists, k_in] packed keys into (score, id)[n_queries, k_out]
 int launch_merge_keys(const uint64_t* keys, int n_queries, int n_lists, int k_in, int k_out, float* out_score,
                       int32_t* out_id, cudaStream_t stream);
+// same with one more list per query stored elsewhere (extra_keys [n_queries, k_extra], nullable) and optional outputs:
+// out_keys [n_queries, k_out] packed keys, out_thr [n_queries] score of the k_out-th best (-inf if fewer); out_score /
+// out_id may be null when out_keys is given
+int launch_merge_keys_ex(const uint64_t* keys, int n_queries, int n_lists, int k_in, const uint64_t* extra_keys, int k_extra,
+                         int k_out, float* out_score, int32_t* out_id, uint64_t* out_keys, float* out_thr,
+                         cudaStream_t stream);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int next_pow2(int v) {

@@ -56,9 +56,11 @@ struct MmaArgs {
   int n_slabs;
   int n_groups;
   int tiles_per_group;
-  int n_tiles;
+  int tile_lo, tile_hi;  // this launch covers passage tiles [tile_lo, tile_hi) (the sampled prefix, or the rest)
   int n_stages;
-  uint64_t* part_keys;  // [n_queries, n_groups, 2 column halves, k]
+  const float* seed_thr;  // optional [n_queries]: a proven lower bound of every query's k-th best score; lists start there
+  uint64_t* part_keys;  // [n_queries, lists_per_query, k]; this launch fills slots [group * 2 + half]
+  int lists_per_query;
   int* progress;        // [n_groups, n_slabs] tiles issued so far (soft pacing between the slabs of a group)
   uint64_t* lists;      // [blocks, 128, list capacity + 1] per-thread candidate lists
   int stage_limit;
@@ -279,6 +281,15 @@ __device__ __forceinline__ void epilogue_scan(const MmaArgs& a, const uint32_t t
   uint64_t* warp_lists = block_lists + static_cast<size_t>(half * 4 + quad) * 32 * LIST_STRIDE;
   uint64_t* my_list = warp_lists + lane * LIST_STRIDE;
   ListState st{0, -INFINITY, 0ull};
+  if (a.seed_thr != nullptr && query < a.n_queries) {
+    // nothing below a proven lower bound of the query's k-th best score can end up in its top-k: start the list
+    // there instead of at -inf (an equal score still passes: the key's id bits are never all zero)
+    const float seed = __ldg(a.seed_thr + query);
+    if (seed > -INFINITY) {
+      st.thr_score = seed;
+      st.thr_key = static_cast<uint64_t>(float_to_ordered(seed)) << 32;
+    }
+  }
   uint32_t buf = 0, acc_phase = 0;
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_phase);
@@ -340,7 +351,7 @@ __device__ __forceinline__ void epilogue_scan(const MmaArgs& a, const uint32_t t
   st = compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, st);
   const int cnt = st.cnt;
   if (query < a.n_queries) {
-    uint64_t* dst = a.part_keys + ((static_cast<int64_t>(query) * a.n_groups + group) * 2 + half) * a.k;
+    uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.lists_per_query + group * 2 + half) * a.k;
     for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? __ldcg(reinterpret_cast<const unsigned long long*>(my_list + j)) : 0ull;
   }
 }
@@ -575,7 +586,7 @@ __device__ __forceinline__ void epilogue_scan_fused(const MmaArgs& a, const uint
   st = compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, st);
   const int cnt = st.cnt;
   if (live) {
-    uint64_t* dst = a.part_keys + ((static_cast<int64_t>(query) * a.n_groups + group) * 2 + half) * a.k;
+    uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.lists_per_query + group * 2 + half) * a.k;
     for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? __ldcg(reinterpret_cast<const unsigned long long*>(my_list + j)) : 0ull;
   }
   if (a.counters != nullptr) {
@@ -603,8 +614,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_kernel(const __grid_c
   if (static_cast<int>(blockIdx.x) >= n_slabs * a.n_groups) return;
   const int slab = blockIdx.x % n_slabs;
   const int group = blockIdx.x / n_slabs;
-  const int tile_begin = min(a.n_tiles, group * a.tiles_per_group);
-  const int tile_end = min(a.n_tiles, tile_begin + a.tiles_per_group);
+  const int tile_begin = min(a.tile_hi, a.tile_lo + group * a.tiles_per_group);
+  const int tile_end = min(a.tile_hi, tile_begin + a.tiles_per_group);
   const int n_kb = a.dim / MM_BK;
   const int a_cols = A_IN_TMEM ? a.dim / 2 : 0;  // TMEM columns holding the packed query slab
   const uint32_t tmem_cols = A_IN_TMEM ? 512u : (2 * BN <= 32 ? 32u : (2 * BN <= 64 ? 64u : (2 * BN <= 128 ? 128u : (2 * BN <= 256 ? 256u : 512u))));
@@ -830,8 +841,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) dense_mma_pair_kernel(const __g
   // every block of the grid belongs to a live pair (the host sizes the grid exactly)
   const int slab = 2 * (pair % n_pairs_slab) + static_cast<int>(cta_rank);
   const int group = pair / n_pairs_slab;
-  const int tile_begin = min(a.n_tiles, group * a.tiles_per_group);
-  const int tile_end = min(a.n_tiles, tile_begin + a.tiles_per_group);
+  const int tile_begin = min(a.tile_hi, a.tile_lo + group * a.tiles_per_group);
+  const int tile_end = min(a.tile_hi, tile_begin + a.tiles_per_group);
   const int n_kb = a.dim / MM_BK;
 
   extern __shared__ unsigned char smem_dyn[];
@@ -1017,10 +1028,38 @@ static void copy_fused_fields(MmaArgs& a, const MmaArgs* fused) {
   a.ff_debug = fused->ff_debug;
 }
 
+// Passage groups of one launch over `tiles` tiles: as many as the SMs (or CTA pairs) left after one block per query
+// slab (pair) allow.  Pure function of its arguments: the sampled and the seeded phase and the workspace layout
+// all derive their list counts from it.
+struct MmaPlan {
+  int n_slabs, n_groups, tiles_per_group, blocks;
+};
+static MmaPlan mma_plan(bool pair, int n_queries, int tiles, int sms) {
+  MmaPlan p{};
+  p.n_slabs = (n_queries + MM_BM - 1) / MM_BM;
+  const int units = pair ? (p.n_slabs + 1) / 2 : p.n_slabs;      // blocks (or CTA pairs) per passage group
+  const int slots = pair ? sms / 2 : sms;
+  p.n_groups = units > 0 ? slots / units : 0;
+  if (p.n_groups > tiles) p.n_groups = tiles;
+  if (p.n_groups < 1) p.n_groups = 1;
+  p.tiles_per_group = (tiles + p.n_groups - 1) / p.n_groups;
+  p.n_groups = (tiles + p.tiles_per_group - 1) / p.tiles_per_group;
+  p.blocks = (pair ? 2 * units : units) * p.n_groups;
+  return p;
+}
+
+// what one launch covers and where its lists go
+struct MmaRange {
+  int tile_lo, tile_hi;       // passage tiles [tile_lo, tile_hi)
+  const float* seed_thr;      // optional [n_queries] proven lower bounds of the k-th best score
+  uint64_t* part;             // [n_queries, lists_per_query, k]
+  int lists_per_query;        // >= 2 * groups of this launch
+};
+
 template <int BN, bool A_IN_TMEM, int KPL, bool FUSED = false>
 static int launch_mma(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
-                      int64_t id_base, uint64_t* part, int* progress, uint64_t* lists, int stage_limit,
-                      int* n_groups_out, cudaStream_t stream, const MmaArgs* fused = nullptr) {
+                      int64_t id_base, const MmaRange& r, int* progress, uint64_t* lists, int stage_limit,
+                      cudaStream_t stream, const MmaArgs* fused = nullptr) {
   constexpr int STAGE_BYTES = (A_IN_TMEM ? 0 : MM_A_STAGE_BYTES) + BN * MM_BK * 2;
   CUtensorMap map_q, map_e;
   int rc = make_map(&map_q, queries, n_queries, dim, MM_BM);
@@ -1028,6 +1067,11 @@ static int launch_mma(const void* passages, int64_t n_rows, int dim, const void*
   rc = make_map(&map_e, passages, n_rows, dim, BN);
   if (rc != RAGB_OK) return rc;
 
+  const int sms = device_sm_count();
+  const MmaPlan plan = mma_plan(false, n_queries, r.tile_hi - r.tile_lo, sms);
+  RAGB_REQUIRE(plan.n_slabs <= sms, RAGB_ELIMIT, "ragb_dense_mma_topk: n_queries=%d needs more than %d slabs of 128",
+               n_queries, sms);
+  RAGB_REQUIRE(2 * plan.n_groups <= r.lists_per_query, RAGB_EINVAL, "ragb_dense_mma_topk: internal list layout mismatch");
   MmaArgs a{};
   a.queries = static_cast<const uint4*>(queries);
   a.n_rows = n_rows;
@@ -1035,16 +1079,14 @@ static int launch_mma(const void* passages, int64_t n_rows, int dim, const void*
   a.n_queries = n_queries;
   a.dim = dim;
   a.k = k;
-  a.n_slabs = (n_queries + MM_BM - 1) / MM_BM;
-  const int sms = device_sm_count();
-  RAGB_REQUIRE(a.n_slabs <= sms, RAGB_ELIMIT, "ragb_dense_mma_topk: n_queries=%d needs more than %d slabs of 128",
-               n_queries, sms);
-  a.n_tiles = static_cast<int>(ceil_div64(n_rows, BN));
-  a.n_groups = sms / a.n_slabs;
-  if (a.n_groups > a.n_tiles) a.n_groups = a.n_tiles;
-  a.tiles_per_group = (a.n_tiles + a.n_groups - 1) / a.n_groups;
-  a.n_groups = (a.n_tiles + a.tiles_per_group - 1) / a.tiles_per_group;
-  a.part_keys = part;
+  a.n_slabs = plan.n_slabs;
+  a.n_groups = plan.n_groups;
+  a.tiles_per_group = plan.tiles_per_group;
+  a.tile_lo = r.tile_lo;
+  a.tile_hi = r.tile_hi;
+  a.seed_thr = r.seed_thr;
+  a.part_keys = r.part;
+  a.lists_per_query = r.lists_per_query;
   a.progress = progress;
   a.lists = lists;
   copy_fused_fields(a, fused);
@@ -1061,21 +1103,27 @@ static int launch_mma(const void* passages, int64_t n_rows, int dim, const void*
   const size_t smem = 1024 + static_cast<size_t>(stages) * STAGE_BYTES + TABLE_BYTES;
   RAGB_CUDA(cudaFuncSetAttribute(dense_mma_kernel<BN, A_IN_TMEM, KPL, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-  dense_mma_kernel<BN, A_IN_TMEM, KPL, FUSED><<<a.n_slabs * a.n_groups, MM_THREADS, smem, stream>>>(map_q, map_e, a);
+  RAGB_CUDA(cudaFuncSetAttribute(dense_mma_kernel<BN, A_IN_TMEM, KPL, FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
+  dense_mma_kernel<BN, A_IN_TMEM, KPL, FUSED><<<plan.blocks, MM_THREADS, smem, stream>>>(map_q, map_e, a);
   RAGB_AFTER_LAUNCH(1);
-  *n_groups_out = a.n_groups;
   return RAGB_OK;
 }
 
 template <int KPL, bool FUSED = false>
 static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
-                           int64_t id_base, uint64_t* part, int* progress, uint64_t* lists, int stage_limit,
-                           int* n_groups_out, cudaStream_t stream, const MmaArgs* fused = nullptr) {
+                           int64_t id_base, const MmaRange& r, int* progress, uint64_t* lists, int stage_limit,
+                           cudaStream_t stream, const MmaArgs* fused = nullptr) {
   CUtensorMap map_q, map_e;
   int rc = make_map(&map_q, queries, n_queries, dim, MM_BM);
   if (rc != RAGB_OK) return rc;
   rc = make_map(&map_e, passages, n_rows, dim, MM2_BN / 2);   // each block loads half a passage tile
   if (rc != RAGB_OK) return rc;
+  const int sms = device_sm_count();
+  const MmaPlan plan = mma_plan(true, n_queries, r.tile_hi - r.tile_lo, sms);
+  RAGB_REQUIRE((plan.n_slabs + 1) / 2 <= sms / 2, RAGB_ELIMIT, "ragb_dense_mma_topk: n_queries=%d needs more than %d CTA pairs",
+               n_queries, sms / 2);
+  RAGB_REQUIRE(2 * plan.n_groups <= r.lists_per_query, RAGB_EINVAL, "ragb_dense_mma_topk: internal list layout mismatch");
   MmaArgs a{};
   a.queries = static_cast<const uint4*>(queries);
   a.n_rows = n_rows;
@@ -1083,17 +1131,14 @@ static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const 
   a.n_queries = n_queries;
   a.dim = dim;
   a.k = k;
-  a.n_slabs = (n_queries + MM_BM - 1) / MM_BM;
-  const int n_pairs_slab = (a.n_slabs + 1) / 2;
-  const int clusters = device_sm_count() / 2;
-  RAGB_REQUIRE(n_pairs_slab <= clusters, RAGB_ELIMIT, "ragb_dense_mma_topk: n_queries=%d needs more than %d CTA pairs",
-               n_queries, clusters);
-  a.n_tiles = static_cast<int>(ceil_div64(n_rows, MM2_BN));
-  a.n_groups = clusters / n_pairs_slab;
-  if (a.n_groups > a.n_tiles) a.n_groups = a.n_tiles;
-  a.tiles_per_group = (a.n_tiles + a.n_groups - 1) / a.n_groups;
-  a.n_groups = (a.n_tiles + a.tiles_per_group - 1) / a.tiles_per_group;
-  a.part_keys = part;
+  a.n_slabs = plan.n_slabs;
+  a.n_groups = plan.n_groups;
+  a.tiles_per_group = plan.tiles_per_group;
+  a.tile_lo = r.tile_lo;
+  a.tile_hi = r.tile_hi;
+  a.seed_thr = r.seed_thr;
+  a.part_keys = r.part;
+  a.lists_per_query = r.lists_per_query;
   a.progress = progress;
   a.lists = lists;
   copy_fused_fields(a, fused);
@@ -1108,8 +1153,12 @@ static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const 
   const size_t smem = 1024 + static_cast<size_t>(stages) * MM2_STAGE_BYTES + TABLE_BYTES;
   RAGB_CUDA(cudaFuncSetAttribute(dense_mma_pair_kernel<KPL, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
+  // the SM keeps its maximal shared-memory carve-out even when this kernel asks for less (RAGB_MMA_STAGES), so
+  // blocks of another kernel (BM25 on a second stream) can become co-resident without reconfiguring the SM
+  RAGB_CUDA(cudaFuncSetAttribute(dense_mma_pair_kernel<KPL, FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * n_pairs_slab * a.n_groups);
+  cfg.gridDim = dim3(plan.blocks);
   cfg.blockDim = dim3(MM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -1122,7 +1171,6 @@ static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const 
   cfg.numAttrs = 1;
   RAGB_CUDA(cudaLaunchKernelEx(&cfg, dense_mma_pair_kernel<KPL, FUSED>, map_q, map_e, a));
   RAGB_AFTER_LAUNCH(1);
-  *n_groups_out = a.n_groups;
   return RAGB_OK;
 }
 
@@ -1137,6 +1185,117 @@ static int mma_list_kpl(int k) {   // capacity 32*KPL >= k + 32
 static size_t mma_list_bytes(int k) {
   return static_cast<size_t>(148) * 2 * MM_BM * (32 * mma_list_kpl(k) + 1) * sizeof(uint64_t);
 }
+constexpr int MM_MAX_LISTS = 148 * 2;   // lists per query of one launch, at most (one group per SM, two column halves)
+
+static int mma_stage_limit() {
+  static const int v = [] {
+    const char* e = getenv("RAGB_MMA_STAGES");  // tuning aid / overlap: leaves shared memory for co-resident blocks
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+// Sampled prefix: the first 1/32 of the tiles is searched un-seeded; the k-th best score found there is a proven
+// lower bound of the final k-th best, and every list of the remaining 31/32 starts from it.  Without it each of
+// the 2 x groups lists of a query warms up from -inf on its own: 36 x k (1 + ln(n / k)) appends and a sort per
+// (capacity - k) of them - 1.2 ms of the 2.8 ms at 1.25M rows and k = 50.  With it a query admits ~31 k candidates
+// in total, spread over all its lists, and almost no list is compacted before the end.  Small shards skip the prefix.
+static int mma_sample_tiles(int n_tiles) {
+  static const int div = [] {
+    const char* e = getenv("RAGB_MMA_SAMPLE_DIV");  // tuning aid: 0 = no sampled prefix
+    return e ? atoi(e) : 32;
+  }();
+  if (div <= 0 || n_tiles < 512) return 0;
+  return n_tiles / div;
+}
+
+struct MmaWorkspace {
+  int* progress;
+  uint64_t* lists;
+  uint64_t* sample_keys;   // [n_queries, k] merged result of the sampled prefix
+  uint64_t* part;          // [n_queries, <= MM_MAX_LISTS, k]
+};
+static size_t mma_workspace_bytes(int n_queries, int k) {
+  return MM_PROGRESS_BYTES + mma_list_bytes(k) + static_cast<size_t>(n_queries) * (MM_MAX_LISTS + 1) * k * sizeof(uint64_t);
+}
+static MmaWorkspace mma_carve(void* workspace, int n_queries, int k) {
+  unsigned char* p = static_cast<unsigned char*>(workspace);
+  MmaWorkspace w;
+  w.progress = reinterpret_cast<int*>(p);
+  w.lists = reinterpret_cast<uint64_t*>(p + MM_PROGRESS_BYTES);
+  w.sample_keys = reinterpret_cast<uint64_t*>(p + MM_PROGRESS_BYTES + mma_list_bytes(k));
+  w.part = w.sample_keys + static_cast<size_t>(n_queries) * k;
+  return w;
+}
+
+// one un-fused launch over a tile range with the variant / list-capacity dispatch
+static int mma_dispatch(int variant, const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries,
+                        int k, int64_t id_base, const MmaRange& r, const MmaWorkspace& w, cudaStream_t stream) {
+  const int kpl = mma_list_kpl(k);
+  const int sl = mma_stage_limit();
+#define RAGB_MMA_ARGS passages, n_rows, dim, queries, n_queries, k, id_base, r, w.progress, w.lists, sl, stream
+#define RAGB_MMA_DISPATCH(FN, ...)                                         \
+  do {                                                                    \
+    if (kpl == 2) return FN<__VA_ARGS__ 2>(RAGB_MMA_ARGS);                \
+    if (kpl == 4) return FN<__VA_ARGS__ 4>(RAGB_MMA_ARGS);                \
+    return FN<__VA_ARGS__ 8>(RAGB_MMA_ARGS);                              \
+  } while (0)
+#define RAGB_COMMA ,
+  if (variant == 0) RAGB_MMA_DISPATCH(launch_mma, 128 RAGB_COMMA false RAGB_COMMA);
+  if (variant == 1) RAGB_MMA_DISPATCH(launch_mma, 64 RAGB_COMMA true RAGB_COMMA);
+  if (variant == 2 || n_queries <= MM_BM) RAGB_MMA_DISPATCH(launch_mma, 256 RAGB_COMMA false RAGB_COMMA);   // a lone slab has no partner
+  RAGB_MMA_DISPATCH(launch_mma_pair, );
+#undef RAGB_MMA_DISPATCH
+#undef RAGB_COMMA
+#undef RAGB_MMA_ARGS
+}
+static int mma_tile_rows(int variant) { return variant == 0 ? 128 : (variant == 1 ? 64 : 256); }
+static bool mma_uses_pairs(int variant, int n_queries) { return variant == 3 && n_queries > MM_BM; }
+
+static int mma_common_checks(const char* who, const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
+                             int32_t n_queries, int32_t k, int64_t id_base, int32_t variant, const void* workspace,
+                             size_t workspace_bytes) {
+  RAGB_REQUIRE(passages_bf16 && queries_bf16 && workspace, RAGB_EINVAL, "%s: null pointer", who);
+  RAGB_REQUIRE(((reinterpret_cast<uintptr_t>(passages_bf16) | reinterpret_cast<uintptr_t>(queries_bf16)) & 15) == 0,
+               RAGB_EINVAL, "%s: inputs must be 16-byte aligned", who);
+  RAGB_REQUIRE(n_rows > 0 && n_queries > 0, RAGB_EINVAL, "%s: empty shape", who);
+  RAGB_REQUIRE(dim >= MM_BK && dim % MM_BK == 0, RAGB_EINVAL, "%s: dim=%d must be a multiple of %d", who, dim, MM_BK);
+  RAGB_REQUIRE(k > 0 && k <= 100, RAGB_ELIMIT, "%s: k=%d outside [1,100]", who, k);
+  RAGB_REQUIRE(variant >= 0 && variant <= 3, RAGB_EINVAL, "%s: variant must be 0, 1, 2 or 3", who);
+  RAGB_REQUIRE(variant != 1 || dim <= 768, RAGB_ELIMIT, "%s: variant 1 keeps the query slab in TMEM and needs dim <= 768", who);
+  RAGB_REQUIRE(id_base >= 0 && id_base + n_rows < (1ll << 31), RAGB_ELIMIT, "%s: ids must fit int32", who);
+  RAGB_REQUIRE(workspace_bytes >= mma_workspace_bytes(n_queries, k), RAGB_ENOSPC, "%s: workspace too small", who);
+  return RAGB_OK;
+}
+
+// phase 1: search the sampled prefix, leave its merged list in the workspace, report the per-query k-th best score
+static int mma_sample_phase(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
+                            int64_t id_base, int variant, float* thr_out, const MmaWorkspace& w, cudaStream_t stream) {
+  const int n_tiles = static_cast<int>(ceil_div64(n_rows, mma_tile_rows(variant)));
+  const int ts = mma_sample_tiles(n_tiles);
+  if (ts == 0)   // no prefix: merging zero lists leaves an empty sample list and the bound -inf for every query
+    return launch_merge_keys_ex(w.part, n_queries, 0, k, nullptr, 0, k, nullptr, nullptr, w.sample_keys, thr_out, stream);
+  const MmaPlan plan = mma_plan(mma_uses_pairs(variant, n_queries), n_queries, ts, device_sm_count());
+  const MmaRange r{0, ts, nullptr, w.part, 2 * plan.n_groups};
+  int rc = mma_dispatch(variant, passages, n_rows, dim, queries, n_queries, k, id_base, r, w, stream);
+  if (rc != RAGB_OK) return rc;
+  return launch_merge_keys_ex(w.part, n_queries, 2 * plan.n_groups, k, nullptr, 0, k, nullptr, nullptr, w.sample_keys, thr_out,
+                              stream);
+}
+
+// phase 2: the rest of the tiles, every list seeded with thr (own or exchanged between shards), final merge
+static int mma_seeded_phase(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
+                            int64_t id_base, int variant, const float* thr, float* out_score, int32_t* out_id,
+                            const MmaWorkspace& w, cudaStream_t stream) {
+  const int n_tiles = static_cast<int>(ceil_div64(n_rows, mma_tile_rows(variant)));
+  const int ts = mma_sample_tiles(n_tiles);
+  const MmaPlan plan = mma_plan(mma_uses_pairs(variant, n_queries), n_queries, n_tiles - ts, device_sm_count());
+  const MmaRange r{ts, n_tiles, thr, w.part, 2 * plan.n_groups};
+  int rc = mma_dispatch(variant, passages, n_rows, dim, queries, n_queries, k, id_base, r, w, stream);
+  if (rc != RAGB_OK) return rc;
+  return launch_merge_keys_ex(w.part, n_queries, 2 * plan.n_groups, k, w.sample_keys, k, k, out_score, out_id, nullptr, nullptr,
+                              stream);
+}
 
 }  // namespace ragb
 
@@ -1146,7 +1305,7 @@ extern "C" {
 
 size_t ragb_dense_mma_workspace_bytes(int32_t n_queries, int32_t k) {
   if (n_queries <= 0 || k <= 0) return 0;
-  return MM_PROGRESS_BYTES + mma_list_bytes(k) + static_cast<size_t>(n_queries) * 148 * 2 * k * sizeof(uint64_t);
+  return mma_workspace_bytes(n_queries, k) + static_cast<size_t>(n_queries) * sizeof(float);   // + own thresholds
 }
 
 int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
@@ -1154,52 +1313,44 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
                         int32_t* out_id, void* workspace, size_t workspace_bytes, ragb_stream_t stream_) {
   RAGB_ENTRY();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  RAGB_REQUIRE(passages_bf16 && queries_bf16 && out_score && out_id && workspace, RAGB_EINVAL,
-               "ragb_dense_mma_topk: null pointer");
-  RAGB_REQUIRE(((reinterpret_cast<uintptr_t>(passages_bf16) | reinterpret_cast<uintptr_t>(queries_bf16)) & 15) == 0,
-               RAGB_EINVAL, "ragb_dense_mma_topk: inputs must be 16-byte aligned");
-  RAGB_REQUIRE(n_rows > 0 && n_queries > 0, RAGB_EINVAL, "ragb_dense_mma_topk: empty shape");
-  RAGB_REQUIRE(dim >= MM_BK && dim % MM_BK == 0, RAGB_EINVAL, "ragb_dense_mma_topk: dim=%d must be a multiple of %d", dim,
-               MM_BK);
-  RAGB_REQUIRE(k > 0 && k <= 100, RAGB_ELIMIT, "ragb_dense_mma_topk: k=%d outside [1,100]", k);
-  RAGB_REQUIRE(variant >= 0 && variant <= 3, RAGB_EINVAL, "ragb_dense_mma_topk: variant must be 0, 1, 2 or 3");
-  RAGB_REQUIRE(variant != 1 || dim <= 768, RAGB_ELIMIT, "ragb_dense_mma_topk: variant 1 keeps the query slab in TMEM and needs dim <= 768");
-  RAGB_REQUIRE(id_base >= 0 && id_base + n_rows < (1ll << 31), RAGB_ELIMIT, "ragb_dense_mma_topk: ids must fit int32");
-  RAGB_REQUIRE(workspace_bytes >= ragb_dense_mma_workspace_bytes(n_queries, k), RAGB_ENOSPC,
-               "ragb_dense_mma_topk: workspace too small");
-  int* progress = static_cast<int*>(workspace);
-  uint64_t* lists = reinterpret_cast<uint64_t*>(static_cast<unsigned char*>(workspace) + MM_PROGRESS_BYTES);
-  uint64_t* part = reinterpret_cast<uint64_t*>(static_cast<unsigned char*>(workspace) + MM_PROGRESS_BYTES + mma_list_bytes(k));
-  static const int stage_limit = [] {
-    const char* e = getenv("RAGB_MMA_STAGES");  // tuning aid only
-    return e ? atoi(e) : 0;
-  }();
-  int n_groups = 0;
-  int rc;
-  // list capacity per query thread: 64 (k <= 32), 128 (k <= 96) or 256 slots: always k + 32 or more
-#define RAGB_MMA_ARGS passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, progress, lists, stage_limit, &n_groups, stream
-#define RAGB_MMA_DISPATCH(FN, ...)                                   \
-  do {                                                              \
-    const int kpl = mma_list_kpl(k);                                \
-    if (kpl == 2) rc = FN<__VA_ARGS__ 2>(RAGB_MMA_ARGS);            \
-    else if (kpl == 4) rc = FN<__VA_ARGS__ 4>(RAGB_MMA_ARGS);       \
-    else rc = FN<__VA_ARGS__ 8>(RAGB_MMA_ARGS);                     \
-  } while (0)
-#define RAGB_COMMA ,
-  if (variant == 0) {
-    RAGB_MMA_DISPATCH(launch_mma, 128 RAGB_COMMA false RAGB_COMMA);
-  } else if (variant == 1) {
-    RAGB_MMA_DISPATCH(launch_mma, 64 RAGB_COMMA true RAGB_COMMA);
-  } else if (variant == 2 || n_queries <= MM_BM) {   // a lone slab has no partner for a CTA pair
-    RAGB_MMA_DISPATCH(launch_mma, 256 RAGB_COMMA false RAGB_COMMA);
-  } else {
-    RAGB_MMA_DISPATCH(launch_mma_pair, );
-  }
-#undef RAGB_MMA_DISPATCH
-#undef RAGB_COMMA
-#undef RAGB_MMA_ARGS
+  RAGB_REQUIRE(out_score && out_id, RAGB_EINVAL, "ragb_dense_mma_topk: null pointer");
+  RAGB_REQUIRE(workspace_bytes >= ragb_dense_mma_workspace_bytes(n_queries, k), RAGB_ENOSPC, "ragb_dense_mma_topk: workspace too small");
+  int rc = mma_common_checks("ragb_dense_mma_topk", passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant,
+                             workspace, workspace_bytes);
   if (rc != RAGB_OK) return rc;
-  return launch_merge_keys(part, n_queries, n_groups * 2, k, k, out_score, out_id, stream);
+  const MmaWorkspace w = mma_carve(workspace, n_queries, k);
+  float* thr = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + mma_workspace_bytes(n_queries, k));
+  rc = mma_sample_phase(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant, thr, w, stream);
+  if (rc != RAGB_OK) return rc;
+  return mma_seeded_phase(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant, thr, out_score, out_id, w,
+                          stream);
+}
+
+int ragb_dense_mma_sample(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
+                          int32_t n_queries, int32_t k, int64_t id_base, int32_t variant, float* thr_out,
+                          void* workspace, size_t workspace_bytes, ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(thr_out, RAGB_EINVAL, "ragb_dense_mma_sample: null pointer");
+  int rc = mma_common_checks("ragb_dense_mma_sample", passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant,
+                             workspace, workspace_bytes);
+  if (rc != RAGB_OK) return rc;
+  return mma_sample_phase(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant, thr_out,
+                          mma_carve(workspace, n_queries, k), stream);
+}
+
+int ragb_dense_mma_seeded(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
+                          int32_t n_queries, int32_t k, int64_t id_base, int32_t variant, const float* thr,
+                          float* out_score, int32_t* out_id, void* workspace, size_t workspace_bytes,
+                          ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(thr && out_score && out_id, RAGB_EINVAL, "ragb_dense_mma_seeded: null pointer");
+  int rc = mma_common_checks("ragb_dense_mma_seeded", passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant,
+                             workspace, workspace_bytes);
+  if (rc != RAGB_OK) return rc;
+  return mma_seeded_phase(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant, thr, out_score, out_id,
+                          mma_carve(workspace, n_queries, k), stream);
 }
 
 int ragb_dense_mma_fused_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
@@ -1232,9 +1383,7 @@ int ragb_dense_mma_fused_topk(const void* passages_bf16, int64_t n_rows, int32_t
   RAGB_REQUIRE(id_base >= 0 && id_base + n_rows < (1ll << 31), RAGB_ELIMIT, "ragb_dense_mma_fused_topk: ids must fit int32");
   RAGB_REQUIRE(workspace_bytes >= ragb_dense_mma_workspace_bytes(n_queries, k), RAGB_ENOSPC,
                "ragb_dense_mma_fused_topk: workspace too small");
-  int* progress = static_cast<int*>(workspace);
-  uint64_t* lists = reinterpret_cast<uint64_t*>(static_cast<unsigned char*>(workspace) + MM_PROGRESS_BYTES);
-  uint64_t* part = reinterpret_cast<uint64_t*>(static_cast<unsigned char*>(workspace) + MM_PROGRESS_BYTES + mma_list_bytes(k));
+  const MmaWorkspace w = mma_carve(workspace, n_queries, k);
   MmaArgs f{};
   f.bm25 = bm25_scores;
   f.bm25_ld = bm25_rows;
@@ -1251,11 +1400,14 @@ int ragb_dense_mma_fused_topk(const void* passages_bf16, int64_t n_rows, int32_t
     return e ? atoi(e) : 0;
   }();
   f.ff_debug = ff_debug;
-  int n_groups = 0;
   int rc;
   const int kpl = mma_list_kpl(k);
-#define RAGB_FUSED_ARGS passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, part, progress, lists, 0, &n_groups, stream, &f
-  if (n_queries <= MM_BM) {   // a lone slab has no partner for a CTA pair
+  const bool pair = n_queries > MM_BM;   // a lone slab has no partner for a CTA pair
+  const int n_tiles = static_cast<int>(ceil_div64(n_rows, MM2_BN));
+  const MmaPlan plan = mma_plan(pair, n_queries, n_tiles, device_sm_count());
+  const MmaRange r{0, n_tiles, nullptr, w.part, 2 * plan.n_groups};
+#define RAGB_FUSED_ARGS passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, r, w.progress, w.lists, 0, stream, &f
+  if (!pair) {
     if (kpl == 2) rc = launch_mma<256, false, 2, true>(RAGB_FUSED_ARGS);
     else if (kpl == 4) rc = launch_mma<256, false, 4, true>(RAGB_FUSED_ARGS);
     else rc = launch_mma<256, false, 8, true>(RAGB_FUSED_ARGS);
@@ -1266,7 +1418,7 @@ int ragb_dense_mma_fused_topk(const void* passages_bf16, int64_t n_rows, int32_t
   }
 #undef RAGB_FUSED_ARGS
   if (rc != RAGB_OK) return rc;
-  return launch_merge_keys(part, n_queries, n_groups * 2, k, k, out_score, out_id, stream);
+  return launch_merge_keys(w.part, n_queries, 2 * plan.n_groups, k, k, out_score, out_id, stream);
 }
 
 // Debug aid (not part of the documented ABI): evaluate the full-fusion bound of the fused epilogue for n

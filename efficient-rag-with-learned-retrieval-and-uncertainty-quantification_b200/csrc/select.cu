@@ -77,12 +77,19 @@ __global__ void __launch_bounds__(SEL_THREADS) sort_rows_kernel(const float* __r
 // Merge candidate lists.  Input either packed keys [n_queries, n_lists, k_in] or separate
 // (score, id) arrays with id -1 = empty.  One block per query.
 // ---------------------------------------------------------------------------------------
+// Optional extras (all nullable): ``extra_keys`` [n_queries, k_extra] one more list per query stored elsewhere (the
+// sampled prefix of the seeded dense search); ``out_keys`` [n_queries, k_out] the merged list as packed keys instead
+// of (score, id); ``out_thr`` [n_queries] the score of the k_out-th best candidate, -inf while fewer than k_out exist
+// (a proven lower bound of the final k-th best score whenever the input is a subset of the candidates).
 __global__ void __launch_bounds__(SEL_THREADS) topk_merge_kernel(const uint64_t* __restrict__ in_keys,
                                                                  const float* __restrict__ in_score,
                                                                  const int32_t* __restrict__ in_id, int n_lists,
                                                                  int k_in, int k_out, int capacity,
                                                                  float* __restrict__ out_score,
-                                                                 int32_t* __restrict__ out_id) {
+                                                                 int32_t* __restrict__ out_id,
+                                                                 const uint64_t* __restrict__ extra_keys, int k_extra,
+                                                                 uint64_t* __restrict__ out_keys,
+                                                                 float* __restrict__ out_thr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
   __shared__ SelSmem st;
@@ -110,12 +117,24 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_merge_kernel(const uint64_t*
       }
     }
   }
+  if (extra_keys != nullptr) {
+    for (int base = 0; base < k_extra; base += SEL_CHUNK) {
+      tk.reserve(SEL_CHUNK);
+      const uint64_t thr = *tk.threshold;
+      for (int idx = base + threadIdx.x; idx < min(k_extra, base + SEL_CHUNK); idx += SEL_THREADS)
+        tk.offer(extra_keys[static_cast<int64_t>(q) * k_extra + idx], thr);
+    }
+  }
   tk.finish();
   for (int i = threadIdx.x; i < k_out; i += SEL_THREADS) {
     uint64_t key = keys[i];
-    out_score[static_cast<int64_t>(q) * k_out + i] = key ? key_score(key) : 0.0f;
-    out_id[static_cast<int64_t>(q) * k_out + i] = key ? key_id(key) : -1;
+    if (out_keys != nullptr) out_keys[static_cast<int64_t>(q) * k_out + i] = key;
+    if (out_score != nullptr) {
+      out_score[static_cast<int64_t>(q) * k_out + i] = key ? key_score(key) : 0.0f;
+      out_id[static_cast<int64_t>(q) * k_out + i] = key ? key_id(key) : -1;
+    }
   }
+  if (out_thr != nullptr && threadIdx.x == 0) out_thr[q] = keys[k_out - 1] ? key_score(keys[k_out - 1]) : -INFINITY;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -281,9 +300,15 @@ __global__ void __launch_bounds__(256) retrieval_uncertainty_kernel(const float*
 // Host-side helpers shared with the scoring kernels ---------------------------------------
 int launch_merge_keys(const uint64_t* keys, int n_queries, int n_lists, int k_in, int k_out, float* out_score,
                       int32_t* out_id, cudaStream_t stream) {
+  return launch_merge_keys_ex(keys, n_queries, n_lists, k_in, nullptr, 0, k_out, out_score, out_id, nullptr, nullptr, stream);
+}
+
+int launch_merge_keys_ex(const uint64_t* keys, int n_queries, int n_lists, int k_in, const uint64_t* extra_keys, int k_extra,
+                         int k_out, float* out_score, int32_t* out_id, uint64_t* out_keys, float* out_thr,
+                         cudaStream_t stream) {
   const int capacity = topk_capacity(k_out);
   topk_merge_kernel<<<n_queries, SEL_THREADS, capacity * sizeof(uint64_t), stream>>>(
-      keys, nullptr, nullptr, n_lists, k_in, k_out, capacity, out_score, out_id);
+      keys, nullptr, nullptr, n_lists, k_in, k_out, capacity, out_score, out_id, extra_keys, k_extra, out_keys, out_thr);
   RAGB_AFTER_LAUNCH(1);
   return RAGB_OK;
 }
@@ -354,7 +379,7 @@ int ragb_topk_merge(const float* in_score, const int32_t* in_id, int32_t n_queri
                RAGB_MAX_TOPK);
   const int capacity = topk_capacity(k_out);
   topk_merge_kernel<<<n_queries, SEL_THREADS, capacity * sizeof(uint64_t), stream>>>(
-      nullptr, in_score, in_id, n_lists, k_in, k_out, capacity, out_score, out_id);
+      nullptr, in_score, in_id, n_lists, k_in, k_out, capacity, out_score, out_id, nullptr, 0, nullptr, nullptr);
   RAGB_AFTER_LAUNCH(1);
   return RAGB_OK;
 }

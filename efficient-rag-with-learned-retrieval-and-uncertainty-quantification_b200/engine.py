@@ -119,6 +119,25 @@ class HybridEngine:
             e.record()
             return e
 
+        # Sharded corpus: both kernels prune against a proven lower bound of the query's k-th best score (the BM25
+        # seed; the k-th best of the dense kernel's sampled prefix).  The k-th best of the WHOLE corpus is at least
+        # the k-th best of any shard, so the bounds are raised to their maximum over the shards first: one tiny
+        # all-reduce ([2, B] floats, latency-bound) in front of the two kernels.  Results do not depend on it.
+        exchange = self.world > 1 and big and hasattr(self.sparse, "seed")
+        if exchange:
+            t0 = mark() if events is not None else None
+            b_seed = self.sparse.seed(q_terms, q_off, max_terms, pool)
+            d_thr, d_ws = ops.dense_mma_sample(self.passages, q_emb, pool, self.id_base, self.mma_variant)
+            both = torch.stack([b_seed, d_thr])
+            dist.all_reduce(both, op=dist.ReduceOp.MAX, group=self.group)
+            t1 = mark() if events is not None else None
+            bs, bi = self.sparse.score_topk(q_terms, q_off, max_terms, pool, both[0])
+            t2 = mark() if events is not None else None
+            ds, di = ops.dense_mma_seeded(self.passages, q_emb, pool, self.id_base, self.mma_variant, both[1], d_ws)
+            if events is not None:
+                events["seed_exchange"], events["bm25"], events["dense"] = (t0, t1), (t1, t2), (t2, mark())
+            return bs, bi, ds, di
+
         if not (overlap and big):
             t0 = mark() if events is not None else None
             bs, bi = self.sparse.score_topk(q_terms, q_off, max_terms, pool)

@@ -151,9 +151,11 @@ def _bm25_args(term_off, post_doc, post_tf, norm, idf, q_terms, q_off):
 @torch.library.custom_op(f"{NS}::bm25_score_topk", mutates_args=(), device_types="cuda")
 def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
                     dense_tf: Tensor, dense_terms: Tensor, dense_imp: Tensor, dense_maximp: Tensor, q_terms: Tensor,
-                    q_off: Tensor, max_query_terms: int, id_base: int, k: int) -> Tuple[Tensor, Tensor]:
+                    q_off: Tensor, max_query_terms: int, id_base: int, k: int, seed: Tensor) -> Tuple[Tensor, Tensor]:
     """dense_imp (float16 [n_dense, stride]) / dense_maximp (float32 [n_dense]): optional impact bounds of the table
-    terms (ragb200.h); pass empty tensors to run without them - the results are the same."""
+    terms (ragb200.h); pass empty tensors to run without them - the results are the same.
+    seed (float32 [B] or empty): proven lower bounds of every query's k-th best score (``bm25_seed``, possibly raised
+    to the maximum over all shards); empty = the kernel seeds itself."""
     term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
                                                                         q_terms, q_off)
     n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
@@ -168,19 +170,47 @@ def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: T
         if tuple(dense_imp.shape) != tuple(dense_tf.shape) or dense_maximp.shape[0] != n_dense:
             raise ValueError("dense_imp must have the shape of dense_tf and dense_maximp one entry per row")
         imp, maximp = dense_imp.data_ptr(), dense_maximp.data_ptr()
+    seed_ptr = None
+    if seed.numel():
+        seed = _need(seed, torch.float32, "seed")
+        if seed.numel() != n_q:
+            raise ValueError("seed must hold one bound per query")
+        seed_ptr = seed.data_ptr()
     with torch.cuda.device(dev):
         check(lib.ragb_bm25_score_topk(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf),
                                        idf.shape[0], k1, dt, stride, dterms, n_dense, imp, maximp, _ptr(q_terms), _ptr(q_off), n_q,
-                                       max_query_terms, n_docs, id_base, k, _ptr(score), _ptr(ids), _ptr(ws),
+                                       max_query_terms, n_docs, id_base, k, seed_ptr, _ptr(score), _ptr(ids), _ptr(ws),
                                        ws.numel(), _stream()))
     return score, ids
 
 
 @bm25_score_topk.register_fake
 def _(term_off, post_doc, post_tf, norm, idf, k1, dense_tf, dense_terms, dense_imp, dense_maximp, q_terms, q_off,
-      max_query_terms, id_base, k):
+      max_query_terms, id_base, k, seed):
     n_q = q_off.shape[0] - 1
     return norm.new_empty((n_q, k)), norm.new_empty((n_q, k), dtype=torch.int32)
+
+
+@torch.library.custom_op(f"{NS}::bm25_seed", mutates_args=(), device_types="cuda")
+def bm25_seed(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
+              dense_tf: Tensor, dense_terms: Tensor, q_terms: Tensor, q_off: Tensor, max_query_terms: int,
+              k: int) -> Tensor:
+    """Proven lower bounds [B] of every query's k-th best BM25 score over this shard (0 = none); see ragb200.h."""
+    term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
+                                                                        q_terms, q_off)
+    n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
+    out = torch.empty(n_q, dtype=torch.float32, device=dev)
+    dt, stride, dterms, n_dense = _dense_table(dense_tf, dense_terms, n_docs)
+    with torch.cuda.device(dev):
+        check(lib.ragb_bm25_seed(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf), idf.shape[0], k1,
+                                 dt, stride, dterms, n_dense, _ptr(q_terms), _ptr(q_off), n_q, max_query_terms, n_docs, k,
+                                 _ptr(out), _stream()))
+    return out
+
+
+@bm25_seed.register_fake
+def _(term_off, post_doc, post_tf, norm, idf, k1, dense_tf, dense_terms, q_terms, q_off, max_query_terms, k):
+    return norm.new_empty((q_off.shape[0] - 1,))
 
 
 @torch.library.custom_op(f"{NS}::bm25_scores", mutates_args=(), device_types="cuda")
@@ -249,6 +279,49 @@ def dense_mma_topk(passages: Tensor, queries: Tensor, k: int, id_base: int, vari
 
 @dense_mma_topk.register_fake
 def _(passages, queries, k, id_base, variant):
+    n_q = queries.shape[0]
+    return (queries.new_empty((n_q, k), dtype=torch.float32), queries.new_empty((n_q, k), dtype=torch.int32))
+
+
+@torch.library.custom_op(f"{NS}::dense_mma_sample", mutates_args=(), device_types="cuda")
+def dense_mma_sample(passages: Tensor, queries: Tensor, k: int, id_base: int, variant: int) -> Tuple[Tensor, Tensor]:
+    """Phase 1 of the seeded tcgen05 search (ragb200.h): -> (thr float32 [B], workspace uint8).  ``thr`` may be raised to
+    the maximum over all shards before it is handed to ``dense_mma_seeded`` together with the SAME workspace."""
+    passages, queries = _dense_args(passages, queries)
+    n_q, dev = queries.shape[0], passages.device
+    thr = torch.empty(n_q, dtype=torch.float32, device=dev)
+    ws = _workspace(lib.ragb_dense_mma_workspace_bytes(n_q, k), dev)
+    with torch.cuda.device(dev):
+        check(lib.ragb_dense_mma_sample(_ptr(passages), passages.shape[0], passages.shape[1], _ptr(queries), n_q, k,
+                                        id_base, variant, _ptr(thr), _ptr(ws), ws.numel(), _stream()))
+    return thr, ws
+
+
+@dense_mma_sample.register_fake
+def _(passages, queries, k, id_base, variant):
+    return queries.new_empty((queries.shape[0],), dtype=torch.float32), queries.new_empty((16,), dtype=torch.uint8)
+
+
+@torch.library.custom_op(f"{NS}::dense_mma_seeded", mutates_args=("workspace",), device_types="cuda")
+def dense_mma_seeded(passages: Tensor, queries: Tensor, k: int, id_base: int, variant: int, thr: Tensor,
+                     workspace: Tensor) -> Tuple[Tensor, Tensor]:
+    """Phase 2: the rest of the shard with every candidate list seeded by ``thr``, merged with phase 1."""
+    passages, queries = _dense_args(passages, queries)
+    thr = _need(thr, torch.float32, "thr")
+    n_q, dev = queries.shape[0], passages.device
+    if thr.numel() != n_q or workspace.dtype != torch.uint8 or not workspace.is_contiguous():
+        raise ValueError("thr must hold one bound per query and workspace must be the tensor dense_mma_sample returned")
+    score = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.ragb_dense_mma_seeded(_ptr(passages), passages.shape[0], passages.shape[1], _ptr(queries), n_q, k,
+                                        id_base, variant, _ptr(thr), _ptr(score), _ptr(ids), _ptr(workspace),
+                                        workspace.numel(), _stream()))
+    return score, ids
+
+
+@dense_mma_seeded.register_fake
+def _(passages, queries, k, id_base, variant, thr, workspace):
     n_q = queries.shape[0]
     return (queries.new_empty((n_q, k), dtype=torch.float32), queries.new_empty((n_q, k), dtype=torch.int32))
 

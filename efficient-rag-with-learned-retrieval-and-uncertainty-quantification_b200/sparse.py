@@ -123,10 +123,19 @@ class SparseShard:
         self.dense_terms = cand.to(torch.int32).contiguous()
         self.dense_tf = ops.bm25_build_dense_table(self.term_off, self.post_doc, self.post_tf, self.dense_terms, self.n_docs, stride)
 
-    def score_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int):
+    def score_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int, seed: Optional[Tensor] = None):
+        """``seed`` (float32 [B], optional): proven lower bounds of every query's k-th best score, e.g. ``self.seed``
+        raised to the maximum over all shards; None = the kernel seeds itself."""
+        if seed is None:
+            seed = torch.empty(0, dtype=torch.float32, device=self.post_doc.device)
         return ops.bm25_score_topk(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1,
                                    self.dense_tf, self.dense_terms, self.dense_imp, self.dense_maximp, q_terms, q_off,
-                                   max_terms, self.id_base, k)
+                                   max_terms, self.id_base, k, seed)
+
+    def seed(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int) -> Tensor:
+        """Proven lower bounds [B] of the k-th best score of every query over this shard (ragb_bm25_seed)."""
+        return ops.bm25_seed(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1, self.dense_tf,
+                             self.dense_terms, q_terms, q_off, max_terms, k)
 
     def scores_tiled(self, q_terms: Tensor, q_off: Tensor, max_terms: int, out: Tensor) -> None:
         """get_scores of a batch written into the tiled matrix ``out[ceil(n_docs / 256), rows >= B, 256]``."""
@@ -287,8 +296,8 @@ class SegmentedIndex:
     def idf(self) -> Tensor:
         return self.segments[0].idf
 
-    def score_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int):
-        parts = [s.score_topk(q_terms, q_off, max_terms, k) for s in self.segments]
+    def score_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int, seed: Optional[Tensor] = None):
+        parts = [s.score_topk(q_terms, q_off, max_terms, k, seed) for s in self.segments]
         if len(parts) == 1:
             return parts[0]
         return ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1), k)

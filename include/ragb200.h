@@ -103,8 +103,19 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
                          const uint16_t* dense_imp_fp16, const float* dense_max_imp,
                          const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
                          int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
-                         float* out_score, int32_t* out_id,
+                         const float* seed_thr, float* out_score, int32_t* out_id,
                          void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+/* Threshold seeding on its own: seed_out[q] = a PROVEN lower bound of query q's k-th best score over this shard
+ * (0 = none).  ragb_bm25_score_topk computes it itself when seed_thr is null; a caller that shards the corpus
+ *  calls this first, takes the MAXIMUM over all shards (one all-reduce) and passes the result as
+ * seed_thr, so that every shard prunes against the best bound any shard has proven - the k-th best of the whole
+ * corpus is at least the k-th best of any part of it.  Results are identical with any valid bound. */
+int ragb_bm25_seed(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf,
+                   const float* norm, const float* idf, int64_t vocab, double k1,
+                   const uint8_t* dense_tf, int64_t dense_stride,
+                   const int32_t* dense_terms, int32_t n_dense,
+                   const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
+                   int32_t max_query_terms, int64_t n_docs, int32_t k, float* seed_out, ragb_stream_t stream);
 /* Same arithmetic, full score vectors (get_scores itself).
  * tiled = 0: out_scores[q * out_ld + d], out_ld >= n_docs (row-major).
  * tiled = 1: out_scores[((d / 256) * out_ld + q) * 256 + d % 256], out_ld >= n_queries: 256-document tiles
@@ -138,6 +149,22 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
                         const void* queries_bf16, int32_t n_queries, int32_t k, int64_t id_base,
                         int32_t variant, float* out_score, int32_t* out_id,
                         void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+/* The same search in its two phases, for callers that shard the corpus.  On large shards ragb_dense_mma_topk
+ * first searches a sampled prefix (1/32 of the passage tiles): the k-th best score found there is a proven lower
+ * bound of the final k-th best, and every candidate list of the remaining tiles starts from it instead of from
+ * -inf.  ragb_dense_mma_sample runs the first phase (its merged list stays in the workspace) and reports the
+ * bounds in thr_out[n_queries] (-inf = none); the caller may raise them to the MAXIMUM over all shards (one
+ * all-reduce, shared with ragb_bm25_seed); ragb_dense_mma_seeded then searches the rest with thr and merges both
+ * phases.  Same workspace (contents preserved between the calls), same arguments; results are identical with
+ * any valid bounds. */
+int ragb_dense_mma_sample(const void* passages_bf16, int64_t n_rows, int32_t dim,
+                          const void* queries_bf16, int32_t n_queries, int32_t k, int64_t id_base,
+                          int32_t variant, float* thr_out,
+                          void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+int ragb_dense_mma_seeded(const void* passages_bf16, int64_t n_rows, int32_t dim,
+                          const void* queries_bf16, int32_t n_queries, int32_t k, int64_t id_base,
+                          int32_t variant, const float* thr, float* out_score, int32_t* out_id,
+                          void* workspace, size_t workspace_bytes, ragb_stream_t stream);
 /* Full-fusion mode: RetrievalRouter.hybrid_rerank (rag_uq/router.py:179-202) evaluated over ALL
  * passages of the shard inside the epilogue of the tcgen05 GEMM: for every (query, passage)
  *   fused = gate(bm25, dense) * dense + (1 - gate) * bm25,   gate = RetrievalRouter.forward with

@@ -334,6 +334,29 @@ def test_bm25_shards_with_global_statistics_equal_unsharded(rq, dev):
     i = torch.stack([p[1] for p in parts], dim=1)
     ms, mi = rq.ops.topk_merge(s, i, k)
     assert torch.equal(mi, wi) and torch.equal(ms, ws)            # bit-identical, not just close
+    # the same with the pruning bounds exchanged between the shards (what HybridEngine does at world > 1): every
+    # shard starts from the MAXIMUM of the shards' proven bounds - still bit-identical to the unsharded index
+    seeds = torch.stack([sh.seed(qb.q_terms, qb.q_off, qb.max_terms, k) for sh in shards]).amax(dim=0)
+    parts = [sh.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k, seeds) for sh in shards]
+    ms2, mi2 = rq.ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1), k)
+    assert torch.equal(mi2, wi) and torch.equal(ms2, ws)
+
+
+@pytest.mark.parametrize("n,n_q,k", [(120_000, 48, 50), (9_000, 20, 10)])
+def test_bm25_external_seed_only_prunes(rq, dev, n, n_q, k):
+    """ragb_bm25_seed + seed_thr: any PROVEN lower bound of the k-th best score gives the same result - the kernel's own
+    seed, no seed at all (zeros), and the tightest possible one (the true k-th best score itself)."""
+    from rag_uq_b200 import synth
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    shard = rq.build_shard(doc_off, doc_tok, vocab).finalize()
+    qb = synth.make_queries(n_q, n, 64, cdf, dev)
+    base_s, base_i = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+    own = shard.seed(qb.q_terms, qb.q_off, qb.max_terms, k)
+    kth = torch.where(base_i[:, k - 1] >= 0, base_s[:, k - 1], torch.zeros_like(base_s[:, k - 1]))
+    assert bool((own <= kth + 1e-6).all()), "a seed exceeds the k-th best score it is supposed to bound from below"
+    for seed in (own, torch.zeros_like(own), kth.contiguous()):
+        s, i = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k, seed)
+        assert torch.equal(i, base_i) and torch.equal(s, base_s)
 
 
 # ------------------------------------------------------------------------------------------
@@ -376,6 +399,31 @@ def test_dense_mma_topk(rq, dev, variant, n, b, k, dim):
     score, ids = rq.ops.dense_mma_topk(passages, q, k, 7, variant)
     torch.cuda.synchronize()
     _check_dense(score, ids, want, min(k, n), id_base=7)
+
+
+@pytest.mark.parametrize("n,b,k,variant", [(150_000, 200, 50, 3), (140_000, 130, 10, 2), (131_072, 300, 100, 3)])
+def test_dense_mma_seeded_two_phase(rq, dev, n, b, k, variant):
+    """Shards of >= 512 passage tiles are searched in two phases (sampled prefix -> proven bound -> seeded rest):
+    the result equals the float64 oracle; the explicit two-call form (ragb_dense_mma_sample / _seeded) equals the
+    one-call form bit for bit - with its own bounds, with no bounds (-inf) and with the tightest valid bounds (the true
+    k-th best scores, as another shard might have proven them)."""
+    passages, q, want = _dense_case(rq, dev, n, b)
+    score, ids = rq.ops.dense_mma_topk(passages, q, k, 11, variant)
+    _check_dense(score, ids, want, k, id_base=11)
+    thr, ws = rq.ops.dense_mma_sample(passages, q, k, 11, variant)
+    assert bool(torch.isfinite(thr).all()) and bool((thr <= score[:, k - 1]).all())     # proven LOWER bounds
+    s2, i2 = rq.ops.dense_mma_seeded(passages, q, k, 11, variant, thr, ws)
+    assert torch.equal(s2, score) and torch.equal(i2, ids)
+    for bound in (torch.full_like(thr, float("-inf")), score[:, k - 1].contiguous()):
+        thr3, ws3 = rq.ops.dense_mma_sample(passages, q, k, 11, variant)
+        s3, i3 = rq.ops.dense_mma_seeded(passages, q, k, 11, variant, torch.maximum(thr3, bound), ws3)
+        assert torch.equal(s3, score) and torch.equal(i3, ids)
+    # small shards have no sampled prefix: the bound is -inf and the seeded phase covers everything
+    p_small, q_small, want_small = _dense_case(rq, dev, 5000, 130)
+    thr, ws = rq.ops.dense_mma_sample(p_small, q_small, k, 0, variant)
+    assert bool(torch.isinf(thr).all()) and bool((thr < 0).all())
+    s4, i4 = rq.ops.dense_mma_seeded(p_small, q_small, k, 0, variant, thr, ws)
+    _check_dense(s4, i4, want_small, min(k, 5000))
 
 
 def test_hnsw_recall_against_exact_search(rq, dev):
