@@ -57,6 +57,9 @@ def parse_args():
                         "passage) pair inside the tcgen05 epilogue (RetrievalRouter.hybrid_rerank over [B, N])")
     p.add_argument("--mc-samples", type=int, default=0, help="MC-Dropout passes over the fused candidates (c4: 30)")
     p.add_argument("--candidates", type=int, default=0, help="fused candidates kept per query before the rerank (c4: 100)")
+    p.add_argument("--no-graph", action="store_true",
+                   help="batches of <= 8 queries on one GPU run as ONE CUDA graph per step (HybridEngine.graphed_search: BM25 "
+                        "chain and GEMV as parallel branches); this flag times the eager launch sequence instead")
     p.add_argument("--verify", type=int, default=8,
                    help="after the timed region, check the first VERIFY queries of batch 0 against the CPU oracle streamed over "
                         "the WHOLE corpus (oracle/large_check.py: float64 rank_bm25 arithmetic, exact float64 inner products, "
@@ -362,8 +365,17 @@ def run_ours(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     dense_ms, bm25_ms, exch_ms = [], [], []
 
+    graphed = None
+    if args.batch <= 8 and world == 1 and args.mode == "pool" and args.mc_samples == 0 and args.candidates <= args.k \
+            and not args.no_graph:
+        graphed = engine.graphed_search(router, args.batch, max_terms, args.k, args.pool)
+
     def step(q_terms, q_off, q_emb, probes=None):
         with torch.no_grad():
+            if graphed is not None:                      # one graph launch: static buffers in, static buffers out
+                graphed.load(q_terms, q_off, q_emb)
+                out = graphed.replay()
+                return out[0], out[1]
             events = {} if probes is not None else None
             if args.mode == "full-fusion":
                 vals, ids = engine.full_fusion_topk(q_terms, q_off, max_terms, q_emb, router, args.k, events=events)
@@ -417,12 +429,25 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), ops.launch_count() - launches0, probes, out
+        launched = ops.launch_count() - launches0
+        if graphed is not None:                          # kernels inside a replayed graph do not pass through the counter
+            launched += n_steps * graphed.kernels_per_replay
+        return float(t[0]), launched, probes, out
 
     timed(args.warmup, False)
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches, probes, _ = timed(args.steps, False)
     clocks = sampler.stop() if sampler else None
+    if graphed is not None:
+        # per-kernel times cannot be taken inside a graph: a few eager steps outside the timed region provide them
+        probes = []
+        with torch.no_grad():
+            for s_ in range(max(5, args.warmup)):
+                b_ = batches[s_ % n_sets]
+                evs_ = {}
+                engine.local_pools(b_.q_terms, b_.q_off, max_terms, b_.q_emb, args.pool, events=evs_)
+                probes.append(evs_)
+        torch.cuda.synchronize()
     for evs in probes:
         bm25_ms.append(evs["bm25"][0].elapsed_time(evs["bm25"][1]))
         dense_ms.append(evs["dense"][0].elapsed_time(evs["dense"][1]))
@@ -476,7 +501,10 @@ def run_ours(args):
                                    f"bf16 row-sharded over {world} GPU(s), batch {args.batch} queries x 8 terms",
                        "l2": "inputs exceed L2 (embedding shard %.1f GB, postings %.1f GB per GPU); 4 rotating query batches"
                              % (n_local * DIM * 2 / 1e9, engine.sparse.nnz * 6 / 1e9),
-                       "streams": ("BM25 and dense kernels on one stream, back to back" if not args.overlap or args.batch <= 8 else
+                       "streams": ("ONE CUDA graph per step (%d library kernels): BM25 chain and GEMV as parallel branches; the "
+                                   "per-kernel times are from eager steps outside the timed region" % graphed.kernels_per_replay
+                                   if graphed is not None else
+                                   "BM25 and dense kernels on one stream, back to back" if not args.overlap or args.batch <= 8 else
                                    "BM25 and dense kernels overlapped on two streams; per-kernel times are measured while "
                                    "they share the SMs"),
                        "build_seconds": round(build_s, 1)},

@@ -205,6 +205,14 @@ class HybridEngine:
             out["gate_mean"], out["gate_std"] = unc.mean_gate, unc.std_gate
         return out
 
+    # ---- latency path: the whole small-batch step as ONE CUDA graph --------------------------------
+    def graphed_search(self, router, batch: int, max_terms: int, k: int = 10, pool: int = 50) -> "GraphedSearch":
+        """Capture ``retrieve_and_rerank`` for ``batch`` <= 8 queries of at most ``max_terms`` tokens into a CUDA graph
+        (at batch 1 the step is ~10 launches for a few hundred microseconds of work, so launch latency
+        and the serial BM25 -> GEMV order dominate).  Inside the graph the BM25 chain and the GEMV run as two
+        parallel branches; replaying it costs one launch.  Single shard only (an NCCL exchange is not captured)."""
+        return GraphedSearch(self, router, batch, max_terms, k, pool)
+
     # ---- full-fusion mode ----------------------------------------------------------------
     def _max_passage_norm(self) -> float:
         """Largest L2 norm of a passage row (computed once, chunked): with the largest query norm it bounds |dense|."""
@@ -299,3 +307,77 @@ def _mark(events):
     e = torch.cuda.Event(enable_timing=True)
     e.record()
     return e
+
+
+class GraphedSearch:
+    """Static-shape, graph-captured hybrid search + router rerank for small query batches (config C2)."""
+
+    def __init__(self, engine: HybridEngine, router, batch: int, max_terms: int, k: int, pool: int):
+        if engine.world != 1:
+            raise NotImplementedError("graphed_search captures a single-shard step (no collective inside the graph)")
+        if not (1 <= batch <= _lib.GEMV_MAX_BATCH):
+            raise ValueError(f"graphed_search serves batches of 1..{_lib.GEMV_MAX_BATCH} queries (the GEMV path)")
+        if not getattr(router, "stats_initialized", False) and batch > 1:
+            per_query = True
+        else:
+            per_query = not getattr(router, "stats_initialized", False)
+        dev = engine.passages.device
+        self.engine, self.router, self.batch, self.max_terms, self.k, self.pool = engine, router, batch, max_terms, k, pool
+        # static inputs: every query padded to max_terms tokens with -1 (out of vocabulary: contributes nothing)
+        self.q_terms = torch.full((batch * max_terms,), -1, dtype=torch.int32, device=dev)
+        self.q_off = (torch.arange(batch + 1, dtype=torch.int32, device=dev) * max_terms).contiguous()
+        self.q_emb = torch.zeros((batch, engine.passages.shape[1]), dtype=torch.bfloat16, device=dev)
+        self._side = torch.cuda.Stream(device=dev)
+
+        def body():
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):                       # branch 2: dense GEMV over the whole shard
+                ds, di = ops.dense_gemv_topk(engine.passages, self.q_emb, pool, engine.id_base)
+            bs, bi = engine.sparse.score_topk(self.q_terms, self.q_off, max_terms, pool)   # branch 1: seed + BM25 + merge
+            cur.wait_stream(self._side)
+            ids, sb, sd, sh = ops.hybrid_fuse_topk(bs, bi, ds, di, k)
+            fused, order = router.hybrid_rerank(sb, sd, top_k=k, per_query_stats=per_query)
+            ranked = torch.gather(ids, 1, order)
+            return ranked, fused, torch.gather(sb, 1, order), torch.gather(sd, 1, order)
+
+        with torch.no_grad():
+            warm = torch.cuda.Stream(device=dev)                       # warm-up off the default stream, as capture requires
+            warm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(warm):
+                for _ in range(2):
+                    body()
+            torch.cuda.current_stream().wait_stream(warm)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(self.graph):
+                self.out = body()
+            self.kernels_per_replay = _lib.launch_count() - before    # libragb200 kernels inside the graph
+
+    def load(self, q_terms: Tensor, q_off: Tensor, q_emb: Tensor) -> None:
+        """Copy one ragged batch (term ids, offsets, embeddings) into the graph's static, padded buffers."""
+        n = q_off.shape[0] - 1
+        if n != self.batch:
+            raise ValueError(f"this graph was captured for {self.batch} queries, got {n}")
+        lens = (q_off[1:] - q_off[:-1]).to(torch.int64)
+        if q_terms.numel() == self.batch * self.max_terms and bool((lens == self.max_terms).all()):
+            self.q_terms.copy_(q_terms)                                 # already in the padded layout
+        else:
+            if int(lens.max()) > self.max_terms:
+                raise ValueError("a query is longer than the max_terms this graph was captured for")
+            self.q_terms.fill_(-1)
+            pos = torch.arange(q_terms.shape[0], device=q_terms.device) - torch.repeat_interleave(q_off[:-1].to(torch.int64), lens)
+            row = torch.repeat_interleave(torch.arange(n, device=q_terms.device), lens)
+            self.q_terms[row * self.max_terms + pos] = q_terms[:int(lens.sum())]
+        self.q_emb.copy_(q_emb)
+
+    def replay(self):
+        """-> (ids int32 [B,k], fused [B,k], bm25 [B,k], dense [B,k]) of the batch loaded last; the tensors are the
+        graph's static outputs (overwritten by the next replay)."""
+        self.graph.replay()
+        return self.out
+
+    def __call__(self, q_terms: Tensor, q_off: Tensor, q_emb: Tensor):
+        self.load(q_terms, q_off, q_emb)
+        return self.replay()

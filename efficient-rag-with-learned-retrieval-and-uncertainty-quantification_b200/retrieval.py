@@ -21,6 +21,7 @@ first, then the document added earlier.
 from __future__ import annotations
 
 import hashlib
+import itertools
 import json
 import logging
 import os
@@ -134,13 +135,22 @@ class BM25Index:
         self._stale = False
 
     def encode_queries(self, queries: Sequence[str]):
-        """-> (q_terms int32, q_off int32, max_terms) on the index device; unknown words become -1."""
-        rows = [[self.vocab.get(t, -1) for t in self._tokenize(q)] for q in queries]
-        longest = max((len(r) for r in rows), default=0)
+        """Batched tokeniser + vocabulary lookup: -> (q_terms int32, q_off int32, max_terms) on the index device;
+        unknown words become -1 (they contribute nothing, like ``idf.get(q) or 0`` in rank_bm25).
+
+        Tokenisation is the reference's (``text.lower().split()``, :118-120) applied per query; the id lookup runs as
+        ONE C-level pass over all tokens of the batch (``map`` over the interned-vocabulary dict straight into a numpy
+        buffer), not a Python loop per token."""
+        rows = [q.lower().split() for q in queries]
+        lens = np.fromiter(map(len, rows), dtype=np.int64, count=len(rows))
+        longest = int(lens.max()) if len(rows) else 0
         if longest > _lib.MAX_QUERY_TERMS:
             raise ValueError(f"a query has {longest} tokens; the BM25 kernel accepts at most {_lib.MAX_QUERY_TERMS}")
-        flat = np.asarray([t for r in rows for t in r], dtype=np.int32)
-        off = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
+        total = int(lens.sum())
+        flat = np.fromiter(map(self.vocab.get, itertools.chain.from_iterable(rows), itertools.repeat(-1)), dtype=np.int32,
+                           count=total)
+        off = np.zeros(len(rows) + 1, dtype=np.int32)
+        np.cumsum(lens, out=off[1:])
         dev = self.bm25.post_doc.device if self.bm25 is not None else _default_device()
         if flat.size == 0:
             flat = np.full(1, -1, dtype=np.int32)
@@ -405,6 +415,20 @@ class HybridRetriever:
     def hybrid_search(self, query: str, top_k: int = 10, retrieval_pool_size: int = 50) -> List[RetrievalResult]:
         return self.hybrid_search_many([query], None, top_k, retrieval_pool_size)[0]
 
+    def _row_numbers(self, side: str, ids_of_row: List[str], dev) -> torch.Tensor:
+        """int32 [rows of one index] on the device: the retriever's number of the document in each index row, -1
+        when the retriever holds no document for it.  Rebuilt only when the index or the document store grew."""
+        cache = self.__dict__.setdefault("_row_number_cache", {})
+        key = (len(ids_of_row), len(self._order), len(self.documents), str(dev))
+        hit = cache.get(side)
+        if hit is None or hit[0] != key or hit[2] is not ids_of_row:
+            order, docs = self._order, self.documents
+            table = np.fromiter((order[d] if d in docs else -1 for d in ids_of_row), dtype=np.int32, count=len(ids_of_row))
+            hit = (key, torch.from_numpy(table).to(dev) if len(ids_of_row) else torch.zeros(1, dtype=torch.int32, device=dev),
+                   ids_of_row)
+            cache[side] = hit
+        return hit[1]
+
     def hybrid_search_many(self, queries: Sequence[str], query_embeddings=None, top_k: int = 10,
                            retrieval_pool_size: int = 50) -> List[List[RetrievalResult]]:
         """``hybrid_search`` for several queries with one pair of kernel launches.
@@ -421,28 +445,26 @@ class HybridRetriever:
         dev = (bm[0] if bm is not None else de[0]).device
         # common numbering = insertion order into this retriever; documents the retriever holds no
         # text for are dropped BEFORE fusion, as the reference does (:494-496)
-        names = list(self.documents.keys())
-        order = self._order
+        names = self.__dict__.get("_names")
+        if names is None or len(names) != len(self._order):
+            names = self.__dict__["_names"] = sorted(self._order, key=self._order.get)     # number -> document id
 
-        def number(doc_id: str) -> int:
-            return order.get(doc_id, -1)
-
-        def pools(pair, ids_of_row, width):
-            score = torch.zeros((n, width), dtype=torch.float32)
-            ident = torch.full((n, width), -1, dtype=torch.int32)
+        def pools(pair, ids_of_row, side, width):
+            """Index rows -> retriever numbering on the device: one gather through a cached row -> number table
+            (-1 = the retriever holds no document for that row), no Python loop over B x pool."""
+            score = torch.zeros((n, width), dtype=torch.float32, device=dev)
+            ident = torch.full((n, width), -1, dtype=torch.int32, device=dev)
             if pair is not None:
-                s_host, r_host = pair[0].cpu(), pair[1].cpu().tolist()
-                for qi in range(n):
-                    for j, r in enumerate(r_host[qi]):
-                        if r >= 0:
-                            ident[qi, j] = number(ids_of_row[r])
-                            if ident[qi, j] < 0:
-                                s_host[qi, j] = 0.0
-                score[:, :s_host.shape[1]] = s_host
-            return score.to(dev), ident.to(dev)
+                table = self._row_numbers(side, ids_of_row, dev)
+                rows = pair[1].to(torch.int64)
+                mapped = torch.where(rows >= 0, table[rows.clamp(min=0)], torch.full_like(rows, -1, dtype=torch.int32))
+                w = pair[0].shape[1]
+                ident[:, :w] = mapped
+                score[:, :w] = torch.where(mapped >= 0, pair[0], torch.zeros_like(pair[0]))
+            return score, ident
 
-        bs, bi = pools(bm, self.bm25_index.doc_ids, pool)
-        ds, di = pools(de, self.dense_index.ids, pool)
+        bs, bi = pools(bm, self.bm25_index.doc_ids, "bm25", pool)
+        ds, di = pools(de, self.dense_index.ids, "dense", pool)
         k = min(top_k, 2 * pool)
         ids, sb, sd, sh = (t.cpu().tolist() for t in ops.hybrid_fuse_topk(bs, bi, ds, di, k))
         out: List[List[RetrievalResult]] = []

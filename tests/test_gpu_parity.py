@@ -523,7 +523,13 @@ def test_hybrid_engine_end_to_end_c1(rq, dev, n_q, k, pool):
     per_query = [router_oracle.hybrid_rerank(torch.tensor(sb[q:q + 1]), torch.tensor(sd[q:q + 1]), state, False, k) for q in range(n_q)]
     ov, oi = torch.cat([p[0] for p in per_query]), torch.cat([p[1] for p in per_query])
     torch.testing.assert_close(res["fused"].cpu(), ov, rtol=1e-5, atol=1e-5)
-    assert np.array_equal(res["ids"].cpu().numpy(), np.take_along_axis(ids, oi.numpy(), axis=1))
+    want_ids = np.take_along_axis(ids, oi.numpy(), axis=1)
+    got_ids, got_vals = res["ids"].cpu().numpy(), res["fused"].cpu().numpy()
+    for q in range(n_q):      # padding entries (id -1) all fuse to the same value: their mutual order is a tie
+        real = want_ids[q] >= 0
+        every = {int(i): float(v) for i, v in zip(want_ids[q][real], ov[q].numpy()[real])}
+        assert_ranking_matches([int(i) for i in got_ids[q] if i >= 0], [float(v) for v, i in zip(got_vals[q], got_ids[q]) if i >= 0],
+                               [int(i) for i in want_ids[q][real]], [float(v) for v in ov[q].numpy()[real]], every, 1e-5, 1e-5)
     if n_q > 1:   # ... and it differs from normalising over the whole [B, k] call, which hybrid_rerank does by default
         bv, bi_ = router_oracle.hybrid_rerank(torch.tensor(sb), torch.tensor(sd), state, False, k)
         dv, di_ = router.hybrid_rerank(torch.tensor(sb, device=dev), torch.tensor(sd, device=dev), top_k=k)
@@ -1124,6 +1130,68 @@ def test_shard_directory_reload_gives_identical_results(rq, dev, tmp_path):
     got = again.hybrid_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, 10, 50)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_graphed_small_batch_search_equals_eager(rq, dev):
+    """C2 latency path: the whole batch-1 (and batch-4) step captured as one CUDA graph - BM25 chain and GEMV as parallel
+    branches - returns exactly what the eager call sequence returns, replay after replay, also for ragged queries."""
+    from rag_uq_b200 import synth
+    n, dim = 60_000, 768
+    engine, cdf = synth.build_synthetic_engine(n, dim, dev)
+    torch.manual_seed(7)
+    router = rq.RetrievalRouter().to(dev).eval()
+    router.bm25_mean.fill_(8.0); router.bm25_std.fill_(6.0); router.dense_mean.fill_(0.2); router.dense_std.fill_(0.3)
+    router.stats_initialized = True
+    for batch in (1, 4):
+        gs = engine.graphed_search(router, batch, max_terms=8, k=10, pool=50)
+        for first in (0, 17, 400):
+            qb = synth.make_queries(batch, n, dim, cdf, dev, first_query=first)
+            with torch.no_grad():
+                want = engine.retrieve_and_rerank(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, 10, 50)
+                ids, fused, sb, sd = (t.clone() for t in gs(qb.q_terms, qb.q_off, qb.q_emb))
+            assert torch.equal(ids, want["ids"]) and torch.equal(fused, want["fused"])
+            assert torch.equal(sb, want["bm25"]) and torch.equal(sd, want["dense"])
+        # a ragged batch (3 and 5 tokens ...) goes through the padded static buffers
+        qb = synth.make_queries(batch, n, dim, cdf, dev, first_query=900)
+        lens = [3 + (i % 5) for i in range(batch)]
+        rows = qb.q_terms.view(batch, -1)
+        flat = torch.cat([rows[i, :lens[i]] for i in range(batch)]).contiguous()
+        off = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=dev)
+        with torch.no_grad():
+            want = engine.retrieve_and_rerank(flat, off, 8, qb.q_emb, router, 10, 50)
+            ids, fused, _, _ = gs(flat, off, qb.q_emb)
+        assert torch.equal(ids, want["ids"]) and torch.equal(fused, want["fused"])
+    with pytest.raises(ValueError):
+        engine.graphed_search(router, 9, 8)
+
+
+def test_batched_string_api_tokenizer_and_pool_join(rq, dev, tmp_path):
+    """N3: hybrid_search_many = one tokeniser / vocabulary pass and one device-side pool join for the whole batch; it
+    returns exactly what per-query hybrid_search returns (also when the retriever holds no document for some rows)."""
+    rng = np.random.default_rng(4)
+    words = [f"w{i}" for i in range(300)]
+    texts = [" ".join(rng.choice(words, size=rng.integers(5, 40))) for _ in range(500)]
+    table = {t: rng.standard_normal(64).astype(np.float32) for t in texts}
+    embed = lambda batch: np.stack([table.get(t, np.ones(64, np.float32)) for t in batch])   # noqa: E731
+    r = rq.HybridRetriever(bm25_persist_path=None, chroma_persist_path=None, embed_fn=embed)
+    r.add_documents([rq.Document(id=f"doc{i}", text=t) for i, t in enumerate(texts)])
+    queries = [texts[3], "w1 W2  w2 unknown", "", texts[77][:25], "zzz qqq"] + [texts[i] for i in range(100, 130)]
+    terms, off, longest = r.bm25_index.encode_queries(queries)
+    want_rows = [[r.bm25_index.vocab.get(t, -1) for t in q.lower().split()] for q in queries]
+    assert off.cpu().tolist() == np.concatenate([[0], np.cumsum([len(x) for x in want_rows])]).tolist()
+    assert terms.cpu().tolist()[:int(off[-1])] == [t for row in want_rows for t in row] and longest == max(len(x) for x in want_rows)
+    many = r.hybrid_search_many(queries, None, top_k=10, retrieval_pool_size=50)
+    for q, got in zip(queries, many):
+        one = r.hybrid_search(q, top_k=10, retrieval_pool_size=50)
+        assert [(g.doc_id, g.bm25_score, g.dense_score, g.hybrid_score) for g in got] == \
+            [(g.doc_id, g.bm25_score, g.dense_score, g.hybrid_score) for g in one]
+    # rows the retriever holds no document for are dropped before the fusion (:494-496): forget 100 documents
+    for i in range(0, 500, 5):
+        del r.documents[f"doc{i}"]
+    r.__dict__.pop("_row_number_cache", None)
+    after = r.hybrid_search_many(queries[:8], None, top_k=10)
+    gone = {f"doc{i}" for i in range(0, 500, 5)}
+    assert all(g.doc_id not in gone for res in after for g in res) and any(len(res) for res in after)
 
 
 def test_retrieval_uncertainty(rq, dev):
