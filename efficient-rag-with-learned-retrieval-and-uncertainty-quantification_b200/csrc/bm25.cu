@@ -668,34 +668,45 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
           __syncwarp();
         }
         const __half2 thr2 = __half2half2(__float2half_rd(tk.thr_score - approx_slack));
+        // Terms outside, the (up to) four 256-document ranges of the super-range inside: the four 128-bit loads of a
+        // term are independent, so a lane keeps four requests in flight instead of one (the pass streams the fp16
+        // rows from DRAM and was latency-bound with a single load per lane outstanding).
+        const int n_rng = (s1 - s0 + BM_RANGE - 1) / BM_RANGE;
+        __half2 acc[BM_SUPER][4];
+#pragma unroll
+        for (int r = 0; r < BM_SUPER; ++r)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[r][j] = __float2half2_rn(0.0f);
+        const int64_t off0 = static_cast<int64_t>(s0) + j0;
 #pragma unroll 1
+        for (int i = 0; i < nd; ++i) {
+          const __half2 w2 = __half2half2(__float2half_ru(fmaxf(s_dwgt[i], 0.0f)));
+          const __half* row = s_irow[i] + off0;
+          uint4 v[BM_SUPER];
+#pragma unroll
+          for (int r = 0; r < BM_SUPER; ++r)
+            v[r] = r < n_rng ? __ldg(reinterpret_cast<const uint4*>(row + r * BM_RANGE)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int r = 0; r < BM_SUPER; ++r) {
+            acc[r][0] = __hfma2(w2, *reinterpret_cast<const __half2*>(&v[r].x), acc[r][0]);
+            acc[r][1] = __hfma2(w2, *reinterpret_cast<const __half2*>(&v[r].y), acc[r][1]);
+            acc[r][2] = __hfma2(w2, *reinterpret_cast<const __half2*>(&v[r].z), acc[r][2]);
+            acc[r][3] = __hfma2(w2, *reinterpret_cast<const __half2*>(&v[r].w), acc[r][3]);
+          }
+        }
+#pragma unroll
         for (int r = 0; r < BM_SUPER; ++r) {
-          const int d0 = s0 + r * BM_RANGE;
-          if (d0 >= s1) break;
-          __half2 acc[4];
+          if (r < n_rng) {
+            unsigned m8 = 0u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = __float2half2_rn(0.0f);
-          const int64_t off = static_cast<int64_t>(d0) + j0;
-          uint4 cur = __ldg(reinterpret_cast<const uint4*>(s_irow[0] + off));
-          for (int i = 0; i < nd; ++i) {
-            const __half2 w2 = __half2half2(__float2half_ru(fmaxf(s_dwgt[i], 0.0f)));
-            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-            if (i + 1 < nd) nxt = __ldg(reinterpret_cast<const uint4*>(s_irow[i + 1] + off));
-            acc[0] = __hfma2(w2, *reinterpret_cast<const __half2*>(&cur.x), acc[0]);
-            acc[1] = __hfma2(w2, *reinterpret_cast<const __half2*>(&cur.y), acc[1]);
-            acc[2] = __hfma2(w2, *reinterpret_cast<const __half2*>(&cur.z), acc[2]);
-            acc[3] = __hfma2(w2, *reinterpret_cast<const __half2*>(&cur.w), acc[3]);
-            cur = nxt;
+            for (int j = 0; j < 4; ++j) {
+              const unsigned mk = __hge2_mask(acc[r][j], thr2);   // 0xFFFF per half that passes
+              m8 |= ((mk & 1u) | ((mk >> 15) & 2u)) << (2 * j);
+            }
+            const int left = s1 - (s0 + r * BM_RANGE) - j0;     // documents of this lane that exist
+            if (left < 8) m8 &= left <= 0 ? 0u : ((1u << left) - 1u);
+            if (m8) atomicOr(s_bits + r * (BM_RANGE / 32) + (lane >> 2), m8 << ((lane & 3) * 8));
           }
-          unsigned m8 = 0u;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const unsigned mk = __hge2_mask(acc[j], thr2);   // 0xFFFF per half that passes
-            m8 |= ((mk & 1u) | ((mk >> 15) & 2u)) << (2 * j);
-          }
-          const int left = s1 - d0 - j0;                    // documents of this lane that exist
-          if (left < 8) m8 &= left <= 0 ? 0u : ((1u << left) - 1u);
-          if (m8) atomicOr(s_bits + r * (BM_RANGE / 32) + (lane >> 2), m8 << ((lane & 3) * 8));
         }
         __syncwarp();
         int marks = __popc(s_bits[lane]);

@@ -42,6 +42,8 @@ struct BlockTopK {
   int k;
   int capacity;        // power of two, > k
   uint64_t floor_key;
+  int known;           // *count as of the last reserve() - the same value in every thread of the block
+  bool dirty;          // this thread appended since the last reserve()
 
   __device__ __forceinline__ void init(uint64_t* keys_, int* count_, uint64_t* thr_, int k_, int capacity_,
                                        uint64_t floor_key_) {
@@ -51,6 +53,8 @@ struct BlockTopK {
     k = k_;
     capacity = capacity_;
     floor_key = floor_key_;
+    known = 0;
+    dirty = false;
     for (int i = threadIdx.x; i < capacity; i += NT) keys[i] = 0ull;
     if (threadIdx.x == 0) {
       *count = 0;
@@ -66,17 +70,27 @@ struct BlockTopK {
     if (key > thr) {
       int slot = atomicAdd(count, 1);
       keys[k + slot] = key;
+      dirty = true;
     }
   }
 
   // Block-wide: make room for `incoming` further appends.  Contains barriers.
+  // The flush decision must be block-uniform (flush() has barriers inside), so it is taken on `known`, a register
+  // copy of *count that every thread refreshes at the same point: the vote tells whether anybody appended since
+  // the last call (after warm-up: almost never - one barrier per call); only then is *count re-read, and a second
+  // barrier keeps faster warps from appending again before every thread has read it.  Reading *count right after a
+  // single barrier would let a slow warp see appends of the NEXT round and disagree with the others.
   __device__ __forceinline__ void reserve(int incoming) {
-    __syncthreads();
-    const bool must_flush = *count + incoming > room();
-    // every thread has taken the (therefore block-uniform) decision before the first offer() of a faster warp
-    // moves *count: without this barrier two warps could disagree and meet mismatched barriers inside flush()
-    __syncthreads();
-    if (must_flush) flush();
+    const int any = __syncthreads_or(dirty ? 1 : 0);   // also orders every earlier append before the read below
+    dirty = false;
+    if (any) {
+      known = *count;
+      __syncthreads();
+    }
+    if (known + incoming > room()) {
+      flush();
+      known = 0;
+    }
   }
 
   // Block-wide: fold the appended candidates into the sorted top-k.  Contains barriers;

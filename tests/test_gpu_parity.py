@@ -670,7 +670,9 @@ def test_full_fusion_bound_as_the_kernel_indexes_it(rq, dev, hidden, scale, dens
         g = np.where(d <= b, lo[ib, idx], hi[ib, idx]).astype(np.float32)
         return (g * (d - b) + b).astype(np.float32)
 
-    same = np.isclose(got, bound_at(fb, fd), rtol=1e-6, atol=1e-6)
+    # b + g (d - b) cancels when g is close to 1: the kernel's single-rounding fmaf and numpy's two roundings differ
+    # by up to a few ulp of b (b <= 34: ulp 4e-6)
+    same = np.isclose(got, bound_at(fb, fd), rtol=1e-6, atol=1.2e-5)
     near_line = (np.abs(xd - np.round(xd)) < 1e-4) | (np.abs(xb - np.round(xb)) < 1e-4) | (np.abs(xb - 0.25) < 1e-3)
     assert (same | near_line).all(), f"{int((~(same | near_line)).sum())} pairs read a cell that is not their floor cell"
     assert same.mean() > 0.999
