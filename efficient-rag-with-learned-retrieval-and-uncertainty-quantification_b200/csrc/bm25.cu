@@ -102,6 +102,8 @@ struct Bm25Args {
   const float* dense_maximp; // optional [n_dense]: row maxima of dense_imp (a term contributes at most weight * maximp)
   int window_mode;           // > 0: hash-window mode for the pruned phase, aiming at this many postings per window
   float* seed_thr;           // [queries] proven lower bound of each query's k-th best score (0 = none)
+  int stripe0;               // this launch covers stripes [stripe0, stripe0 + gridDim.y) of n_stripes
+  int n_stripes;
   int debug;
 };
 
@@ -281,7 +283,8 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
   __shared__ int s_dterms[BM_MAX_DENSE];
 
   const int q = blockIdx.x;
-  const int64_t stripe_begin = static_cast<int64_t>(blockIdx.y) * a.stripe_docs;
+  const int stripe = a.stripe0 + static_cast<int>(blockIdx.y);
+  const int64_t stripe_begin = static_cast<int64_t>(stripe) * a.stripe_docs;
   const int64_t stripe_end = min(a.n_docs, stripe_begin + a.stripe_docs);
   const int64_t sub_docs = a.stripe_docs / BM_WARPS;
   const int64_t w_begin = min(stripe_end, stripe_begin + warp * sub_docs);
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
   // fp16 bound pass: every HFMA2 rounds once, |error| <= 2^-11 * (partial sum <= ub_weights)
   const float approx_slack = static_cast<float>(nd) * ub_weights * (1.0f / 2048.0f) * 1.01f + 1e-3f;
 
-  if (a.debug && tid == 0 && blockIdx.y == 0) {
+  if (a.debug && tid == 0 && stripe == 0) {
     if (seed_dbg > 0.0f) atomicAdd(&g_bm25_dbg[4], 1ull);
     if (seed_dbg > ub_table) atomicAdd(&g_bm25_dbg[5], 1ull);
   }
@@ -841,7 +844,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
     }
     __syncthreads();
     bitonic_sort_desc<BM_THREADS>(all_keys, n);
-    uint64_t* dst = a.part_keys + (static_cast<int64_t>(q) * gridDim.y + blockIdx.y) * a.k;
+    uint64_t* dst = a.part_keys + (static_cast<int64_t>(q) * a.n_stripes + stripe) * a.k;
     for (int i = tid; i < a.k; i += BM_THREADS) dst[i] = all_keys[i];
     // publish this stripe's k-th best score (positive floats order like their bit patterns)
     if (tid == 0 && all_keys[a.k - 1] != 0ull) {
@@ -1274,24 +1277,21 @@ int ragb_bm25_seed(const int64_t* term_off, const int32_t* post_doc, const uint1
   return RAGB_OK;
 }
 
-int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
-                         const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
-                         const int32_t* dense_terms, int32_t n_dense, const uint16_t* dense_imp_fp16,
-                         const float* dense_max_imp, const int32_t* q_terms, const int32_t* q_off,
-                         int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
-                         const float* seed_thr, float* out_score, int32_t* out_id, void* workspace,
-                         size_t workspace_bytes, ragb_stream_t stream_) {
-  RAGB_ENTRY();
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int rc = bm25_common_checks("ragb_bm25_score_topk", term_off, post_doc, post_tf, norm, idf, vocab, q_terms, q_off,
-                              n_queries, n_docs, max_query_terms, dense_tf, dense_stride, dense_terms, n_dense);
+// Argument block shared by the one-call and the staged form of the top-k search.
+static int bm25_topk_args(const char* who, Bm25Args& a, int* stripes_out, const int64_t* term_off, const int32_t* post_doc,
+                          const uint16_t* post_tf, const float* norm, const float* idf, int64_t vocab, double k1,
+                          const uint8_t* dense_tf, int64_t dense_stride, const int32_t* dense_terms, int32_t n_dense,
+                          const uint16_t* dense_imp_fp16, const float* dense_max_imp, const int32_t* q_terms,
+                          const int32_t* q_off, int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base,
+                          int32_t k, void* workspace, size_t workspace_bytes) {
+  int rc = bm25_common_checks(who, term_off, post_doc, post_tf, norm, idf, vocab, q_terms, q_off, n_queries, n_docs,
+                              max_query_terms, dense_tf, dense_stride, dense_terms, n_dense);
   if (rc != RAGB_OK) return rc;
-  RAGB_REQUIRE(out_score && out_id && workspace, RAGB_EINVAL, "ragb_bm25_score_topk: null pointer");
-  RAGB_REQUIRE(k > 0 && k <= RAGB_MAX_TOPK, RAGB_ELIMIT, "ragb_bm25_score_topk: k=%d outside [1,%d]", k, RAGB_MAX_TOPK);
-  RAGB_REQUIRE(id_base >= 0 && id_base + n_docs < (1ll << 31), RAGB_ELIMIT, "ragb_bm25_score_topk: ids must fit int32");
-  RAGB_REQUIRE(workspace_bytes >= ragb_bm25_topk_workspace_bytes(n_queries, n_docs, k), RAGB_ENOSPC,
-               "ragb_bm25_score_topk: workspace too small");
-  Bm25Args a{};
+  RAGB_REQUIRE(workspace, RAGB_EINVAL, "%s: null pointer", who);
+  RAGB_REQUIRE(k > 0 && k <= RAGB_MAX_TOPK, RAGB_ELIMIT, "%s: k=%d outside [1,%d]", who, k, RAGB_MAX_TOPK);
+  RAGB_REQUIRE(id_base >= 0 && id_base + n_docs < (1ll << 31), RAGB_ELIMIT, "%s: ids must fit int32", who);
+  RAGB_REQUIRE(workspace_bytes >= ragb_bm25_topk_workspace_bytes(n_queries, n_docs, k), RAGB_ENOSPC, "%s: workspace too small", who);
+  a = Bm25Args{};
   a.term_off = term_off;
   a.post_doc = post_doc;
   a.post_tf = post_tf;
@@ -1308,10 +1308,9 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   a.dense_terms = dense_terms;
   a.dense_stride = dense_stride;
   a.n_dense = n_dense;
-  RAGB_REQUIRE((dense_imp_fp16 == nullptr) == (dense_max_imp == nullptr), RAGB_EINVAL,
-               "ragb_bm25_score_topk: dense_imp_fp16 and dense_max_imp go together");
+  RAGB_REQUIRE((dense_imp_fp16 == nullptr) == (dense_max_imp == nullptr), RAGB_EINVAL, "%s: dense_imp_fp16 and dense_max_imp go together", who);
   RAGB_REQUIRE(dense_imp_fp16 == nullptr || (n_dense > 0 && (reinterpret_cast<uintptr_t>(dense_imp_fp16) & 15) == 0),
-               RAGB_EINVAL, "ragb_bm25_score_topk: dense_imp_fp16 needs the dense table and 16-byte alignment");
+               RAGB_EINVAL, "%s: dense_imp_fp16 needs the dense table and 16-byte alignment", who);
   a.dense_imp = reinterpret_cast<const __half*>(dense_imp_fp16);
   a.dense_maximp = dense_max_imp;
   a.k = k;
@@ -1319,25 +1318,107 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   a.part_keys = static_cast<uint64_t*>(workspace);
   a.out_scores = nullptr;
   const int stripes = bm25_stripes(n_queries, n_docs, &a.stripe_docs);
+  a.n_stripes = stripes;
   a.seed_thr = reinterpret_cast<float*>(a.part_keys + static_cast<size_t>(n_queries) * stripes * k);
   static const int debug_flag = [] { const char* e = getenv("RAGB_BM25_DEBUG"); return e ? atoi(e) : 0; }();
   a.debug = debug_flag;
   // postings aimed at per window (0 turns window mode off); tuning aid, the default is what was measured best
   static const int window_flag = [] { const char* e = getenv("RAGB_BM25_WINDOW"); return e ? atoi(e) : 256; }();
   a.window_mode = window_flag;
+  *stripes_out = stripes;
+  return RAGB_OK;
+}
+
+// seeds for a search: the caller's bounds (copied, the kernel raises its private copy) or the seed kernel
+static int bm25_init_seeds(const Bm25Args& a, const float* seed_thr, int n_queries, cudaStream_t stream) {
   if (seed_thr != nullptr) {
-    // bounds proven elsewhere (ragb_bm25_seed, possibly raised to the maximum over all shards): the kernel keeps
-    // raising its private copy, the caller's array stays untouched
     RAGB_CUDA(cudaMemcpyAsync(a.seed_thr, seed_thr, sizeof(float) * n_queries, cudaMemcpyDeviceToDevice, stream));
   } else {
     bm25_seed_kernel<<<n_queries, SEED_THREADS, 0, stream>>>(a);
     RAGB_AFTER_LAUNCH(1);
   }
-  const size_t smem = bm25_smem_bytes(a.max_terms, a.capacity, false);
-  RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  bm25_kernel<false><<<dim3(n_queries, stripes), BM_THREADS, smem, stream>>>(a);
+  return RAGB_OK;
+}
+
+// the scoring kernel over stripes [s0, s1); shared memory per block padded to at least min_smem bytes (0 = natural)
+static int bm25_launch_stripes(Bm25Args a, int n_queries, int s0, int s1, size_t min_smem, cudaStream_t stream) {
+  if (s1 <= s0) return RAGB_OK;
+  size_t smem = bm25_smem_bytes(a.max_terms, a.capacity, false);
+  if (min_smem > smem) smem = min_smem;
+  RAGB_REQUIRE(smem <= 200 * 1024, RAGB_ELIMIT, "ragb_bm25_score_part: shared-memory padding %zu too large", smem);
+  a.stripe0 = s0;
+  RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  bm25_kernel<false><<<dim3(n_queries, s1 - s0), BM_THREADS, smem, stream>>>(a);
   RAGB_AFTER_LAUNCH(1);
+  return RAGB_OK;
+}
+
+int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
+                         const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
+                         const int32_t* dense_terms, int32_t n_dense, const uint16_t* dense_imp_fp16,
+                         const float* dense_max_imp, const int32_t* q_terms, const int32_t* q_off,
+                         int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
+                         const float* seed_thr, float* out_score, int32_t* out_id, void* workspace,
+                         size_t workspace_bytes, ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(out_score && out_id, RAGB_EINVAL, "ragb_bm25_score_topk: null pointer");
+  Bm25Args a;
+  int stripes = 0;
+  int rc = bm25_topk_args("ragb_bm25_score_topk", a, &stripes, term_off, post_doc, post_tf, norm, idf, vocab, k1, dense_tf,
+                          dense_stride, dense_terms, n_dense, dense_imp_fp16, dense_max_imp, q_terms, q_off, n_queries,
+                          max_query_terms, n_docs, id_base, k, workspace, workspace_bytes);
+  if (rc != RAGB_OK) return rc;
+  rc = bm25_init_seeds(a, seed_thr, n_queries, stream);
+  if (rc != RAGB_OK) return rc;
+  rc = bm25_launch_stripes(a, n_queries, 0, stripes, 0, stream);
+  if (rc != RAGB_OK) return rc;
   return launch_merge_keys(a.part_keys, n_queries, stripes, k, k, out_score, out_id, stream);
+}
+
+int32_t ragb_bm25_stripe_count(int32_t n_queries, int64_t n_docs) {
+  if (n_queries <= 0 || n_docs <= 0) return 0;
+  int64_t stripe_docs;
+  return bm25_stripes(n_queries, n_docs, &stripe_docs);
+}
+
+int ragb_bm25_score_part(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
+                         const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
+                         const int32_t* dense_terms, int32_t n_dense, const uint16_t* dense_imp_fp16,
+                         const float* dense_max_imp, const int32_t* q_terms, const int32_t* q_off,
+                         int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
+                         const float* seed_thr, int32_t stripe_begin, int32_t stripe_end, int64_t min_smem_bytes,
+                         void* workspace, size_t workspace_bytes, ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Bm25Args a;
+  int stripes = 0;
+  int rc = bm25_topk_args("ragb_bm25_score_part", a, &stripes, term_off, post_doc, post_tf, norm, idf, vocab, k1, dense_tf,
+                          dense_stride, dense_terms, n_dense, dense_imp_fp16, dense_max_imp, q_terms, q_off, n_queries,
+                          max_query_terms, n_docs, id_base, k, workspace, workspace_bytes);
+  if (rc != RAGB_OK) return rc;
+  RAGB_REQUIRE(0 <= stripe_begin && stripe_begin <= stripe_end && stripe_end <= stripes, RAGB_EINVAL,
+               "ragb_bm25_score_part: stripes [%d, %d) outside [0, %d]", stripe_begin, stripe_end, stripes);
+  RAGB_REQUIRE(min_smem_bytes >= 0, RAGB_EINVAL, "ragb_bm25_score_part: negative shared-memory padding");
+  if (stripe_begin == 0) {   // the part that starts the search also starts the thresholds
+    rc = bm25_init_seeds(a, seed_thr, n_queries, stream);
+    if (rc != RAGB_OK) return rc;
+  }
+  return bm25_launch_stripes(a, n_queries, stripe_begin, stripe_end, static_cast<size_t>(min_smem_bytes), stream);
+}
+
+int ragb_bm25_score_finish(int32_t n_queries, int64_t n_docs, int32_t k, float* out_score, int32_t* out_id,
+                           const void* workspace, size_t workspace_bytes, ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(out_score && out_id && workspace, RAGB_EINVAL, "ragb_bm25_score_finish: null pointer");
+  RAGB_REQUIRE(n_queries > 0 && n_docs > 0 && k > 0 && k <= RAGB_MAX_TOPK, RAGB_EINVAL, "ragb_bm25_score_finish: bad shape");
+  RAGB_REQUIRE(workspace_bytes >= ragb_bm25_topk_workspace_bytes(n_queries, n_docs, k), RAGB_ENOSPC,
+               "ragb_bm25_score_finish: workspace too small");
+  int64_t stripe_docs;
+  const int stripes = bm25_stripes(n_queries, n_docs, &stripe_docs);
+  return launch_merge_keys(static_cast<const uint64_t*>(workspace), n_queries, stripes, k, k, out_score, out_id, stream);
 }
 
 int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,

@@ -12,6 +12,8 @@
 // a full SM keeps ~100 KB in flight, multiplies against the queries held in shared memory
 // as fp32, and reduces with shuffles.  Scores go straight into the block's running top-k
 // (one per query); the score vector never exists in memory.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "topk.cuh"
 
@@ -27,7 +29,8 @@ template <int NQ, int CHUNKS>  // CHUNKS = ceil(dim / 256): 16-byte loads per la
 __global__ void __launch_bounds__(GV_THREADS) gemv_topk_kernel(const uint4* __restrict__ passages, int64_t n_rows,
                                                                int dim, const __nv_bfloat16* __restrict__ queries,
                                                                int k, int capacity, int64_t id_base,
-                                                               int64_t rows_per_block,
+                                                               int64_t row_first, int64_t rows_per_block,
+                                                               const float* __restrict__ seed_thr,
                                                                uint64_t* __restrict__ part_keys) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_q = reinterpret_cast<float*>(smem_raw);                                 // [NQ][dim]
@@ -39,10 +42,20 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_topk_kernel(const uint4* __re
   for (int i = tid; i < NQ * dim; i += GV_THREADS) s_q[i] = __bfloat162float(queries[i]);
   BlockTopK<GV_THREADS> tk[NQ];
 #pragma unroll
-  for (int qi = 0; qi < NQ; ++qi) tk[qi].init(s_keys + qi * capacity, &s_count[qi], &s_thr[qi], k, capacity, 0ull);
+  for (int qi = 0; qi < NQ; ++qi) {
+    // a proven lower bound of the query's k-th best score (the k-th best of the sampled prefix) as the floor of the
+    // selection: nothing below it is ever appended, so after the prefix a block appends a handful of candidates and
+    // never sorts before the end (an equal score still passes: the id bits of a key are never all zero)
+    uint64_t floor_key = 0ull;
+    if (seed_thr != nullptr) {
+      const float seed = __ldg(seed_thr + qi);
+      if (seed > -INFINITY) floor_key = static_cast<uint64_t>(float_to_ordered(seed)) << 32;
+    }
+    tk[qi].init(s_keys + qi * capacity, &s_count[qi], &s_thr[qi], k, capacity, floor_key);
+  }
 
   const int vec_per_row = dim >> 3;
-  const int64_t begin = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  const int64_t begin = row_first + static_cast<int64_t>(blockIdx.x) * rows_per_block;
   const int64_t end = min(n_rows, begin + rows_per_block);
 
   for (int64_t tile = begin; tile < end; tile += GV_TILE) {
@@ -52,6 +65,7 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_topk_kernel(const uint4* __re
 #pragma unroll
     for (int qi = 0; qi < NQ; ++qi) thr[qi] = s_thr[qi];
 
+    bool appended = false;   // this thread appended to SOME query's list in this tile (reserve() must hear about it)
     for (int r0 = warp * GV_ROWS_PER_WARP; r0 < GV_TILE; r0 += GV_WARPS * GV_ROWS_PER_WARP) {
       const int64_t row0 = tile + r0;
       if (row0 >= end) break;
@@ -128,10 +142,13 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_topk_kernel(const uint4* __re
           if (key > t) {
             const int slot = atomicAdd(&s_count[slot_q], 1);
             s_keys[slot_q * capacity + k + slot] = key;
+            appended = true;
           }
         }
       }
     }
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) tk[qi].dirty |= appended;
   }
 #pragma unroll
   for (int qi = 0; qi < NQ; ++qi) tk[qi].finish();
@@ -168,11 +185,12 @@ __global__ void __launch_bounds__(256) dense_scores_kernel(const uint4* __restri
 static int gemv_grid() { return device_sm_count() * 4; }
 
 template <int NQ>
-static int launch_gemv(const void* passages, int64_t n_rows, int dim, const void* queries, int k, int64_t id_base,
-                       uint64_t* part, int grid, cudaStream_t stream) {
+static int launch_gemv(const void* passages, int64_t row_first, int64_t n_rows, int dim, const void* queries, int k,
+                       int64_t id_base, const float* seed_thr, uint64_t* part, int grid, cudaStream_t stream) {
+  // scores rows [row_first, n_rows) with `grid` blocks
   const int capacity = topk_capacity(k);
   const size_t smem = sizeof(float) * NQ * dim + sizeof(uint64_t) * NQ * capacity;
-  const int64_t rows_per_block = ceil_div64(n_rows, grid);
+  const int64_t rows_per_block = ceil_div64(n_rows - row_first, grid);
   const int chunks = (dim + 255) / 256;
 #define RAGB_GEMV_CASE(C)                                                                                          \
   case C: {                                                                                                        \
@@ -180,7 +198,8 @@ static int launch_gemv(const void* passages, int64_t n_rows, int dim, const void
                                    static_cast<int>(smem)));                                                       \
     gemv_topk_kernel<NQ, C><<<grid, GV_THREADS, smem, stream>>>(static_cast<const uint4*>(passages), n_rows, dim,  \
                                                                  static_cast<const __nv_bfloat16*>(queries), k,    \
-                                                                 capacity, id_base, rows_per_block, part);         \
+                                                                 capacity, id_base, row_first, rows_per_block,     \
+                                                                 seed_thr, part);                                  \
     break;                                                                                                         \
   }
   switch (chunks) {
@@ -204,9 +223,39 @@ using namespace ragb;
 
 extern "C" {
 
+// workspace: [n_queries, <= 148 * 4, k] block lists, [n_queries, k] merged list of the sampled prefix, [n_queries] bounds
 size_t ragb_dense_gemv_workspace_bytes(int32_t n_queries, int32_t k) {
   if (n_queries <= 0 || k <= 0) return 0;
-  return static_cast<size_t>(n_queries) * 148 * 4 * k * sizeof(uint64_t);
+  return static_cast<size_t>(n_queries) * (148 * 4 + 1) * k * sizeof(uint64_t) + static_cast<size_t>(n_queries) * sizeof(float);
+}
+
+// one pass over rows [row_first, row_last) for all queries (groups of 4 / 2 / 1: register budget); -> grid used
+static int gemv_pass(const void* passages, int64_t row_first, int64_t row_last, int dim, const __nv_bfloat16* q, int n_queries,
+                     int k, int64_t id_base, const float* seed_thr, uint64_t* part, int* grid_out, cudaStream_t stream) {
+  int grid = gemv_grid();
+  if (grid > 148 * 4) grid = 148 * 4;
+  const int64_t max_blocks = ceil_div64(row_last - row_first, GV_WARPS * GV_ROWS_PER_WARP);
+  if (grid > max_blocks) grid = static_cast<int>(max_blocks);
+  *grid_out = grid;
+  int done = 0;
+  int rc = RAGB_OK;
+  while (done < n_queries && rc == RAGB_OK) {
+    const int left = n_queries - done;
+    uint64_t* dst = part + static_cast<int64_t>(done) * grid * k;
+    const __nv_bfloat16* qg = q + static_cast<int64_t>(done) * dim;
+    const float* sg = seed_thr != nullptr ? seed_thr + done : nullptr;
+    if (left >= 4) {
+      rc = launch_gemv<4>(passages, row_first, row_last, dim, qg, k, id_base, sg, dst, grid, stream);
+      done += 4;
+    } else if (left >= 2) {
+      rc = launch_gemv<2>(passages, row_first, row_last, dim, qg, k, id_base, sg, dst, grid, stream);
+      done += 2;
+    } else {
+      rc = launch_gemv<1>(passages, row_first, row_last, dim, qg, k, id_base, sg, dst, grid, stream);
+      done += 1;
+    }
+  }
+  return rc;
 }
 
 int ragb_dense_gemv_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
@@ -225,33 +274,36 @@ int ragb_dense_gemv_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
                RAGB_GEMV_MAX_BATCH);
   RAGB_REQUIRE(k > 0 && k <= RAGB_MAX_TOPK, RAGB_ELIMIT, "ragb_dense_gemv_topk: k=%d outside [1,%d]", k, RAGB_MAX_TOPK);
   RAGB_REQUIRE(id_base >= 0 && id_base + n_rows < (1ll << 31), RAGB_ELIMIT, "ragb_dense_gemv_topk: ids must fit int32");
-  int grid = gemv_grid();
-  if (grid > 148 * 4) grid = 148 * 4;
-  const int64_t max_blocks = ceil_div64(n_rows, GV_WARPS * GV_ROWS_PER_WARP);
-  if (grid > max_blocks) grid = static_cast<int>(max_blocks);
-  RAGB_REQUIRE(workspace_bytes >= static_cast<size_t>(n_queries) * grid * k * sizeof(uint64_t), RAGB_ENOSPC,
+  RAGB_REQUIRE(workspace_bytes >= ragb_dense_gemv_workspace_bytes(n_queries, k), RAGB_ENOSPC,
                "ragb_dense_gemv_topk: workspace too small");
   uint64_t* part = static_cast<uint64_t*>(workspace);
-  // queries are processed in groups of 1, 2 or 4 (register budget); passages are re-read per group
-  int done = 0;
-  int rc = RAGB_OK;
+  uint64_t* sample_keys = part + static_cast<size_t>(n_queries) * 148 * 4 * k;
+  float* thr = reinterpret_cast<float*>(sample_keys + static_cast<size_t>(n_queries) * k);
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(queries_bf16);
-  while (done < n_queries && rc == RAGB_OK) {
-    const int left = n_queries - done;
-    uint64_t* dst = part + static_cast<int64_t>(done) * grid * k;
-    if (left >= 4) {
-      rc = launch_gemv<4>(passages_bf16, n_rows, dim, q + static_cast<int64_t>(done) * dim, k, id_base, dst, grid, stream);
-      done += 4;
-    } else if (left >= 2) {
-      rc = launch_gemv<2>(passages_bf16, n_rows, dim, q + static_cast<int64_t>(done) * dim, k, id_base, dst, grid, stream);
-      done += 2;
-    } else {
-      rc = launch_gemv<1>(passages_bf16, n_rows, dim, q + static_cast<int64_t>(done) * dim, k, id_base, dst, grid, stream);
-      done += 1;
-    }
+  // Sampled prefix (as in ragb_dense_mma_topk): the k-th best score of the first 1/32 of the rows is a proven lower
+  // bound of the final k-th best and becomes the floor of every block's selection over the remaining rows.  Without
+  // it every block appends its first 512 rows unconditionally and sorts 1024 keys with block barriers two or three
+  // times before its threshold settles: at 1M rows (2.5 MB per block) that warm-up costs a quarter of the kernel.
+  static const int sample_div = [] {
+    const char* e = getenv("RAGB_GEMV_SAMPLE_DIV");   // tuning aid: 0 = no sampled prefix
+    return e ? atoi(e) : 32;
+  }();
+  int64_t prefix = (sample_div > 0 && n_rows >= 262144) ? (n_rows / sample_div) / 32 * 32 : 0;
+  if (prefix < 4 * static_cast<int64_t>(k)) prefix = 0;
+  int grid = 0;
+  int rc;
+  const float* seed = nullptr;
+  if (prefix > 0) {
+    rc = gemv_pass(passages_bf16, 0, prefix, dim, q, n_queries, k, id_base, nullptr, part, &grid, stream);
+    if (rc != RAGB_OK) return rc;
+    rc = launch_merge_keys_ex(part, n_queries, grid, k, nullptr, 0, k, nullptr, nullptr, sample_keys, thr, stream);
+    if (rc != RAGB_OK) return rc;
+    seed = thr;
   }
+  rc = gemv_pass(passages_bf16, prefix, n_rows, dim, q, n_queries, k, id_base, seed, part, &grid, stream);
   if (rc != RAGB_OK) return rc;
-  return launch_merge_keys(part, n_queries, grid, k, k, out_score, out_id, stream);
+  return launch_merge_keys_ex(part, n_queries, grid, k, prefix > 0 ? sample_keys : nullptr, k, k, out_score, out_id, nullptr,
+                              nullptr, stream);
 }
 
 int ragb_dense_scores(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,

@@ -1232,7 +1232,9 @@ static MmaWorkspace mma_carve(void* workspace, int n_queries, int k) {
 static int mma_dispatch(int variant, const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries,
                         int k, int64_t id_base, const MmaRange& r, const MmaWorkspace& w, cudaStream_t stream) {
   const int kpl = mma_list_kpl(k);
-  const int sl = mma_stage_limit();
+  // variant 4 = variant 3 with a 4-stage operand ring (129 KB instead of 225 KB of shared memory per block): measured
+  // as fast as the full ring, and it leaves room for one block of another kernel on the same SM (two-stream overlap)
+  const int sl = variant == 4 ? 4 : mma_stage_limit();
 #define RAGB_MMA_ARGS passages, n_rows, dim, queries, n_queries, k, id_base, r, w.progress, w.lists, sl, stream
 #define RAGB_MMA_DISPATCH(FN, ...)                                         \
   do {                                                                    \
@@ -1250,7 +1252,7 @@ static int mma_dispatch(int variant, const void* passages, int64_t n_rows, int d
 #undef RAGB_MMA_ARGS
 }
 static int mma_tile_rows(int variant) { return variant == 0 ? 128 : (variant == 1 ? 64 : 256); }
-static bool mma_uses_pairs(int variant, int n_queries) { return variant == 3 && n_queries > MM_BM; }
+static bool mma_uses_pairs(int variant, int n_queries) { return variant >= 3 && n_queries > MM_BM; }
 
 static int mma_common_checks(const char* who, const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
                              int32_t n_queries, int32_t k, int64_t id_base, int32_t variant, const void* workspace,
@@ -1261,7 +1263,7 @@ static int mma_common_checks(const char* who, const void* passages_bf16, int64_t
   RAGB_REQUIRE(n_rows > 0 && n_queries > 0, RAGB_EINVAL, "%s: empty shape", who);
   RAGB_REQUIRE(dim >= MM_BK && dim % MM_BK == 0, RAGB_EINVAL, "%s: dim=%d must be a multiple of %d", who, dim, MM_BK);
   RAGB_REQUIRE(k > 0 && k <= 100, RAGB_ELIMIT, "%s: k=%d outside [1,100]", who, k);
-  RAGB_REQUIRE(variant >= 0 && variant <= 3, RAGB_EINVAL, "%s: variant must be 0, 1, 2 or 3", who);
+  RAGB_REQUIRE(variant >= 0 && variant <= 4, RAGB_EINVAL, "%s: variant must be 0, 1, 2, 3 or 4", who);
   RAGB_REQUIRE(variant != 1 || dim <= 768, RAGB_ELIMIT, "%s: variant 1 keeps the query slab in TMEM and needs dim <= 768", who);
   RAGB_REQUIRE(id_base >= 0 && id_base + n_rows < (1ll << 31), RAGB_ELIMIT, "%s: ids must fit int32", who);
   RAGB_REQUIRE(workspace_bytes >= mma_workspace_bytes(n_queries, k), RAGB_ENOSPC, "%s: workspace too small", who);

@@ -14,6 +14,7 @@ it runs after the merge.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -22,6 +23,10 @@ from torch import Tensor
 
 from . import _lib, ops
 from .sparse import SparseShard
+
+
+OVERLAP_FRACTION = float(os.environ.get("RAGB_OVERLAP_FRACTION", "1.0"))   # share of the BM25 stripes scored beside the GEMM
+OVERLAP_SMEM_PAD = int(os.environ.get("RAGB_OVERLAP_SMEM_KB", "0")) * 1024     # shared memory per BM25 block while it is
 
 
 def shard_rows(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
@@ -146,22 +151,47 @@ class HybridEngine:
             if events is not None:
                 events["bm25"], events["dense"] = (t0, t1), (t1, mark())
             return bs, bi, ds, di
+        # ---- two streams, co-resident blocks -------------------------------------------------------------------
+        # The tensor-core kernel needs one 320-thread block per SM, ~38k registers and (with a 4-stage operand ring)
+        # 129 KB of shared memory: what is left of an SM hosts exactly one 8-warp BM25 block if that block's shared
+        # memory is padded to ~96 KB (two of them no longer fit).  So the search is staged: the first stripes of the
+        # BM25 search run NEXT TO the GEMM (one block per SM, a third of the kernel's usual residency), the remaining
+        # stripes after it at full residency, starting from the thresholds the first part has proven.  The dense
+        # kernel's stream has the higher priority and its main kernel becomes eligible (event after the sampled
+        # prefix) when the padded BM25 part does, so the GEMM blocks are placed first.
+        if not isinstance(self.sparse, SparseShard):
+            raise NotImplementedError("overlap=True needs a single-segment BM25 shard")
+        dev = q_emb.device
         if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream(device=q_emb.device)
+            self._side_stream = torch.cuda.Stream(device=dev, priority=-1)
         side = self._side_stream
+        n_q, n_docs = q_emb.shape[0], self.sparse.n_docs
+        stripes = ops.bm25_stripe_count(n_q, n_docs)
+        first = min(stripes, max(0, int(round(stripes * OVERLAP_FRACTION))))
+        ws = ops.bm25_workspace(n_q, n_docs, pool, dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             d0 = mark() if events is not None else None
-            ds, di = self.dense_local_topk(q_emb, pool)
+            variant = 4 if self.mma_variant == 3 else self.mma_variant      # 4-stage ring: room for a co-resident block
+            d_thr, d_ws = ops.dense_mma_sample(self.passages, q_emb, pool, self.id_base, variant)
+            prefix_done = torch.cuda.Event()
+            prefix_done.record()
+            ds, di = ops.dense_mma_seeded(self.passages, q_emb, pool, self.id_base, variant, d_thr, d_ws)
             d1 = mark() if events is not None else None
         b0 = mark() if events is not None else None
-        bs, bi = self.sparse.score_topk(q_terms, q_off, max_terms, pool)
-        b1 = mark() if events is not None else None
+        cur.wait_event(prefix_done)
+        self.sparse.score_part(q_terms, q_off, max_terms, pool, ws, 0, first, OVERLAP_SMEM_PAD if first < stripes else 0)
+        bmid = mark() if events is not None else None
         cur.wait_stream(side)
-        ds.record_stream(cur)
-        di.record_stream(cur)
+        if first < stripes:
+            self.sparse.score_part(q_terms, q_off, max_terms, pool, ws, first, stripes, 0)
+        bs, bi = ops.bm25_score_finish(n_q, n_docs, pool, ws)
+        b1 = mark() if events is not None else None
+        for t in (ds, di, d_ws):
+            t.record_stream(cur)
+        ws.record_stream(side)
         if events is not None:
-            events["bm25"], events["dense"] = (b0, b1), (d0, d1)
+            events["bm25"], events["dense"], events["bm25_beside_dense"] = (b0, b1), (d0, d1), (b0, bmid)
         return bs, bi, ds, di
 
     def hybrid_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, k: int = 10,

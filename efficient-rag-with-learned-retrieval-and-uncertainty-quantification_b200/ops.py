@@ -191,6 +191,54 @@ def _(term_off, post_doc, post_tf, norm, idf, k1, dense_tf, dense_terms, dense_i
     return norm.new_empty((n_q, k)), norm.new_empty((n_q, k), dtype=torch.int32)
 
 
+def bm25_stripe_count(n_queries: int, n_docs: int) -> int:
+    """Stripes ``bm25_score_part`` cuts the documents of a shard into for a batch of n_queries (ragb200.h)."""
+    return int(lib.ragb_bm25_stripe_count(n_queries, n_docs))
+
+
+def bm25_workspace(n_queries: int, n_docs: int, k: int, device) -> Tensor:
+    return _workspace(lib.ragb_bm25_topk_workspace_bytes(n_queries, n_docs, k), device)
+
+
+@torch.library.custom_op(f"{NS}::bm25_score_part", mutates_args=("workspace",), device_types="cuda")
+def bm25_score_part(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
+                    dense_tf: Tensor, dense_terms: Tensor, dense_imp: Tensor, dense_maximp: Tensor, q_terms: Tensor,
+                    q_off: Tensor, max_query_terms: int, id_base: int, k: int, seed: Tensor, stripe_begin: int,
+                    stripe_end: int, min_smem_bytes: int, workspace: Tensor) -> None:
+    """Score the stripes [stripe_begin, stripe_end) of the staged BM25 search into ``workspace`` (ragb200.h)."""
+    term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
+                                                                        q_terms, q_off)
+    n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
+    dt, stride, dterms, n_dense = _dense_table(dense_tf, dense_terms, n_docs)
+    imp, maximp = None, None
+    if n_dense and dense_imp.numel() and dense_maximp.numel():
+        imp = _need(dense_imp, torch.float16, "dense_imp").data_ptr()
+        maximp = _need(dense_maximp, torch.float32, "dense_maximp").data_ptr()
+    seed_ptr = _need(seed, torch.float32, "seed").data_ptr() if seed.numel() else None
+    with torch.cuda.device(dev):
+        check(lib.ragb_bm25_score_part(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf), idf.shape[0], k1,
+                                       dt, stride, dterms, n_dense, imp, maximp, _ptr(q_terms), _ptr(q_off), n_q,
+                                       max_query_terms, n_docs, id_base, k, seed_ptr, stripe_begin, stripe_end,
+                                       min_smem_bytes, _ptr(workspace), workspace.numel(), _stream()))
+
+
+@torch.library.custom_op(f"{NS}::bm25_score_finish", mutates_args=(), device_types="cuda")
+def bm25_score_finish(n_queries: int, n_docs: int, k: int, workspace: Tensor) -> Tuple[Tensor, Tensor]:
+    """Merge all stripes of a staged BM25 search: -> (score [B,k], ids [B,k])."""
+    dev = workspace.device
+    score = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((n_queries, k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.ragb_bm25_score_finish(n_queries, n_docs, k, _ptr(score), _ptr(ids), _ptr(workspace), workspace.numel(),
+                                         _stream()))
+    return score, ids
+
+
+@bm25_score_finish.register_fake
+def _(n_queries, n_docs, k, workspace):
+    return workspace.new_empty((n_queries, k), dtype=torch.float32), workspace.new_empty((n_queries, k), dtype=torch.int32)
+
+
 @torch.library.custom_op(f"{NS}::bm25_seed", mutates_args=(), device_types="cuda")
 def bm25_seed(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
               dense_tf: Tensor, dense_terms: Tensor, q_terms: Tensor, q_off: Tensor, max_query_terms: int,

@@ -132,6 +132,16 @@ class SparseShard:
                                    self.dense_tf, self.dense_terms, self.dense_imp, self.dense_maximp, q_terms, q_off,
                                    max_terms, self.id_base, k, seed)
 
+    def score_part(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int, workspace: Tensor, stripe_begin: int,
+                   stripe_end: int, min_smem_bytes: int = 0, seed: Optional[Tensor] = None) -> None:
+        """Stripes [stripe_begin, stripe_end) of the staged search (``ops.bm25_stripe_count`` stripes in all; the part
+        starting at 0 first; ``ops.bm25_score_finish`` merges)."""
+        if seed is None:
+            seed = torch.empty(0, dtype=torch.float32, device=self.post_doc.device)
+        ops.bm25_score_part(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1, self.dense_tf,
+                            self.dense_terms, self.dense_imp, self.dense_maximp, q_terms, q_off, max_terms, self.id_base, k,
+                            seed, stripe_begin, stripe_end, min_smem_bytes, workspace)
+
     def seed(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int) -> Tensor:
         """Proven lower bounds [B] of the k-th best score of every query over this shard (ragb_bm25_seed)."""
         return ops.bm25_seed(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1, self.dense_tf,

@@ -116,6 +116,25 @@ int ragb_bm25_seed(const int64_t* term_off, const int32_t* post_doc, const uint1
                    const int32_t* dense_terms, int32_t n_dense,
                    const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
                    int32_t max_query_terms, int64_t n_docs, int32_t k, float* seed_out, ragb_stream_t stream);
+/* The same search in stages, for a caller that overlaps it with another kernel (HybridEngine, --overlap): the
+ * documents are cut into ragb_bm25_stripe_count(n_queries, n_docs) stripes; ragb_bm25_score_part scores the stripes
+ * [stripe_begin, stripe_end) into the workspace (the part with stripe_begin == 0 must come first: it also installs the
+ * thresholds, from seed_thr or the seed kernel); ragb_bm25_score_finish merges all stripes once every one of them has
+ * been scored.  min_smem_bytes pads the shared memory of every block (0 = natural size): a padding of ~96 KB leaves
+ * room for exactly one such block next to a resident 4-stage ragb_dense_mma_* block on every SM.  Parts that are
+ * scored later start from the thresholds the earlier parts have proven.  Results equal ragb_bm25_score_topk. */
+int32_t ragb_bm25_stripe_count(int32_t n_queries, int64_t n_docs);
+int ragb_bm25_score_part(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf,
+                         const float* norm, const float* idf, int64_t vocab, double k1,
+                         const uint8_t* dense_tf, int64_t dense_stride,
+                         const int32_t* dense_terms, int32_t n_dense,
+                         const uint16_t* dense_imp_fp16, const float* dense_max_imp,
+                         const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
+                         int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
+                         const float* seed_thr, int32_t stripe_begin, int32_t stripe_end, int64_t min_smem_bytes,
+                         void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+int ragb_bm25_score_finish(int32_t n_queries, int64_t n_docs, int32_t k, float* out_score, int32_t* out_id,
+                           const void* workspace, size_t workspace_bytes, ragb_stream_t stream);
 /* Same arithmetic, full score vectors (get_scores itself).
  * tiled = 0: out_scores[q * out_ld + d], out_ld >= n_docs (row-major).
  * tiled = 1: out_scores[((d / 256) * out_ld + q) * 256 + d % 256], out_ld >= n_queries: 256-document tiles

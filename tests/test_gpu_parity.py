@@ -342,6 +342,38 @@ def test_bm25_shards_with_global_statistics_equal_unsharded(rq, dev):
     assert torch.equal(mi2, wi) and torch.equal(ms2, ws)
 
 
+def test_bm25_staged_search_and_two_stream_overlap_equal_the_serial_path(rq, dev):
+    """ragb_bm25_score_part / _finish (stripes scored in several launches, optionally with padded shared memory) equal
+    ragb_bm25_score_topk bit for bit; HybridEngine.local_pools(overlap=True) - BM25 blocks co-resident with the 4-stage
+    tcgen05 kernel on a second, higher-priority stream - returns exactly what the serial path returns."""
+    from rag_uq_b200 import synth
+    n, n_q, k = 400_000, 300, 50
+    engine, cdf = synth.build_synthetic_engine(n, 768, dev)
+    sh = engine.sparse
+    qb = synth.make_queries(n_q, n, 768, cdf, dev)
+    want_s, want_i = sh.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+    stripes = rq.ops.bm25_stripe_count(n_q, n)
+    assert stripes >= 3
+    for cuts, pad in (([0, 1, stripes], 0), ([0, stripes // 2, stripes - 1, stripes], 96 * 1024), ([0, stripes], 0)):
+        ws = rq.ops.bm25_workspace(n_q, n, k, dev)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            sh.score_part(qb.q_terms, qb.q_off, qb.max_terms, k, ws, a, b, pad if a == 0 else 0)
+        s, i = rq.ops.bm25_score_finish(n_q, n, k, ws)
+        assert torch.equal(i, want_i) and torch.equal(s, want_s)
+    with pytest.raises(ValueError):
+        sh.score_part(qb.q_terms, qb.q_off, qb.max_terms, k, rq.ops.bm25_workspace(n_q, n, k, dev), 2, stripes + 1)
+    serial = engine.local_pools(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, k, overlap=False)
+    for _ in range(3):
+        both = engine.local_pools(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, k, overlap=True)
+        torch.cuda.synchronize()
+        for a, b in zip(both, serial):
+            assert torch.equal(a, b)
+    # variant 4 (CTA pairs, 4-stage ring) == variant 3
+    s3, i3 = rq.ops.dense_mma_topk(engine.passages, qb.q_emb, k, 0, 3)
+    s4, i4 = rq.ops.dense_mma_topk(engine.passages, qb.q_emb, k, 0, 4)
+    assert torch.equal(s3, s4) and torch.equal(i3, i4)
+
+
 @pytest.mark.parametrize("n,n_q,k", [(120_000, 48, 50), (9_000, 20, 10)])
 def test_bm25_external_seed_only_prunes(rq, dev, n, n_q, k):
     """ragb_bm25_seed + seed_thr: any PROVEN lower bound of the k-th best score gives the same result - the kernel's own
