@@ -53,6 +53,12 @@ int launch_merge_keys_ex(const uint64_t* keys, int n_queries, int n_lists, int k
                          int k_out, float* out_score, int32_t* out_id, uint64_t* out_keys, float* out_thr,
                          cudaStream_t stream);
 
+// two-level variant for few queries with many lists; scratch holds n_queries * MERGE_SPLIT_MAX * k_out keys
+constexpr int MERGE_SPLIT_MAX = 32;
+int launch_merge_keys_split(const uint64_t* keys, int n_queries, int n_lists, int k_in, const uint64_t* extra_keys, int k_extra,
+                            int k_out, float* out_score, int32_t* out_id, uint64_t* out_keys, float* out_thr, uint64_t* scratch,
+                            cudaStream_t stream);
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int next_pow2(int v) {
   int p = 1;

@@ -226,7 +226,8 @@ extern "C" {
 // workspace: [n_queries, <= 148 * 4, k] block lists, [n_queries, k] merged list of the sampled prefix, [n_queries] bounds
 size_t ragb_dense_gemv_workspace_bytes(int32_t n_queries, int32_t k) {
   if (n_queries <= 0 || k <= 0) return 0;
-  return static_cast<size_t>(n_queries) * (148 * 4 + 1) * k * sizeof(uint64_t) + static_cast<size_t>(n_queries) * sizeof(float);
+  return static_cast<size_t>(n_queries) * (148 * 4 + 1 + MERGE_SPLIT_MAX) * k * sizeof(uint64_t) +
+         static_cast<size_t>(n_queries) * sizeof(float);
 }
 
 // one pass over rows [row_first, row_last) for all queries (groups of 4 / 2 / 1: register budget); -> grid used
@@ -278,7 +279,8 @@ int ragb_dense_gemv_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
                "ragb_dense_gemv_topk: workspace too small");
   uint64_t* part = static_cast<uint64_t*>(workspace);
   uint64_t* sample_keys = part + static_cast<size_t>(n_queries) * 148 * 4 * k;
-  float* thr = reinterpret_cast<float*>(sample_keys + static_cast<size_t>(n_queries) * k);
+  uint64_t* scratch = sample_keys + static_cast<size_t>(n_queries) * k;     // partial lists of the two-level merge
+  float* thr = reinterpret_cast<float*>(scratch + static_cast<size_t>(n_queries) * MERGE_SPLIT_MAX * k);
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(queries_bf16);
   // Sampled prefix (as in ragb_dense_mma_topk): the k-th best score of the first 1/32 of the rows is a proven lower
   // bound of the final k-th best and becomes the floor of every block's selection over the remaining rows.  Without
@@ -296,14 +298,14 @@ int ragb_dense_gemv_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
   if (prefix > 0) {
     rc = gemv_pass(passages_bf16, 0, prefix, dim, q, n_queries, k, id_base, nullptr, part, &grid, stream);
     if (rc != RAGB_OK) return rc;
-    rc = launch_merge_keys_ex(part, n_queries, grid, k, nullptr, 0, k, nullptr, nullptr, sample_keys, thr, stream);
+    rc = launch_merge_keys_split(part, n_queries, grid, k, nullptr, 0, k, nullptr, nullptr, sample_keys, thr, scratch, stream);
     if (rc != RAGB_OK) return rc;
     seed = thr;
   }
   rc = gemv_pass(passages_bf16, prefix, n_rows, dim, q, n_queries, k, id_base, seed, part, &grid, stream);
   if (rc != RAGB_OK) return rc;
-  return launch_merge_keys_ex(part, n_queries, grid, k, prefix > 0 ? sample_keys : nullptr, k, k, out_score, out_id, nullptr,
-                              nullptr, stream);
+  return launch_merge_keys_split(part, n_queries, grid, k, prefix > 0 ? sample_keys : nullptr, k, k, out_score, out_id, nullptr,
+                                 nullptr, scratch, stream);
 }
 
 int ragb_dense_scores(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,

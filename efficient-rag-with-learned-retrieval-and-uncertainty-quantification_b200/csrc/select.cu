@@ -137,6 +137,34 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_merge_kernel(const uint64_t*
   if (out_thr != nullptr && threadIdx.x == 0) out_thr[q] = keys[k_out - 1] ? key_score(keys[k_out - 1]) : -INFINITY;
 }
 
+// First level of the two-level merge: block (q, s) merges lists [s * per, (s + 1) * per) of query q into
+// out_keys[q, s, 0..k_out) (zero = empty).
+__global__ void __launch_bounds__(SEL_THREADS) topk_merge_slices_kernel(const uint64_t* __restrict__ in_keys, int n_lists, int per,
+                                                                        int k_in, int k_out, int capacity,
+                                                                        uint64_t* __restrict__ out_keys) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  __shared__ SelSmem st;
+  BlockTopK<SEL_THREADS> tk;
+  tk.init(keys, &st.count, &st.threshold, k_out, capacity, 0ull);
+  const int q = blockIdx.x, s = blockIdx.y;
+  const int l0 = min(n_lists, s * per), l1 = min(n_lists, l0 + per);
+  const int64_t total = static_cast<int64_t>(l1 - l0) * k_in;
+  const uint64_t* src = in_keys + (static_cast<int64_t>(q) * n_lists + l0) * k_in;
+  for (int64_t base = 0; base < total; base += SEL_CHUNK) {
+    tk.reserve(SEL_CHUNK);
+    const uint64_t thr = *tk.threshold;
+#pragma unroll
+    for (int j = 0; j < SEL_CHUNK / SEL_THREADS; ++j) {
+      const int64_t idx = base + j * SEL_THREADS + threadIdx.x;
+      if (idx < total) tk.offer(src[idx], thr);
+    }
+  }
+  tk.finish();
+  uint64_t* dst = out_keys + (static_cast<int64_t>(q) * gridDim.y + s) * k_out;
+  for (int i = threadIdx.x; i < k_out; i += SEL_THREADS) dst[i] = keys[i];
+}
+
 // ---------------------------------------------------------------------------------------
 // Pool fusion, HybridRetriever.hybrid_search (rag_uq/streaming_index.py:484-523).
 // One block per query, pool <= 256 so at most 512 union rows.
@@ -311,6 +339,27 @@ int launch_merge_keys_ex(const uint64_t* keys, int n_queries, int n_lists, int k
       keys, nullptr, nullptr, n_lists, k_in, k_out, capacity, out_score, out_id, extra_keys, k_extra, out_keys, out_thr);
   RAGB_AFTER_LAUNCH(1);
   return RAGB_OK;
+}
+
+// Two-level merge for FEW queries with MANY lists (the GEMV path: 592 block lists for 1..8 queries).  One block per
+// query would walk n_lists * k_in keys in 512-key rounds with a barrier each (~35 us for 30k keys); here `split` blocks
+// per query merge a slice of the lists each into scratch[n_queries, split, k_out] and a second, tiny launch merges
+// those (plus the optional extra list).  scratch: n_queries * MERGE_SPLIT_MAX * k_out keys.
+int launch_merge_keys_split(const uint64_t* keys, int n_queries, int n_lists, int k_in, const uint64_t* extra_keys, int k_extra,
+                            int k_out, float* out_score, int32_t* out_id, uint64_t* out_keys, float* out_thr, uint64_t* scratch,
+                            cudaStream_t stream) {
+  int split = n_lists / 24;                      // ~24 lists (1200 keys at k = 50) per first-level block
+  if (split > MERGE_SPLIT_MAX) split = MERGE_SPLIT_MAX;
+  if (split < 2 || k_in > k_out || static_cast<int64_t>(n_queries) * split > 148 * 8)
+    return launch_merge_keys_ex(keys, n_queries, n_lists, k_in, extra_keys, k_extra, k_out, out_score, out_id, out_keys, out_thr,
+                                stream);
+  const int capacity = topk_capacity(k_out);
+  const int per = (n_lists + split - 1) / split;
+  topk_merge_slices_kernel<<<dim3(n_queries, split), SEL_THREADS, capacity * sizeof(uint64_t), stream>>>(
+      keys, n_lists, per, k_in, k_out, capacity, scratch);
+  RAGB_AFTER_LAUNCH(1);
+  return launch_merge_keys_ex(scratch, n_queries, split, k_out, extra_keys, k_extra, k_out, out_score, out_id, out_keys, out_thr,
+                              stream);
 }
 
 static int rows_split(int n_rows, int64_t n_cols) {

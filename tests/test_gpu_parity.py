@@ -1217,8 +1217,11 @@ def test_batched_string_api_tokenizer_and_pool_join(rq, dev, tmp_path):
     many = r.hybrid_search_many(queries, None, top_k=10, retrieval_pool_size=50)
     for q, got in zip(queries, many):
         one = r.hybrid_search(q, top_k=10, retrieval_pool_size=50)
-        assert [(g.doc_id, g.bm25_score, g.dense_score, g.hybrid_score) for g in got] == \
-            [(g.doc_id, g.bm25_score, g.dense_score, g.hybrid_score) for g in one]
+        # the batch goes through the tcgen05 kernel, a single query through the GEMV: same dot products, another
+        # summation order (1 ulp), BM25 bit-identical
+        assert [(g.doc_id, g.bm25_score) for g in got] == [(g.doc_id, g.bm25_score) for g in one]
+        np.testing.assert_allclose([g.dense_score for g in got], [g.dense_score for g in one], rtol=0, atol=1e-6)
+        np.testing.assert_allclose([g.hybrid_score for g in got], [g.hybrid_score for g in one], rtol=0, atol=1e-6)
     # rows the retriever holds no document for are dropped before the fusion (:494-496): forget 100 documents
     for i in range(0, 500, 5):
         del r.documents[f"doc{i}"]
