@@ -282,13 +282,13 @@ int ragb_dense_gemv_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
   uint64_t* scratch = sample_keys + static_cast<size_t>(n_queries) * k;     // partial lists of the two-level merge
   float* thr = reinterpret_cast<float*>(scratch + static_cast<size_t>(n_queries) * MERGE_SPLIT_MAX * k);
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(queries_bf16);
-  // Sampled prefix (as in ragb_dense_mma_topk): the k-th best score of the first 1/32 of the rows is a proven lower
-  // bound of the final k-th best and becomes the floor of every block's selection over the remaining rows.  Without
-  // it every block appends its first 512 rows unconditionally and sorts 1024 keys with block barriers two or three
-  // times before its threshold settles: at 1M rows (2.5 MB per block) that warm-up costs a quarter of the kernel.
+  // Optional sampled prefix (as in ragb_dense_mma_topk): the k-th best score of the first 1/DIV of the rows is a proven
+  // lower bound of the final k-th best and becomes the floor of every block's selection over the remaining rows, which
+  // removes the warm-up sorts of the blocks.  OFF by default: measured at 1M rows / batch 1 the extra pass + merge cost
+  // what the warm-up costs (0.345 ms with DIV = 32 against 0.342 ms without).
   static const int sample_div = [] {
     const char* e = getenv("RAGB_GEMV_SAMPLE_DIV");   // tuning aid: 0 = no sampled prefix
-    return e ? atoi(e) : 32;
+    return e ? atoi(e) : 0;
   }();
   int64_t prefix = (sample_div > 0 && n_rows >= 262144) ? (n_rows / sample_div) / 32 * 32 : 0;
   if (prefix < 4 * static_cast<int64_t>(k)) prefix = 0;

@@ -1162,13 +1162,17 @@ static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const 
   cfg.blockDim = dim3(MM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // per-launch form of the carve-out preference (takes precedence over the function attribute): keep the SM at its
+  // maximal shared-memory configuration so that a block of another kernel can be placed next to this one
+  attr[1].id = cudaLaunchAttributePreferredSharedMemoryCarveout;
+  attr[1].val.sharedMemCarveout = 100;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   RAGB_CUDA(cudaLaunchKernelEx(&cfg, dense_mma_pair_kernel<KPL, FUSED>, map_q, map_e, a));
   RAGB_AFTER_LAUNCH(1);
   return RAGB_OK;
