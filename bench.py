@@ -55,6 +55,9 @@ def parse_args():
                    help="pool (default): the reference's hybrid_search semantics (pool-50 union, max-normalised fusion, "
                         "router rerank of the top-k).  full-fusion: router gate + learned fusion for EVERY (query, "
                         "passage) pair inside the tcgen05 epilogue (RetrievalRouter.hybrid_rerank over [B, N])")
+    p.add_argument("--ff-method", default="auto", choices=["auto", "threshold", "exhaustive"],
+                   help="full-fusion mode: threshold-algorithm search over the two exact ranked lists (default; exhaustive "
+                        "epilogue only for queries whose stopping rule does not hold) or the exhaustive [B, N] scan")
     p.add_argument("--mc-samples", type=int, default=0, help="MC-Dropout passes over the fused candidates (c4: 30)")
     p.add_argument("--candidates", type=int, default=0, help="fused candidates kept per query before the rerank (c4: 100)")
     p.add_argument("--no-graph", action="store_true",
@@ -365,6 +368,7 @@ def run_ours(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     dense_ms, bm25_ms, exch_ms = [], [], []
 
+    ff_info = {}
     graphed = None
     if args.batch <= 8 and world == 1 and args.mode == "pool" and args.mc_samples == 0 and args.candidates <= args.k \
             and not args.no_graph:
@@ -378,7 +382,8 @@ def run_ours(args):
                 return out[0], out[1]
             events = {} if probes is not None else None
             if args.mode == "full-fusion":
-                vals, ids = engine.full_fusion_topk(q_terms, q_off, max_terms, q_emb, router, args.k, events=events)
+                vals, ids = engine.full_fusion_topk(q_terms, q_off, max_terms, q_emb, router, args.k, events=events,
+                                                    method=args.ff_method, info=ff_info)
                 if probes is not None:   # one (start, end) pair per kernel, first to last query chunk
                     probes.append({name: (ev[0][0], ev[-1][1]) for name, ev in events.items()})
                 return ids, vals
@@ -495,8 +500,11 @@ def run_ours(args):
                                     f"({'bf16 GEMV' if args.batch <= 8 else 'tcgen05 variant ' + str(args.variant)}) + fusion + router rerank"
                                     + (f" + MC-Dropout T={args.mc_samples} over {max(args.k, args.candidates)} candidates" if args.mc_samples else "")
                                     if args.mode == "pool" else
-                                    f"full-fusion top-{args.k}: BM25 get_scores matrix + tcgen05 GEMM with router gate, learned "
-                                    f"fusion and top-k in the epilogue (every (query, passage) pair)")
+                                    (f"full-fusion top-{args.k}: BM25 get_scores matrix + tcgen05 GEMM with router gate, learned "
+                                     f"fusion and top-k in the epilogue (every (query, passage) pair)" if args.ff_method == "exhaustive" else
+                                     f"full-fusion top-{args.k} (RetrievalRouter.hybrid_rerank over ALL passages) as a threshold-algorithm "
+                                     f"search: exact BM25 top-100 + exact dense top-100 (tcgen05), the other score of every listed passage, "
+                                     f"gate + fusion, proven stopping bound; exhaustive epilogue for queries where it does not hold"))
                                    + f"; {args.passages} passages x {DIM} "
                                    f"bf16 row-sharded over {world} GPU(s), batch {args.batch} queries x 8 terms",
                        "l2": "inputs exceed L2 (embedding shard %.1f GB, postings %.1f GB per GPU); 4 rotating query batches"
@@ -513,6 +521,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "verified": verified, **digest,
+            "full_fusion": (ff_info or None) if args.mode == "full-fusion" else None,
             "roofline": None, "roofline_secondary": None,
             "kernels": {"bm25_ms": bm25_avg, "bm25_postings_per_batch": sum_df,
                         "bm25_posting_gbs": sum_df * 6.0 / (bm25_avg / 1000.0) / 1e9,
@@ -531,14 +540,15 @@ def run_ours(args):
                        "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
                        "traffic": None, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
                        "ms_per_launch": dense_avg, "flops_per_launch": flops})
-        bm25_bytes = sum_df * 6.0 + (4.0 * n_local * args.batch if args.mode == "full-fusion" else 0.0)
+        exhaustive = args.mode == "full-fusion" and args.ff_method == "exhaustive"
+        bm25_bytes = sum_df * 6.0 + (4.0 * n_local * args.batch if exhaustive else 0.0)
         bm25_gbs = bm25_bytes / (bm25_avg / 1000.0) / 1e9
         bm25_roof = {"bound": "hbm", "kernel": "bm25_kernel (+ stripe merge)", "achieved": bm25_gbs, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": bm25_gbs / pk["hbm_gbs"], "traffic": None,
                      "peak_source": pk["source"] + " copy bandwidth", "ms_per_launch": bm25_avg,
                      "bytes_per_launch": bm25_bytes,
                      "note": "algorithmic bytes = 6 B x sum of document frequencies of the batch's query terms"
-                             + (" + 4 B x passages x queries for the score matrix" if args.mode == "full-fusion" else "")}
+                             + (" + 4 B x passages x queries for the score matrix" if exhaustive else "")}
         # measured DRAM traffic per launch (dram__bytes_read + dram__bytes_write of one ncu --set full capture of this
         # very command, profiles/traffic_r01.json); only quoted when the workload is the one that was profiled
         for tpath in sorted((ROOT / "profiles").glob("traffic_r*.json"), reverse=True):

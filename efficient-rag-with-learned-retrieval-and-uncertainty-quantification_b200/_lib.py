@@ -71,6 +71,9 @@ SIGNATURES = {
     "ragb_dense_mma_seeded": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "ragb_dense_mma_fused_topk": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _p, _i64, _p, _p, _p, _p, _p, _i32,
                                             _p, _i32, _i32, C.c_float, C.c_float, _p, _p, _p, _p, _sz, _p]),
+    "ragb_bm25_score_docs": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _i32, _i32, _i64, _i64,
+                                       _p, _i32, _p, _p]),
+    "ragb_dense_score_docs": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _p, _i32, _p, _p]),
     "ragb_dense_scores": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _p]),
     "ragb_topk_rows_workspace_bytes": (_sz, [_i32, _i64, _i32]),
     "ragb_topk_rows": (C.c_int, [_p, _i32, _i64, _i32, _p, _p, _p, _sz, _p]),

@@ -20,7 +20,7 @@ INCLUDE = REPO_ROOT / "include"
 LIB_PATH = PKG_DIR / "libragb200.so"
 OBJ_DIR = PKG_DIR / "build"
 
-SOURCES = ["common.cu", "select.cu", "bm25.cu", "dense_gemv.cu", "dense_mma.cu", "router.cu"]
+SOURCES = ["common.cu", "select.cu", "bm25.cu", "dense_gemv.cu", "dense_mma.cu", "router.cu", "candidates.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

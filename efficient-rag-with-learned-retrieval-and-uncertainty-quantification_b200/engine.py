@@ -265,7 +265,94 @@ class HybridEngine:
 
     def full_fusion_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, router, k: int = 10,
                          query_chunk: Optional[int] = None, fused: Optional[bool] = None, counters: Optional[Tensor] = None,
-                         events=None):
+                         events=None, method: str = "auto", depth: int = 100, info: Optional[dict] = None):
+        """Gate evaluated on the true scores of every (query, passage) pair: the k best fused scores per query.
+
+        ``method`` "auto" (default) / "threshold": the threshold-algorithm search below, with the exhaustive epilogue as
+        the fallback for queries whose stopping rule does not hold; "exhaustive": the [B, N]-scan described under
+        ``_full_fusion_exhaustive`` (``fused`` / ``query_chunk`` / ``counters`` apply to it).
+        """
+        if method == "exhaustive" or fused is not None or not isinstance(self.sparse, SparseShard) \
+                or q_emb.shape[0] <= _lib.GEMV_MAX_BATCH:
+            return self._full_fusion_exhaustive(q_terms, q_off, max_terms, q_emb, router, k, query_chunk, fused, counters, events)
+        return self._full_fusion_threshold(q_terms, q_off, max_terms, q_emb, router, k, depth, events, info)
+
+    def _full_fusion_threshold(self, q_terms, q_off, max_terms, q_emb, router, k, depth, events, info):
+        """Full-fusion as a threshold-algorithm (Fagin) search over the two exact ranked lists - no [B, N] matrix.
+
+        fused(b, d) = b + g(b, d) (d - b) is bounded from above by a function E that is monotone in both scores
+        (``router.full_fusion_envelope``).  So: (1) the streaming kernels deliver the ``depth`` best passages of each
+        side, exactly; (2) every listed passage gets its OTHER score (ragb_bm25_score_docs / ragb_dense_score_docs) and
+        its exact gate and fused score; (3) any passage on neither list has bm25 <= b_depth and dense <= d_depth, hence
+        fused <= E(b_depth, d_depth): if that is below the k-th best fused score found, the top-k is proven complete.
+        Queries for which it is not (a gate that ignores both scores' order, a flat score distribution) are re-run
+        through the exhaustive epilogue.  Oracle: RetrievalRouter.hybrid_rerank(bm25[B,N], dense[B,N], k)."""
+        if not getattr(router, "stats_initialized", False):
+            raise ValueError("full-fusion mode needs router.stats_initialized = True (running statistics)")
+        n_q, n_local = q_emb.shape[0], self.passages.shape[0]
+        depth = max(k, min(depth, _lib.MMA_MAX_TOPK, n_local))
+        e0 = _mark(events)
+        bs, bi = self.sparse.score_topk(q_terms, q_off, max_terms, depth)
+        e1 = _mark(events)
+        ds, di = ops.dense_mma_topk(self.passages, q_emb, depth, self.id_base, self.mma_variant)
+        e2 = _mark(events)
+        # union of the two lists: a passage on both keeps its BM25-list slot
+        dup = (di.unsqueeze(2) == bi.unsqueeze(1)).any(dim=2) & (di >= 0)
+        cand = torch.cat([bi, torch.where(dup, torch.full_like(di, -1), di)], dim=1).contiguous()
+        b_c = self.sparse.score_docs(q_terms, q_off, max_terms, cand)
+        d_c = ops.dense_score_docs(self.passages, q_emb, self.id_base, cand)
+        w1, b1, w2, b2, stats = router._weights()
+        _, fused_c = ops.router_forward(b_c, d_c, w1, b1, w2, b2, stats, 1)
+        fused_c = torch.where(cand >= 0, fused_c, torch.full_like(fused_c, float("-inf"))).contiguous()
+        kk = min(k, n_local)
+        val, idx = ops.topk_rows(fused_c, kk)
+        ids = torch.gather(cand, 1, idx.to(torch.int64).clamp(min=0))
+        ids = torch.where(idx >= 0, ids, torch.full_like(ids, -1))
+        # stopping rule: bound on everything unlisted (an incomplete BM25 list means every other passage scores 0)
+        b_cap = self.bm25_score_cap(q_terms, q_off)
+        b_cap = float(min(64.0, 2.0 ** max(0, int(b_cap - 1e-9).bit_length()))) if b_cap > 0 else 1.0
+        d_hi = self._max_passage_norm() * float(q_emb.float().norm(dim=1).max()) * 1.002 + 1e-3
+        d_hi = float(-(-d_hi * 64 // 1) / 64)
+        env = router.full_fusion_envelope(b_cap, d_hi)
+        n_b, n_d = env.shape
+        b_last = torch.where(bi[:, -1] >= 0, bs[:, -1], torch.zeros_like(bs[:, -1]))
+        d_last = ds[:, -1] + 2e-6                        # tensor-core vs fp32 summation order
+        ib = torch.clamp((b_last * (n_b / b_cap)).floor().long(), 0, n_b - 1)
+        idc = torch.clamp(((d_last + d_hi) * (n_d / (2.0 * d_hi))).floor().long(), 0, n_d - 1)
+        unseen = env[ib, idc]
+        kth = val[:, kk - 1]
+        proven = (unseen <= kth - 1e-5 * kth.abs() - 1e-6) | (depth >= n_local)
+        e3 = _mark(events)
+        redo = torch.nonzero(~proven).flatten()
+        n_redo = int(redo.numel())
+        if info is not None:
+            info.update({"method": "threshold", "depth": depth, "fallback_queries": n_redo})
+        if n_redo:
+            sel = redo.tolist()
+            q_off_h = q_off.tolist()
+            sub_terms = torch.cat([q_terms[q_off_h[q]:q_off_h[q + 1]] for q in sel]) if any(q_off_h[q + 1] > q_off_h[q] for q in sel) \
+                else q_terms[:1]
+            lens = torch.tensor([q_off_h[q + 1] - q_off_h[q] for q in sel], dtype=torch.int32, device=q_off.device)
+            sub_off = torch.cat([lens.new_zeros(1), torch.cumsum(lens, 0).to(torch.int32)]).contiguous()
+            if n_redo <= _lib.GEMV_MAX_BATCH:           # the epilogue kernel wants a real batch: pad by repeating queries
+                pad = (_lib.GEMV_MAX_BATCH + 1) - n_redo
+                sub_emb = torch.cat([q_emb[redo], q_emb[redo[:1]].expand(pad, -1)]).contiguous()
+                sub_terms = torch.cat([sub_terms, sub_terms[:int(lens[0])].repeat(pad)]) if int(lens[0]) else sub_terms
+                sub_off = torch.cat([sub_off, sub_off[-1] + (torch.arange(1, pad + 1, device=q_off.device, dtype=torch.int32) * int(lens[0]))])
+            else:
+                sub_emb = q_emb[redo].contiguous()
+            fv, fi = self._full_fusion_exhaustive(sub_terms.contiguous(), sub_off.contiguous(), max_terms, sub_emb, router, k,
+                                                  None, None, None, None, merge=False)
+            val[redo], ids[redo] = fv[:n_redo, :kk], fi[:n_redo, :kk]
+        if events is not None:
+            events.setdefault("bm25", []).append((e0, e1))
+            events.setdefault("dense", []).append((e1, e2))
+            events.setdefault("candidates", []).append((e2, e3))
+        return self._merge(val, ids, val.shape[1])
+
+    def _full_fusion_exhaustive(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, router, k: int = 10,
+                                query_chunk: Optional[int] = None, fused: Optional[bool] = None,
+                                counters: Optional[Tensor] = None, events=None, merge: bool = True):
         """Gate evaluated for EVERY (query, passage) pair on the true scores ("full-fusion").
 
         Oracle: ``RetrievalRouter.hybrid_rerank(bm25_full[B,N], dense_full[B,N], k)`` (router.py:179-202).
@@ -328,7 +415,7 @@ class HybridEngine:
             out_s.append(val)
             out_i.append(torch.where(idx >= 0, idx + self.id_base, idx))
         score, ids = torch.cat(out_s), torch.cat(out_i)
-        return self._merge(score, ids, score.shape[1])
+        return self._merge(score, ids, score.shape[1]) if merge else (score, ids)
 
 
 def _mark(events):

@@ -437,6 +437,51 @@ def _(passages, queries, bm25, w1, b1, w2, b2, stats, gate_bounds, b_cap, d_hi, 
     return (queries.new_empty((n_q, k), dtype=torch.float32), queries.new_empty((n_q, k), dtype=torch.int32))
 
 
+@torch.library.custom_op(f"{NS}::bm25_score_docs", mutates_args=(), device_types="cuda")
+def bm25_score_docs(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
+                    dense_tf: Tensor, dense_terms: Tensor, q_terms: Tensor, q_off: Tensor, max_query_terms: int,
+                    id_base: int, cand_ids: Tensor) -> Tensor:
+    """Exact BM25 scores [B, C] of the candidate passages cand_ids int32 [B, C] (global ids, -1 = none -> 0);
+    bit-identical to what ``bm25_score_topk`` computes for the same documents."""
+    term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
+                                                                        q_terms, q_off)
+    cand_ids = _need(cand_ids, torch.int32, "cand_ids")
+    n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
+    if cand_ids.dim() != 2 or cand_ids.shape[0] != n_q:
+        raise ValueError("cand_ids must be [B, C]")
+    out = torch.empty(cand_ids.shape, dtype=torch.float32, device=dev)
+    dt, stride, dterms, n_dense = _dense_table(dense_tf, dense_terms, n_docs)
+    with torch.cuda.device(dev):
+        check(lib.ragb_bm25_score_docs(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf), idf.shape[0], k1,
+                                       dt, stride, dterms, n_dense, _ptr(q_terms), _ptr(q_off), n_q, max_query_terms, n_docs,
+                                       id_base, _ptr(cand_ids), cand_ids.shape[1], _ptr(out), _stream()))
+    return out
+
+
+@bm25_score_docs.register_fake
+def _(term_off, post_doc, post_tf, norm, idf, k1, dense_tf, dense_terms, q_terms, q_off, max_query_terms, id_base, cand_ids):
+    return norm.new_empty(cand_ids.shape)
+
+
+@torch.library.custom_op(f"{NS}::dense_score_docs", mutates_args=(), device_types="cuda")
+def dense_score_docs(passages: Tensor, queries: Tensor, id_base: int, cand_ids: Tensor) -> Tensor:
+    """Inner products [B, C] of each query with its candidate passages cand_ids int32 [B, C] (-1 = none -> 0)."""
+    passages, queries = _dense_args(passages, queries)
+    cand_ids = _need(cand_ids, torch.int32, "cand_ids")
+    if cand_ids.dim() != 2 or cand_ids.shape[0] != queries.shape[0]:
+        raise ValueError("cand_ids must be [B, C]")
+    out = torch.empty(cand_ids.shape, dtype=torch.float32, device=passages.device)
+    with torch.cuda.device(passages.device):
+        check(lib.ragb_dense_score_docs(_ptr(passages), passages.shape[0], passages.shape[1], _ptr(queries), queries.shape[0],
+                                        id_base, _ptr(cand_ids), cand_ids.shape[1], _ptr(out), _stream()))
+    return out
+
+
+@dense_score_docs.register_fake
+def _(passages, queries, id_base, cand_ids):
+    return queries.new_empty(cand_ids.shape, dtype=torch.float32)
+
+
 @torch.library.custom_op(f"{NS}::dense_scores", mutates_args=(), device_types="cuda")
 def dense_scores(passages: Tensor, queries: Tensor) -> Tensor:
     passages, queries = _dense_args(passages, queries)

@@ -142,6 +142,11 @@ class SparseShard:
                             self.dense_terms, self.dense_imp, self.dense_maximp, q_terms, q_off, max_terms, self.id_base, k,
                             seed, stripe_begin, stripe_end, min_smem_bytes, workspace)
 
+    def score_docs(self, q_terms: Tensor, q_off: Tensor, max_terms: int, cand_ids: Tensor) -> Tensor:
+        """Exact BM25 scores [B, C] of chosen passages (global ids, -1 = none): ragb_bm25_score_docs."""
+        return ops.bm25_score_docs(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1, self.dense_tf,
+                                   self.dense_terms, q_terms, q_off, max_terms, self.id_base, cand_ids)
+
     def seed(self, q_terms: Tensor, q_off: Tensor, max_terms: int, k: int) -> Tensor:
         """Proven lower bounds [B] of the k-th best score of every query over this shard (ragb_bm25_seed)."""
         return ops.bm25_seed(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1, self.dense_tf,

@@ -210,6 +210,25 @@ int ragb_dense_mma_fused_topk(const void* passages_bf16, int64_t n_rows, int32_t
                               const uint32_t* gate_bound_table, int32_t n_b, int32_t n_d, float b_cap, float d_hi,
                               float* out_score, int32_t* out_id, unsigned long long* counters,
                               void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+/* ---- exact scores of GIVEN (query, passage) pairs -------------------------------------------------------------
+ * The random-access companions of the two streaming scorers, used by the threshold-algorithm form of full-fusion
+ * (RetrievalRouter.hybrid_rerank over all passages, rag_uq/router.py:179-202, without a [B, N] matrix): each side's
+ * streaming kernel delivers its exact ranked list, these fill in the OTHER side's score of every listed passage.
+ * cand_ids [n_queries, n_cand]: global ids, -1 (or an id outside this shard) = none -> score 0.
+ * ragb_bm25_score_docs: rank_bm25 get_scores (streaming_index.py:169) for the chosen documents, same arithmetic and
+ *   summation order as ragb_bm25_score_topk: the scores are bit-identical to the streaming kernel's.
+ * ragb_dense_score_docs: the bf16 inner product of DenseIndex.search (streaming_index.py:353-370) for the chosen rows,
+ *   fp32 accumulation (equal to the tensor-core result to ~1 ulp, not bit for bit). */
+int ragb_bm25_score_docs(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf,
+                         const float* norm, const float* idf, int64_t vocab, double k1,
+                         const uint8_t* dense_tf, int64_t dense_stride,
+                         const int32_t* dense_terms, int32_t n_dense,
+                         const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
+                         int32_t max_query_terms, int64_t n_docs, int64_t id_base,
+                         const int32_t* cand_ids, int32_t n_cand, float* out_scores, ragb_stream_t stream);
+int ragb_dense_score_docs(const void* passages_bf16, int64_t n_rows, int32_t dim,
+                          const void* queries_bf16, int32_t n_queries, int64_t id_base,
+                          const int32_t* cand_ids, int32_t n_cand, float* out_scores, ragb_stream_t stream);
 /* Plain score matrix out[n_queries, n_rows] fp32 (small shapes, tests, un-fused full-fusion mode). */
 int ragb_dense_scores(const void* passages_bf16, int64_t n_rows, int32_t dim,
                       const void* queries_bf16, int32_t n_queries, float* out_scores,

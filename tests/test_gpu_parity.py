@@ -651,6 +651,88 @@ def test_full_fusion_fused_epilogue(rq, dev, n, n_q, k, hidden, scale):
         assert (fi.cpu().long() - 1000 == want_i).float().mean() > 0.98
 
 
+def test_score_docs_kernels(rq, dev):
+    """ragb_bm25_score_docs == the streaming kernel's get_scores at the chosen documents, BIT FOR BIT (same arithmetic,
+    same summation order; duplicated query terms, OOV ids, ids outside the shard, -1 pads); ragb_dense_score_docs == the
+    float64 inner product to fp32 rounding."""
+    from rag_uq_b200 import synth
+    n, dim, n_q, c = 20_000, 768, 24, 37
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    shard = rq.build_shard(doc_off, doc_tok, vocab, id_base=500).finalize()
+    passages = synth.passage_embeddings(0, n, dim, dev)
+    qb = synth.make_queries(n_q, n, dim, cdf, dev)
+    terms = qb.q_terms.clone().view(n_q, -1)
+    terms[3, 4:] = terms[3, :4]                       # duplicated terms count per occurrence
+    terms[5, 0] = vocab + 9                           # out of vocabulary
+    q_terms = terms.reshape(-1).contiguous()
+    full = shard.scores(q_terms, qb.q_off, qb.max_terms)                      # [n_q, n] from bm25_kernel<DENSE_OUT>
+    g = torch.Generator(device="cpu").manual_seed(3)
+    cand = torch.randint(0, n, (n_q, c), generator=g).to(dev).to(torch.int32) + 500
+    cand[:, 0] = qb.source_rows.to(torch.int32) + 500                         # a document that matches every list term
+    cand[2, 5], cand[7, 1], cand[9, 2] = -1, 499, 500 + n                     # pad, below the shard, above the shard
+    got = shard.score_docs(q_terms, qb.q_off, qb.max_terms, cand.contiguous())
+    local = (cand - 500).long()
+    valid = (local >= 0) & (local < n)
+    want = torch.where(valid, torch.gather(full, 1, local.clamp(0, n - 1)), torch.zeros((), device=dev))
+    assert torch.equal(got, want)
+    # and against the top-k kernel's own scores
+    ts, ti = shard.score_topk(q_terms, qb.q_off, qb.max_terms, 50)
+    again = shard.score_docs(q_terms, qb.q_off, qb.max_terms, ti)
+    assert torch.equal(torch.where(ti >= 0, again, torch.zeros_like(again)), torch.where(ti >= 0, ts, torch.zeros_like(ts)))
+    d = rq.ops.dense_score_docs(passages, qb.q_emb, 500, cand.contiguous())
+    want_d = dense_fusion.dense_scores(passages.float().cpu().numpy(), qb.q_emb.float().cpu().numpy())
+    want_d = np.where(valid.cpu().numpy(), np.take_along_axis(want_d, local.clamp(0, n - 1).cpu().numpy(), axis=1), 0.0)
+    np.testing.assert_allclose(d.cpu().numpy(), want_d, rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("n,n_q,k,hidden,scale,dense_favoured", [(10_000, 64, 10, 64, 1.0, False), (33_331, 200, 50, 32, 4.0, False),
+                                                                 (20_000, 150, 10, 16, 8.0, True), (150_000, 256, 10, 64, 1.0, False)])
+def test_full_fusion_threshold_algorithm(rq, dev, n, n_q, k, hidden, scale, dense_favoured):
+    """Full-fusion as a threshold-algorithm search (no [B, N] matrix): equals RetrievalRouter.hybrid_rerank over ALL
+    passages (torch-CPU oracle where the corpus is small enough, the exhaustive epilogue otherwise) - with the default
+    depth (stopping rule proven for nearly every query) and with a depth so small that most queries take the fallback."""
+    from rag_uq_b200 import synth
+    dim = 768
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    passages = synth.passage_embeddings(0, n, dim, dev)
+    engine = rq.HybridEngine(rq.build_shard(doc_off, doc_tok, vocab).finalize(), passages, id_base=1000)
+    qb = synth.make_queries(n_q, n, dim, cdf, dev)
+    torch.manual_seed(11)
+    router = rq.RetrievalRouter(rq.RouterConfig(hidden_dim=hidden)).to(dev).eval()
+    with torch.no_grad():
+        for p in router.parameters():
+            p.mul_(scale)
+        if dense_favoured:
+            router.scorer[3].bias.fill_(6.0)         # gate ~ 1 almost everywhere: fused ~ dense, the BM25 order says little
+    router.bm25_mean.fill_(8.0); router.bm25_std.fill_(6.0); router.dense_mean.fill_(0.1); router.dense_std.fill_(0.2)
+    router.stats_initialized = True
+    tol = 1e-5 * max(1.0, scale * scale)
+    with torch.no_grad():
+        info, info_small = {}, {}
+        ts, ti = engine.full_fusion_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, method="threshold", info=info)
+        ss, si = engine.full_fusion_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, method="threshold",
+                                         depth=k, info=info_small)
+        es, ei = engine.full_fusion_topk(qb.q_terms, qb.q_off, qb.max_terms, qb.q_emb, router, k, method="exhaustive")
+    assert info["method"] == "threshold" and info_small["fallback_queries"] >= info["fallback_queries"]
+    if not dense_favoured:
+        assert info["fallback_queries"] <= n_q // 4      # the stopping rule holds for most queries at depth 100
+    for got_s, got_i in ((ts, ti), (ss, si)):
+        torch.testing.assert_close(got_s, es, rtol=tol, atol=tol)
+        same = got_i == ei
+        assert same.float().mean() > 0.99
+        assert bool(((got_s - es).abs()[~same] <= tol * es.abs()[~same] + 1e-6).all())     # a near-tie swapped
+    if n <= 40_000:
+        okapi = bm25_okapi.OkapiCsr(doc_off.cpu().numpy(), doc_tok.cpu().numpy(), vocab)
+        terms = qb.q_terms.view(n_q, -1).cpu().numpy()
+        bm = torch.tensor(np.stack([okapi.get_scores(terms[q]) for q in range(n_q)]), dtype=torch.float32)
+        de = torch.tensor(dense_fusion.dense_scores(passages.float().cpu().numpy(), qb.q_emb.float().cpu().numpy()),
+                          dtype=torch.float32)
+        state = {key: v.detach().cpu() for key, v in router.state_dict().items()}
+        want_s, want_i = router_oracle.hybrid_rerank(bm, de, state, True, k)
+        torch.testing.assert_close(ts.cpu(), want_s, rtol=3 * tol, atol=3 * tol)
+        assert (ti.cpu().long() - 1000 == want_i).float().mean() > 0.98
+
+
 @pytest.mark.parametrize("hidden,scale,dense_std", [(64, 1.0, 0.3), (32, 6.0, 0.05), (16, 20.0, 0.02), (128, 3.0, 0.1)])
 def test_full_fusion_bound_as_the_kernel_indexes_it(rq, dev, hidden, scale, dense_std):
     """The gate-bound lookup EXACTLY as the fused epilogue evaluates it (FusedBound in csrc/dense_mma.cu, called

@@ -296,6 +296,37 @@ def test_full_fusion_gate_bounds_are_proven_bounds(rq, hidden, scale):
     assert ((bad << 16).view(np.float32) == 0).all() and ((bad & np.uint32(0xFFFF0000)).view(np.float32) == 1).all()
 
 
+@pytest.mark.parametrize("hidden,scale", [(64, 1.0), (16, 20.0), (32, 4.0)])
+def test_full_fusion_envelope_is_a_monotone_proven_bound(rq, hidden, scale):
+    """router.full_fusion_envelope: E[ib, id] bounds the fused score of every (bm25, dense) at or below the cell - the
+    stopping rule of the threshold-algorithm full-fusion search - and is monotone in both directions."""
+    from rag_uq_b200.router import full_fusion_envelope
+    torch.manual_seed(hidden)
+    lin1, lin2 = torch.nn.Linear(3, hidden), torch.nn.Linear(hidden, 1)
+    w1, b1 = (lin1.weight.detach() * scale).numpy(), (lin1.bias.detach() * scale).numpy()
+    w2, b2 = (lin2.weight.detach() * scale).reshape(-1).numpy(), lin2.bias.detach().numpy()
+    stats = np.array([8.0, 6.0, 0.2, 0.3], dtype=np.float32)
+    b_cap, d_hi, n_b, n_d = 32.0, 1.02, 128, 64
+    env = full_fusion_envelope(w1, b1, w2, b2, stats, b_cap, d_hi, n_b, n_d)
+    assert env.shape == (n_b, n_d) and (np.diff(env, axis=0) >= 0).all() and (np.diff(env, axis=1) >= 0).all()
+    rng = np.random.default_rng(1)
+    n = 200_000
+    b = rng.uniform(0, b_cap * 0.999, n).astype(np.float32)
+    d = rng.uniform(-d_hi, d_hi, n).astype(np.float32)
+    bt, dt = torch.tensor(b), torch.tensor(d)
+    bn = (bt - stats[0]) / (torch.tensor(stats[1]) + 1e-6)
+    dn = (dt - stats[2]) / (torch.tensor(stats[3]) + 1e-6)
+    feats = torch.stack([bn, dn, dn - bn], -1)
+    gate = torch.sigmoid(torch.relu(feats @ torch.tensor(w1).T + torch.tensor(b1)) @ torch.tensor(w2) + torch.tensor(b2))
+    fused = (gate * dt + (1 - gate) * bt).numpy()
+    ib = np.clip(np.floor(b * (n_b / b_cap)).astype(int), 0, n_b - 1)
+    idc = np.clip(np.floor((d + d_hi) * (n_d / (2 * d_hi))).astype(int), 0, n_d - 1)
+    assert (env[ib, idc] >= fused - 1e-5).all()
+    # ... and of everything BELOW the cell: compare each point with the envelope of a cell up and to the right of it
+    up_b, up_d = np.minimum(ib + rng.integers(0, 20, n), n_b - 1), np.minimum(idc + rng.integers(0, 10, n), n_d - 1)
+    assert (env[up_b, up_d] >= fused - 1e-5).all()
+
+
 def test_shard_format_round_trip_on_cpu(rq, tmp_path):
     """N2: the raw-array shard directory reproduces every array bit for bit (memmap read, no parsing); loading
     without finalize needs no GPU."""
