@@ -290,6 +290,9 @@ class HybridEngine:
         if not getattr(router, "stats_initialized", False):
             raise ValueError("full-fusion mode needs router.stats_initialized = True (running statistics)")
         n_q, n_local = q_emb.shape[0], self.passages.shape[0]
+        if int(self.sparse.id_base) != int(self.id_base):
+            raise ValueError("the BM25 shard and the engine number their passages from different bases "
+                             f"({self.sparse.id_base} vs {self.id_base}): the two ranked lists could not be joined")
         depth = max(k, min(depth, _lib.MMA_MAX_TOPK, n_local))
         e0 = _mark(events)
         bs, bi = self.sparse.score_topk(q_terms, q_off, max_terms, depth)
@@ -313,7 +316,9 @@ class HybridEngine:
         b_cap = float(min(64.0, 2.0 ** max(0, int(b_cap - 1e-9).bit_length()))) if b_cap > 0 else 1.0
         d_hi = self._max_passage_norm() * float(q_emb.float().norm(dim=1).max()) * 1.002 + 1e-3
         d_hi = float(-(-d_hi * 64 // 1) / 64)
-        env = router.full_fusion_envelope(b_cap, d_hi)
+        # a fine grid (cells of b_cap / 1024 x d_hi / 128): on a large corpus the best BM25 scores lie close together,
+        # so the rule has to separate the depth-th from the k-th score by less than a coarse cell
+        env = router.full_fusion_envelope(b_cap, d_hi, 1024, 256)
         n_b, n_d = env.shape
         b_last = torch.where(bi[:, -1] >= 0, bs[:, -1], torch.zeros_like(bs[:, -1]))
         d_last = ds[:, -1] + 2e-6                        # tensor-core vs fp32 summation order

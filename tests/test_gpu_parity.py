@@ -695,7 +695,7 @@ def test_full_fusion_threshold_algorithm(rq, dev, n, n_q, k, hidden, scale, dens
     dim = 768
     vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
     passages = synth.passage_embeddings(0, n, dim, dev)
-    engine = rq.HybridEngine(rq.build_shard(doc_off, doc_tok, vocab).finalize(), passages, id_base=1000)
+    engine = rq.HybridEngine(rq.build_shard(doc_off, doc_tok, vocab, id_base=1000).finalize(), passages, id_base=1000)
     qb = synth.make_queries(n_q, n, dim, cdf, dev)
     torch.manual_seed(11)
     router = rq.RetrievalRouter(rq.RouterConfig(hidden_dim=hidden)).to(dev).eval()
