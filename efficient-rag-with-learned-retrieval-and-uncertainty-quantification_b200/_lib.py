@@ -67,6 +67,7 @@ SIGNATURES = {
     "ragb_dense_gemv_topk": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _p, _p, _p, _sz, _p]),
     "ragb_dense_mma_workspace_bytes": (_sz, [_i32, _i32]),
     "ragb_dense_mma_topk": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "ragb_dense_mma_topk_min": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "ragb_dense_mma_sample": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _i32, _p, _p, _sz, _p]),
     "ragb_dense_mma_seeded": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "ragb_dense_mma_fused_topk": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i64, _p, _i64, _p, _p, _p, _p, _p, _i32,

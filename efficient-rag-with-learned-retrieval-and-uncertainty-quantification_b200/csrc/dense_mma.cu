@@ -59,6 +59,7 @@ struct MmaArgs {
   int tile_lo, tile_hi;  // this launch covers passage tiles [tile_lo, tile_hi) (the sampled prefix, or the rest)
   int n_stages;
   const float* seed_thr;  // optional [n_queries]: a proven lower bound of every query's k-th best score; lists start there
+  float* min_out;         // optional [n_queries], initialised to +inf by the caller: receives the SMALLEST score of every query
   uint64_t* part_keys;  // [n_queries, lists_per_query, k]; this launch fills slots [group * 2 + half]
   int lists_per_query;
   int* progress;        // [n_groups, n_slabs] tiles issued so far (soft pacing between the slabs of a group)
@@ -290,6 +291,8 @@ __device__ __forceinline__ void epilogue_scan(const MmaArgs& a, const uint32_t t
       st.thr_key = static_cast<uint64_t>(float_to_ordered(seed)) << 32;
     }
   }
+  const bool track_min = a.min_out != nullptr;
+  float lowest = INFINITY;
   uint32_t buf = 0, acc_phase = 0;
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_phase);
@@ -306,6 +309,12 @@ __device__ __forceinline__ void epilogue_scan(const MmaArgs& a, const uint32_t t
       float m = __uint_as_float(v[0]);
 #pragma unroll
       for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+      if (track_min) {   // block-uniform; rows past the end of the shard read as 0, which can only lower the minimum
+        float mn = __uint_as_float(v[0]);
+#pragma unroll
+        for (int i = 1; i < 32; ++i) mn = fminf(mn, __uint_as_float(v[i]));
+        lowest = fminf(lowest, mn);
+      }
       if (__any_sync(0xffffffffu, m >= st.thr_score)) {
         // room for a whole chunk is guaranteed up front, so the admission loop has no votes in it
         const unsigned full = __ballot_sync(0xffffffffu, st.cnt > LIST_CAP - 32);
@@ -353,6 +362,12 @@ __device__ __forceinline__ void epilogue_scan(const MmaArgs& a, const uint32_t t
   if (query < a.n_queries) {
     uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.lists_per_query + group * 2 + half) * a.k;
     for (int j = 0; j < a.k; ++j) dst[j] = j < cnt ? __ldcg(reinterpret_cast<const unsigned long long*>(my_list + j)) : 0ull;
+    if (track_min && lowest < INFINITY) {
+      // float minimum through integer atomics on the raw bits: non-negative floats order like signed ints, negative
+      // ones in reverse like unsigned ints, and every negative pattern is larger (unsigned) than every positive one
+      if (lowest >= 0.0f) atomicMin(reinterpret_cast<int*>(a.min_out + query), __float_as_int(lowest));
+      else atomicMax(reinterpret_cast<unsigned*>(a.min_out + query), __float_as_uint(lowest));
+    }
   }
 }
 
@@ -1052,6 +1067,7 @@ static MmaPlan mma_plan(bool pair, int n_queries, int tiles, int sms) {
 struct MmaRange {
   int tile_lo, tile_hi;       // passage tiles [tile_lo, tile_hi)
   const float* seed_thr;      // optional [n_queries] proven lower bounds of the k-th best score
+  float* min_out;             // optional [n_queries] running minimum of all scores (see ragb_dense_mma_topk_min)
   uint64_t* part;             // [n_queries, lists_per_query, k]
   int lists_per_query;        // >= 2 * groups of this launch
 };
@@ -1085,6 +1101,7 @@ static int launch_mma(const void* passages, int64_t n_rows, int dim, const void*
   a.tile_lo = r.tile_lo;
   a.tile_hi = r.tile_hi;
   a.seed_thr = r.seed_thr;
+  a.min_out = r.min_out;
   a.part_keys = r.part;
   a.lists_per_query = r.lists_per_query;
   a.progress = progress;
@@ -1137,6 +1154,7 @@ static int launch_mma_pair(const void* passages, int64_t n_rows, int dim, const 
   a.tile_lo = r.tile_lo;
   a.tile_hi = r.tile_hi;
   a.seed_thr = r.seed_thr;
+  a.min_out = r.min_out;
   a.part_keys = r.part;
   a.lists_per_query = r.lists_per_query;
   a.progress = progress;
@@ -1276,13 +1294,14 @@ static int mma_common_checks(const char* who, const void* passages_bf16, int64_t
 
 // phase 1: search the sampled prefix, leave its merged list in the workspace, report the per-query k-th best score
 static int mma_sample_phase(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
-                            int64_t id_base, int variant, float* thr_out, const MmaWorkspace& w, cudaStream_t stream) {
+                            int64_t id_base, int variant, float* thr_out, const MmaWorkspace& w, cudaStream_t stream,
+                            float* min_out = nullptr) {
   const int n_tiles = static_cast<int>(ceil_div64(n_rows, mma_tile_rows(variant)));
   const int ts = mma_sample_tiles(n_tiles);
   if (ts == 0)   // no prefix: merging zero lists leaves an empty sample list and the bound -inf for every query
     return launch_merge_keys_ex(w.part, n_queries, 0, k, nullptr, 0, k, nullptr, nullptr, w.sample_keys, thr_out, stream);
   const MmaPlan plan = mma_plan(mma_uses_pairs(variant, n_queries), n_queries, ts, device_sm_count());
-  const MmaRange r{0, ts, nullptr, w.part, 2 * plan.n_groups};
+  const MmaRange r{0, ts, nullptr, min_out, w.part, 2 * plan.n_groups};
   int rc = mma_dispatch(variant, passages, n_rows, dim, queries, n_queries, k, id_base, r, w, stream);
   if (rc != RAGB_OK) return rc;
   return launch_merge_keys_ex(w.part, n_queries, 2 * plan.n_groups, k, nullptr, 0, k, nullptr, nullptr, w.sample_keys, thr_out,
@@ -1292,11 +1311,11 @@ static int mma_sample_phase(const void* passages, int64_t n_rows, int dim, const
 // phase 2: the rest of the tiles, every list seeded with thr (own or exchanged between shards), final merge
 static int mma_seeded_phase(const void* passages, int64_t n_rows, int dim, const void* queries, int n_queries, int k,
                             int64_t id_base, int variant, const float* thr, float* out_score, int32_t* out_id,
-                            const MmaWorkspace& w, cudaStream_t stream) {
+                            const MmaWorkspace& w, cudaStream_t stream, float* min_out = nullptr) {
   const int n_tiles = static_cast<int>(ceil_div64(n_rows, mma_tile_rows(variant)));
   const int ts = mma_sample_tiles(n_tiles);
   const MmaPlan plan = mma_plan(mma_uses_pairs(variant, n_queries), n_queries, n_tiles - ts, device_sm_count());
-  const MmaRange r{ts, n_tiles, thr, w.part, 2 * plan.n_groups};
+  const MmaRange r{ts, n_tiles, thr, min_out, w.part, 2 * plan.n_groups};
   int rc = mma_dispatch(variant, passages, n_rows, dim, queries, n_queries, k, id_base, r, w, stream);
   if (rc != RAGB_OK) return rc;
   return launch_merge_keys_ex(w.part, n_queries, 2 * plan.n_groups, k, w.sample_keys, k, k, out_score, out_id, nullptr, nullptr,
@@ -1330,6 +1349,25 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim, 
   if (rc != RAGB_OK) return rc;
   return mma_seeded_phase(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant, thr, out_score, out_id, w,
                           stream);
+}
+
+int ragb_dense_mma_topk_min(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
+                            int32_t n_queries, int32_t k, int64_t id_base, int32_t variant, float* out_score,
+                            int32_t* out_id, float* min_inout, void* workspace, size_t workspace_bytes,
+                            ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(out_score && out_id && min_inout, RAGB_EINVAL, "ragb_dense_mma_topk_min: null pointer");
+  RAGB_REQUIRE(workspace_bytes >= ragb_dense_mma_workspace_bytes(n_queries, k), RAGB_ENOSPC, "ragb_dense_mma_topk_min: workspace too small");
+  int rc = mma_common_checks("ragb_dense_mma_topk_min", passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant,
+                             workspace, workspace_bytes);
+  if (rc != RAGB_OK) return rc;
+  const MmaWorkspace w = mma_carve(workspace, n_queries, k);
+  float* thr = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + mma_workspace_bytes(n_queries, k));
+  rc = mma_sample_phase(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant, thr, w, stream, min_inout);
+  if (rc != RAGB_OK) return rc;
+  return mma_seeded_phase(passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, variant, thr, out_score, out_id, w,
+                          stream, min_inout);
 }
 
 int ragb_dense_mma_sample(const void* passages_bf16, int64_t n_rows, int32_t dim, const void* queries_bf16,
@@ -1411,7 +1449,7 @@ int ragb_dense_mma_fused_topk(const void* passages_bf16, int64_t n_rows, int32_t
   const bool pair = n_queries > MM_BM;   // a lone slab has no partner for a CTA pair
   const int n_tiles = static_cast<int>(ceil_div64(n_rows, MM2_BN));
   const MmaPlan plan = mma_plan(pair, n_queries, n_tiles, device_sm_count());
-  const MmaRange r{0, n_tiles, nullptr, w.part, 2 * plan.n_groups};
+  const MmaRange r{0, n_tiles, nullptr, nullptr, w.part, 2 * plan.n_groups};
 #define RAGB_FUSED_ARGS passages_bf16, n_rows, dim, queries_bf16, n_queries, k, id_base, r, w.progress, w.lists, 0, stream, &f
   if (!pair) {
     if (kpl == 2) rc = launch_mma<256, false, 2, true>(RAGB_FUSED_ARGS);

@@ -282,9 +282,10 @@ class HybridEngine:
 
         fused(b, d) = b + g(b, d) (d - b) is bounded from above by a function E that is monotone in both scores
         (``router.full_fusion_envelope``).  So: (1) the streaming kernels deliver the ``depth`` best passages of each
-        side, exactly; (2) every listed passage gets its OTHER score (ragb_bm25_score_docs / ragb_dense_score_docs) and
-        its exact gate and fused score; (3) any passage on neither list has bm25 <= b_depth and dense <= d_depth, hence
-        fused <= E(b_depth, d_depth): if that is below the k-th best fused score found, the top-k is proven complete.
+        side, exactly, and the dense kernel also the smallest dense score of the shard; (2) every listed passage gets its
+        OTHER score (ragb_bm25_score_docs / ragb_dense_score_docs) and its exact gate and fused score; (3) any passage on
+        neither list has bm25 <= b_depth and d_min <= dense <= d_depth, hence fused <= max E(b_depth, [d_min, d_depth]):
+        if that is below the k-th best fused score found, the top-k is proven complete.
         Queries for which it is not (a gate that ignores both scores' order, a flat score distribution) are re-run
         through the exhaustive epilogue.  Oracle: RetrievalRouter.hybrid_rerank(bm25[B,N], dense[B,N], k)."""
         if not getattr(router, "stats_initialized", False):
@@ -297,7 +298,7 @@ class HybridEngine:
         e0 = _mark(events)
         bs, bi = self.sparse.score_topk(q_terms, q_off, max_terms, depth)
         e1 = _mark(events)
-        ds, di = ops.dense_mma_topk(self.passages, q_emb, depth, self.id_base, self.mma_variant)
+        ds, di, d_lowest = ops.dense_mma_topk_min(self.passages, q_emb, depth, self.id_base, self.mma_variant)
         e2 = _mark(events)
         # union of the two lists: a passage on both keeps its BM25-list slot
         dup = (di.unsqueeze(2) == bi.unsqueeze(1)).any(dim=2) & (di >= 0)
@@ -322,9 +323,13 @@ class HybridEngine:
         n_b, n_d = env.shape
         b_last = torch.where(bi[:, -1] >= 0, bs[:, -1], torch.zeros_like(bs[:, -1]))
         d_last = ds[:, -1] + 2e-6                        # tensor-core vs fp32 summation order
+        d_first = d_lowest - 2e-6                        # the smallest dense score any passage of the shard has
         ib = torch.clamp((b_last * (n_b / b_cap)).floor().long(), 0, n_b - 1)
-        idc = torch.clamp(((d_last + d_hi) * (n_d / (2.0 * d_hi))).floor().long(), 0, n_d - 1)
-        unseen = env[ib, idc]
+        id_hi = torch.clamp(((d_last + d_hi) * (n_d / (2.0 * d_hi))).floor().long(), 0, n_d - 1)
+        id_lo = torch.clamp(((d_first + d_hi) * (n_d / (2.0 * d_hi))).floor().long(), 0, n_d - 1)
+        cols = torch.arange(n_d, device=env.device)
+        inside = (cols[None, :] >= id_lo[:, None]) & (cols[None, :] <= id_hi[:, None])
+        unseen = torch.where(inside, env[ib], torch.full((), float("-inf"), device=env.device)).amax(dim=1)
         kth = val[:, kk - 1]
         proven = (unseen <= kth - 1e-5 * kth.abs() - 1e-6) | (depth >= n_local)
         e3 = _mark(events)

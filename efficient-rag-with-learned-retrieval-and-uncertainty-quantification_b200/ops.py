@@ -331,6 +331,28 @@ def _(passages, queries, k, id_base, variant):
     return (queries.new_empty((n_q, k), dtype=torch.float32), queries.new_empty((n_q, k), dtype=torch.int32))
 
 
+@torch.library.custom_op(f"{NS}::dense_mma_topk_min", mutates_args=(), device_types="cuda")
+def dense_mma_topk_min(passages: Tensor, queries: Tensor, k: int, id_base: int, variant: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """``dense_mma_topk`` plus the smallest score of every query over the shard (a proven lower bound of it)."""
+    passages, queries = _dense_args(passages, queries)
+    n_q, dev = queries.shape[0], passages.device
+    score = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    lowest = torch.full((n_q,), float("inf"), dtype=torch.float32, device=dev)
+    ws = _workspace(lib.ragb_dense_mma_workspace_bytes(n_q, k), dev)
+    with torch.cuda.device(dev):
+        check(lib.ragb_dense_mma_topk_min(_ptr(passages), passages.shape[0], passages.shape[1], _ptr(queries), n_q, k, id_base,
+                                          variant, _ptr(score), _ptr(ids), _ptr(lowest), _ptr(ws), ws.numel(), _stream()))
+    return score, ids, lowest
+
+
+@dense_mma_topk_min.register_fake
+def _(passages, queries, k, id_base, variant):
+    n_q = queries.shape[0]
+    return (queries.new_empty((n_q, k), dtype=torch.float32), queries.new_empty((n_q, k), dtype=torch.int32),
+            queries.new_empty((n_q,), dtype=torch.float32))
+
+
 @torch.library.custom_op(f"{NS}::dense_mma_sample", mutates_args=(), device_types="cuda")
 def dense_mma_sample(passages: Tensor, queries: Tensor, k: int, id_base: int, variant: int) -> Tuple[Tensor, Tensor]:
     """Phase 1 of the seeded tcgen05 search (ragb200.h): -> (thr float32 [B], workspace uint8).  ``thr`` may be raised to

@@ -170,7 +170,7 @@ class RetrievalRouter(nn.Module):
 
     def full_fusion_envelope(self, b_cap: float, d_hi: float, n_b: int = 128, n_d: int = 64) -> torch.Tensor:
         """float32 [n_b, n_d] on the router's device: E[ib, id] >= fused(b', d') for EVERY b' <= (ib + 1) b_cap / n_b and
-        d' <= -d_hi + (id + 1) 2 d_hi / n_d (``full_fusion_envelope`` below); cached like the bound table."""
+        every d' in column id (``full_fusion_envelope`` below); cached like the bound table."""
         tensors = list(self._weights()[:4]) + [self.bm25_mean, self.bm25_std, self.dense_mean, self.dense_std]
         key = ("env", float(b_cap), float(d_hi), int(n_b), int(n_d), tuple((t.data_ptr(), t._version) for t in tensors))
         cache = self.__dict__.setdefault("_env_cache", {})
@@ -299,13 +299,15 @@ def full_fusion_bounds(w1, b1, w2, b2, stats, b_cap: float, d_hi: float, n_b: in
 
 
 def full_fusion_envelope(w1, b1, w2, b2, stats, b_cap: float, d_hi: float, n_b: int = 128, n_d: int = 64) -> np.ndarray:
-    """Monotone upper envelope of the fused score over the (bm25, dense) grid of ``full_fusion_gate_range``.
+    """Upper envelope, monotone in the BM25 score, of the fused score over the grid of ``full_fusion_gate_range``.
 
     fused(b, d) = b + g (d - b) with lo <= g <= hi on a cell is linear in g and bilinear in (b, d), so over a cell it is
     at most the maximum over the four corners and the two gate bounds; E[ib, id] is the running maximum of that over all
-    cells (ib', id') <= (ib, id): a proven bound on the fused score of ANY passage whose BM25 score is at most the upper
-    edge of row ib and whose dense score is at most the upper edge of column id - the stopping rule of the
-    threshold-algorithm search (engine.full_fusion_topk).  float32 [n_b, n_d], rounded up."""
+    rows ib' <= ib of column id: a proven bound on the fused score of ANY passage whose BM25 score is at most the upper
+    edge of row ib and whose dense score lies in column id.  The maximum of E[ib, id_lo .. id_hi] therefore bounds every
+    passage with bm25 <= b and d_lo <= dense <= d_hi - the stopping rule of the threshold-algorithm search
+    (engine.full_fusion_topk).  The dense range has to be two-sided: the gate moves with the dense score, and
+    (1 - g) * bm25 evaluated at dense scores no passage has would inflate the bound.  float32 [n_b, n_d], rounded up."""
     lo, hi = full_fusion_gate_range(w1, b1, w2, b2, stats, b_cap, d_hi, n_b, n_d)
     b_edges = np.arange(n_b + 1, dtype=np.float64) * (b_cap / n_b)
     d_edges = -d_hi + np.arange(n_d + 1, dtype=np.float64) * (2.0 * d_hi / n_d)
@@ -315,7 +317,7 @@ def full_fusion_envelope(w1, b1, w2, b2, stats, b_cap: float, d_hi: float, n_b: 
             diff = dd[None, :] - bb[:, None]
             for g in (lo, hi):
                 cell = np.maximum(cell, bb[:, None] + g * diff)
-    env = np.maximum.accumulate(np.maximum.accumulate(cell, axis=0), axis=1)
+    env = np.maximum.accumulate(cell, axis=0)
     out = env.astype(np.float32)
     return np.where(out.astype(np.float64) < env, np.nextafter(out, np.float32(np.inf)), out).astype(np.float32)
 

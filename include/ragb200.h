@@ -168,6 +168,15 @@ int ragb_dense_mma_topk(const void* passages_bf16, int64_t n_rows, int32_t dim,
                         const void* queries_bf16, int32_t n_queries, int32_t k, int64_t id_base,
                         int32_t variant, float* out_score, int32_t* out_id,
                         void* workspace, size_t workspace_bytes, ragb_stream_t stream);
+/* ragb_dense_mma_topk that ALSO reports the smallest score of every query: min_inout[n_queries] must hold +inf (or
+ * a running minimum of other shards) on entry and receives min(min_inout[q], min over this shard's rows of the score);
+ * rows past the end of the shard count as 0 (the result is a valid LOWER bound of the true minimum).  With the k-th
+ * largest dense score it brackets the dense score of every passage outside the top-k list - what the stopping rule of
+ * the threshold-algorithm full-fusion needs (engine.full_fusion_topk). */
+int ragb_dense_mma_topk_min(const void* passages_bf16, int64_t n_rows, int32_t dim,
+                            const void* queries_bf16, int32_t n_queries, int32_t k, int64_t id_base,
+                            int32_t variant, float* out_score, int32_t* out_id, float* min_inout,
+                            void* workspace, size_t workspace_bytes, ragb_stream_t stream);
 /* The same search in its two phases, for callers that shard the corpus.  On large shards ragb_dense_mma_topk
  * first searches a sampled prefix (1/32 of the passage tiles): the k-th best score found there is a proven lower
  * bound of the final k-th best, and every candidate list of the remaining tiles starts from it instead of from

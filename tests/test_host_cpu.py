@@ -298,8 +298,9 @@ def test_full_fusion_gate_bounds_are_proven_bounds(rq, hidden, scale):
 
 @pytest.mark.parametrize("hidden,scale", [(64, 1.0), (16, 20.0), (32, 4.0)])
 def test_full_fusion_envelope_is_a_monotone_proven_bound(rq, hidden, scale):
-    """router.full_fusion_envelope: E[ib, id] bounds the fused score of every (bm25, dense) at or below the cell - the
-    stopping rule of the threshold-algorithm full-fusion search - and is monotone in both directions."""
+    """router.full_fusion_envelope: the maximum of E[ib, id_lo..id_hi] bounds the fused score of every (bm25, dense) with
+    bm25 at or below row ib and dense inside the column range - the stopping rule of the threshold-algorithm
+    full-fusion search - and E is monotone in the BM25 direction."""
     from rag_uq_b200.router import full_fusion_envelope
     torch.manual_seed(hidden)
     lin1, lin2 = torch.nn.Linear(3, hidden), torch.nn.Linear(hidden, 1)
@@ -308,7 +309,7 @@ def test_full_fusion_envelope_is_a_monotone_proven_bound(rq, hidden, scale):
     stats = np.array([8.0, 6.0, 0.2, 0.3], dtype=np.float32)
     b_cap, d_hi, n_b, n_d = 32.0, 1.02, 128, 64
     env = full_fusion_envelope(w1, b1, w2, b2, stats, b_cap, d_hi, n_b, n_d)
-    assert env.shape == (n_b, n_d) and (np.diff(env, axis=0) >= 0).all() and (np.diff(env, axis=1) >= 0).all()
+    assert env.shape == (n_b, n_d) and (np.diff(env, axis=0) >= 0).all()
     rng = np.random.default_rng(1)
     n = 200_000
     b = rng.uniform(0, b_cap * 0.999, n).astype(np.float32)
@@ -322,9 +323,13 @@ def test_full_fusion_envelope_is_a_monotone_proven_bound(rq, hidden, scale):
     ib = np.clip(np.floor(b * (n_b / b_cap)).astype(int), 0, n_b - 1)
     idc = np.clip(np.floor((d + d_hi) * (n_d / (2 * d_hi))).astype(int), 0, n_d - 1)
     assert (env[ib, idc] >= fused - 1e-5).all()
-    # ... and of everything BELOW the cell: compare each point with the envelope of a cell up and to the right of it
-    up_b, up_d = np.minimum(ib + rng.integers(0, 20, n), n_b - 1), np.minimum(idc + rng.integers(0, 10, n), n_d - 1)
-    assert (env[up_b, up_d] >= fused - 1e-5).all()
+    # ... and of everything BELOW the row: a point is also bounded by any row above its own, in its own column, and by
+    # the maximum over any column range that contains its column
+    up_b = np.minimum(ib + rng.integers(0, 20, n), n_b - 1)
+    assert (env[up_b, idc] >= fused - 1e-5).all()
+    lo_c, hi_c = np.maximum(idc - rng.integers(0, 5, n), 0), np.minimum(idc + rng.integers(0, 5, n), n_d - 1)
+    ranged = np.array([env[r, a:c + 1].max() for r, a, c in zip(up_b[:5000], lo_c[:5000], hi_c[:5000])])
+    assert (ranged >= fused[:5000] - 1e-5).all()
 
 
 def test_shard_format_round_trip_on_cpu(rq, tmp_path):
