@@ -58,6 +58,7 @@ def parse_args():
     p.add_argument("--ff-method", default="auto", choices=["auto", "threshold", "exhaustive"],
                    help="full-fusion mode: threshold-algorithm search over the two exact ranked lists (default; exhaustive "
                         "epilogue only for queries whose stopping rule does not hold) or the exhaustive [B, N] scan")
+    p.add_argument("--ff-depth", type=int, default=100, help="full-fusion threshold search: length of the two ranked lists")
     p.add_argument("--mc-samples", type=int, default=0, help="MC-Dropout passes over the fused candidates (c4: 30)")
     p.add_argument("--candidates", type=int, default=0, help="fused candidates kept per query before the rerank (c4: 100)")
     p.add_argument("--no-graph", action="store_true",
@@ -383,7 +384,7 @@ def run_ours(args):
             events = {} if probes is not None else None
             if args.mode == "full-fusion":
                 vals, ids = engine.full_fusion_topk(q_terms, q_off, max_terms, q_emb, router, args.k, events=events,
-                                                    method=args.ff_method, info=ff_info)
+                                                    method=args.ff_method, info=ff_info, depth=args.ff_depth)
                 if probes is not None:   # one (start, end) pair per kernel, first to last query chunk
                     probes.append({name: (ev[0][0], ev[-1][1]) for name, ev in events.items()})
                 return ids, vals
