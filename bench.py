@@ -58,7 +58,7 @@ def parse_args():
     p.add_argument("--ff-method", default="auto", choices=["auto", "threshold", "exhaustive"],
                    help="full-fusion mode: threshold-algorithm search over the two exact ranked lists (default; exhaustive "
                         "epilogue only for queries whose stopping rule does not hold) or the exhaustive [B, N] scan")
-    p.add_argument("--ff-depth", type=int, default=100, help="full-fusion threshold search: length of the two ranked lists")
+    p.add_argument("--ff-depth", type=int, default=64, help="full-fusion threshold search: length of the two ranked lists")
     p.add_argument("--mc-samples", type=int, default=0, help="MC-Dropout passes over the fused candidates (c4: 30)")
     p.add_argument("--candidates", type=int, default=0, help="fused candidates kept per query before the rerank (c4: 100)")
     p.add_argument("--no-graph", action="store_true",
@@ -504,7 +504,7 @@ def run_ours(args):
                                     (f"full-fusion top-{args.k}: BM25 get_scores matrix + tcgen05 GEMM with router gate, learned "
                                      f"fusion and top-k in the epilogue (every (query, passage) pair)" if args.ff_method == "exhaustive" else
                                      f"full-fusion top-{args.k} (RetrievalRouter.hybrid_rerank over ALL passages) as a threshold-algorithm "
-                                     f"search: exact BM25 top-100 + exact dense top-100 (tcgen05), the other score of every listed passage, "
+                                     f"search: exact BM25 top-{args.ff_depth} + exact dense top-{args.ff_depth} (tcgen05), the other score of every listed passage, "
                                      f"gate + fusion, proven stopping bound; exhaustive epilogue for queries where it does not hold"))
                                    + f"; {args.passages} passages x {DIM} "
                                    f"bf16 row-sharded over {world} GPU(s), batch {args.batch} queries x 8 terms",

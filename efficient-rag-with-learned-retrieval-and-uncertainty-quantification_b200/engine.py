@@ -265,7 +265,7 @@ class HybridEngine:
 
     def full_fusion_topk(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, router, k: int = 10,
                          query_chunk: Optional[int] = None, fused: Optional[bool] = None, counters: Optional[Tensor] = None,
-                         events=None, method: str = "auto", depth: int = 100, info: Optional[dict] = None):
+                         events=None, method: str = "auto", depth: int = 64, info: Optional[dict] = None):
         """Gate evaluated on the true scores of every (query, passage) pair: the k best fused scores per query.
 
         ``method`` "auto" (default) / "threshold": the threshold-algorithm search below, with the exhaustive epilogue as
@@ -294,7 +294,9 @@ class HybridEngine:
         if int(self.sparse.id_base) != int(self.id_base):
             raise ValueError("the BM25 shard and the engine number their passages from different bases "
                              f"({self.sparse.id_base} vs {self.id_base}): the two ranked lists could not be joined")
-        depth = max(k, min(depth, _lib.MMA_MAX_TOPK, n_local))
+        # two ranked lists of `depth` passages each (at least 2 k: the rule needs the depth-th score clearly below the
+        # k-th); 64 measured best at k = 10 on 10M passages (31.6 ms against 32.8 ms at 100, one fallback query either way)
+        depth = max(k, min(max(depth, 2 * k), _lib.MMA_MAX_TOPK, n_local))
         e0 = _mark(events)
         bs, bi = self.sparse.score_topk(q_terms, q_off, max_terms, depth)
         e1 = _mark(events)
