@@ -8,7 +8,7 @@ Importing this package loads libragb200.so and fails loudly if it has not been b
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
 from . import ops  # noqa: F401   (registers the torch.library custom ops)
 from .confidence import ConfidenceResult, MCDropoutConfidence, RouterUncertainty
-from .engine import HybridEngine, gather_candidates, global_bm25_statistics, shard_rows
+from .engine import HybridEngine, exchange_pools, gather_candidates, global_bm25_statistics, shard_rows
 from .retrieval import BM25Index, DenseIndex, Document, HybridRetriever, RetrievalResult, StreamingIndex
 from .router import RetrievalRouter, RouterConfig
 from .shard_io import load_engine, load_shard, save_engine, save_shard
@@ -18,6 +18,6 @@ __version__ = "0.1.0"
 __all__ = [
     "RetrievalRouter", "RouterConfig", "MCDropoutConfidence", "ConfidenceResult", "RouterUncertainty",
     "HybridRetriever", "StreamingIndex", "BM25Index", "DenseIndex", "Document", "RetrievalResult",
-    "HybridEngine", "SparseShard", "SegmentedIndex", "build_shard", "build_shard_blocked", "shard_rows", "gather_candidates",
+    "HybridEngine", "SparseShard", "SegmentedIndex", "build_shard", "build_shard_blocked", "shard_rows", "gather_candidates", "exchange_pools",
     "global_bm25_statistics", "save_shard", "load_shard", "save_engine", "load_engine",
 ]

@@ -79,6 +79,7 @@ SIGNATURES = {
     "ragb_topk_rows_workspace_bytes": (_sz, [_i32, _i64, _i32]),
     "ragb_topk_rows": (C.c_int, [_p, _i32, _i64, _i32, _p, _p, _p, _sz, _p]),
     "ragb_topk_merge": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
+    "ragb_topk_merge_strided": (C.c_int, [_p, _p, _i32, _i32, _i32, _i64, _i64, _i32, _p, _p, _p]),
     "ragb_hybrid_fuse_topk": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "ragb_retrieval_uncertainty": (C.c_int, [_p, _p, _i32, _i32, _f64, _p, _p]),
     "ragb_router_scratch_bytes": (_sz, [_i32, _i32]),

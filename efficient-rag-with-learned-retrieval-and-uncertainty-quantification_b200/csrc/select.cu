@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_merge_kernel(const uint64_t*
                                                                  int32_t* __restrict__ out_id,
                                                                  const uint64_t* __restrict__ extra_keys, int k_extra,
                                                                  uint64_t* __restrict__ out_keys,
-                                                                 float* __restrict__ out_thr) {
+                                                                 float* __restrict__ out_thr, int64_t query_stride,
+                                                                 int64_t list_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
   __shared__ SelSmem st;
@@ -110,8 +111,12 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_merge_kernel(const uint64_t*
         if (in_keys != nullptr) {
           key = in_keys[off + idx];
         } else {
-          int32_t id = in_id[off + idx];
-          key = id >= 0 ? make_key(in_score[off + idx], id) : 0ull;
+          // (score, id) arrays: contiguous [n_queries, n_lists, k_in] when the strides are 0, else element
+          // (q, list, j) lives at q * query_stride + list * list_stride + j (the all-gathered exchange buffer)
+          const int64_t at = list_stride == 0 ? off + idx
+                                              : static_cast<int64_t>(q) * query_stride + (idx / k_in) * list_stride + idx % k_in;
+          int32_t id = in_id[at];
+          key = id >= 0 ? make_key(in_score[at], id) : 0ull;
         }
         tk.offer(key, thr);  // key 0 never beats a threshold
       }
@@ -336,7 +341,7 @@ int launch_merge_keys_ex(const uint64_t* keys, int n_queries, int n_lists, int k
                          cudaStream_t stream) {
   const int capacity = topk_capacity(k_out);
   topk_merge_kernel<<<n_queries, SEL_THREADS, capacity * sizeof(uint64_t), stream>>>(
-      keys, nullptr, nullptr, n_lists, k_in, k_out, capacity, out_score, out_id, extra_keys, k_extra, out_keys, out_thr);
+      keys, nullptr, nullptr, n_lists, k_in, k_out, capacity, out_score, out_id, extra_keys, k_extra, out_keys, out_thr, 0, 0);
   RAGB_AFTER_LAUNCH(1);
   return RAGB_OK;
 }
@@ -428,7 +433,25 @@ int ragb_topk_merge(const float* in_score, const int32_t* in_id, int32_t n_queri
                RAGB_MAX_TOPK);
   const int capacity = topk_capacity(k_out);
   topk_merge_kernel<<<n_queries, SEL_THREADS, capacity * sizeof(uint64_t), stream>>>(
-      nullptr, in_score, in_id, n_lists, k_in, k_out, capacity, out_score, out_id, nullptr, 0, nullptr, nullptr);
+      nullptr, in_score, in_id, n_lists, k_in, k_out, capacity, out_score, out_id, nullptr, 0, nullptr, nullptr, 0, 0);
+  RAGB_AFTER_LAUNCH(1);
+  return RAGB_OK;
+}
+
+int ragb_topk_merge_strided(const float* in_score, const int32_t* in_id, int32_t n_queries, int32_t n_lists, int32_t k_in,
+                            int64_t query_stride, int64_t list_stride, int32_t k_out, float* out_score, int32_t* out_id,
+                            ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(in_score && in_id && out_score && out_id, RAGB_EINVAL, "ragb_topk_merge_strided: null pointer");
+  RAGB_REQUIRE(n_queries > 0 && n_lists > 0 && k_in > 0 && query_stride > 0 && list_stride > 0, RAGB_EINVAL,
+               "ragb_topk_merge_strided: bad shape");
+  RAGB_REQUIRE(k_out > 0 && k_out <= RAGB_MAX_TOPK, RAGB_ELIMIT, "ragb_topk_merge_strided: k_out=%d outside [1,%d]", k_out,
+               RAGB_MAX_TOPK);
+  const int capacity = topk_capacity(k_out);
+  topk_merge_kernel<<<n_queries, SEL_THREADS, capacity * sizeof(uint64_t), stream>>>(
+      nullptr, in_score, in_id, n_lists, k_in, k_out, capacity, out_score, out_id, nullptr, 0, nullptr, nullptr, query_stride,
+      list_stride);
   RAGB_AFTER_LAUNCH(1);
   return RAGB_OK;
 }

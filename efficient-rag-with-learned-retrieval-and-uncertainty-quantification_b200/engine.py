@@ -25,6 +25,8 @@ from . import _lib, ops
 from .sparse import SparseShard
 
 
+# sharded search: raise the pruning bounds of both kernels to their maximum over the shards before the kernels run
+EXCHANGE_BOUNDS = os.environ.get("RAGB_EXCHANGE_BOUNDS", "1") != "0"
 OVERLAP_FRACTION = float(os.environ.get("RAGB_OVERLAP_FRACTION", "1.0"))   # share of the BM25 stripes scored beside the GEMM
 OVERLAP_SMEM_PAD = int(os.environ.get("RAGB_OVERLAP_SMEM_KB", "0")) * 1024     # shared memory per BM25 block while it is
 
@@ -63,6 +65,22 @@ def gather_candidates(score: Tensor, ids: Tensor, group=None) -> Tuple[Tensor, T
     gathered = flat.view(world, b, 2, k)
     return (gathered[:, :, 0].permute(1, 0, 2).contiguous().view(torch.float32),
             gathered[:, :, 1].permute(1, 0, 2).contiguous())
+
+
+def exchange_pools(bs: Tensor, bi: Tensor, ds: Tensor, di: Tensor, group=None):
+    """The one exchange of a sharded hybrid search: all-gather the two local pools of every rank ([B, 2, 2 * pool] int32 per
+    rank: fp32 score bit patterns next to the ids, ONE collective) and merge each side over the ranks straight out of the
+    gathered buffer (ragb_topk_merge_strided: no transposing copies).  -> global (bs, bi, ds, di), identical on every rank."""
+    world = dist.get_world_size(group)
+    n_q, pool = bs.shape
+    packed = torch.empty((n_q, 2, 2 * pool), dtype=torch.int32, device=bs.device)
+    packed[:, 0, :pool], packed[:, 0, pool:] = bs.view(torch.int32), ds.view(torch.int32)
+    packed[:, 1, :pool], packed[:, 1, pool:] = bi, di
+    gathered = torch.empty((world, n_q, 2, 2 * pool), dtype=torch.int32, device=bs.device)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    gbs, gbi = ops.topk_merge_gathered(gathered, 0, pool)
+    gds, gdi = ops.topk_merge_gathered(gathered, 1, pool)
+    return gbs, gbi, gds, gdi
 
 
 class HybridEngine:
@@ -128,11 +146,13 @@ class HybridEngine:
         # seed; the k-th best of the dense kernel's sampled prefix).  The k-th best of the WHOLE corpus is at least
         # the k-th best of any shard, so the bounds are raised to their maximum over the shards first: one tiny
         # all-reduce ([2, B] floats, latency-bound) in front of the two kernels.  Results do not depend on it.
-        exchange = self.world > 1 and big and hasattr(self.sparse, "seed")
+        exchange = self.world > 1 and big and hasattr(self.sparse, "seed") and EXCHANGE_BOUNDS
         if exchange:
             t0 = mark() if events is not None else None
             b_seed = self.sparse.seed(q_terms, q_off, max_terms, pool)
+            ta = mark() if events is not None else None
             d_thr, d_ws = ops.dense_mma_sample(self.passages, q_emb, pool, self.id_base, self.mma_variant)
+            tb = mark() if events is not None else None
             both = torch.stack([b_seed, d_thr])
             dist.all_reduce(both, op=dist.ReduceOp.MAX, group=self.group)
             t1 = mark() if events is not None else None
@@ -140,7 +160,8 @@ class HybridEngine:
             t2 = mark() if events is not None else None
             ds, di = ops.dense_mma_seeded(self.passages, q_emb, pool, self.id_base, self.mma_variant, both[1], d_ws)
             if events is not None:
-                events["seed_exchange"], events["bm25"], events["dense"] = (t0, t1), (t1, t2), (t2, mark())
+                events["bm25_seed"], events["dense_prefix"], events["seed_exchange"] = (t0, ta), (ta, tb), (tb, t1)
+                events["bm25"], events["dense"] = (t1, t2), (t2, mark())
             return bs, bi, ds, di
 
         if not (overlap and big):
@@ -199,14 +220,7 @@ class HybridEngine:
         """-> ids int32 [B,k] (-1 pads), bm25 [B,k], dense [B,k], hybrid [B,k]."""
         bs, bi, ds, di = self.local_pools(q_terms, q_off, max_terms, q_emb, pool, overlap)
         if self.world > 1:
-            # one exchange for both pools: [B, 2, pool] score + id
-            s = torch.stack([bs, ds], dim=1).reshape(bs.shape[0], 2 * pool)
-            i = torch.stack([bi, di], dim=1).reshape(bs.shape[0], 2 * pool)
-            gs, gi = gather_candidates(s, i, self.group)          # [B, G, 2*pool]
-            gs = gs.view(bs.shape[0], self.world, 2, pool)
-            gi = gi.view(bs.shape[0], self.world, 2, pool)
-            bs, bi = ops.topk_merge(gs[:, :, 0].contiguous(), gi[:, :, 0].contiguous(), pool)
-            ds, di = ops.topk_merge(gs[:, :, 1].contiguous(), gi[:, :, 1].contiguous(), pool)
+            bs, bi, ds, di = exchange_pools(bs, bi, ds, di, self.group)
         return ops.hybrid_fuse_topk(bs, bi, ds, di, k)
 
     def retrieve_and_rerank(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, router, k: int = 10,

@@ -563,6 +563,33 @@ def _(scores, ids, k_out):
     return scores.new_empty((scores.shape[0], k_out)), ids.new_empty((scores.shape[0], k_out))
 
 
+@torch.library.custom_op(f"{NS}::topk_merge_gathered", mutates_args=(), device_types="cuda")
+def topk_merge_gathered(gathered: Tensor, side: int, k_out: int) -> Tuple[Tensor, Tensor]:
+    """Merge one side of the all-gathered exchange buffer in place: ``gathered`` int32 [G, B, 2, n_sides * pool] holds, per
+    rank and query, the fp32 score bit patterns (index 0) and the ids (index 1) of n_sides pools next to each other;
+    -> the best k_out of pool ``side`` over all ranks, (score [B, k_out], ids [B, k_out])."""
+    gathered = _need(gathered, torch.int32, "gathered")
+    if gathered.dim() != 4 or gathered.shape[2] != 2:
+        raise ValueError("gathered must be [G, B, 2, n_sides * pool]")
+    n_ranks, n_q, _, width = gathered.shape
+    pool = k_out
+    if width % pool or not (0 <= side < width // pool):
+        raise ValueError("the last dimension must be a whole number of pools of k_out entries")
+    val = torch.empty((n_q, k_out), dtype=torch.float32, device=gathered.device)
+    out = torch.empty((n_q, k_out), dtype=torch.int32, device=gathered.device)
+    base = gathered.data_ptr() + 4 * side * pool
+    with torch.cuda.device(gathered.device):
+        check(lib.ragb_topk_merge_strided(base, base + 4 * width, n_q, n_ranks, pool, 2 * width, n_q * 2 * width, k_out,
+                                          _ptr(val), _ptr(out), _stream()))
+    return val, out
+
+
+@topk_merge_gathered.register_fake
+def _(gathered, side, k_out):
+    n_q = gathered.shape[1]
+    return gathered.new_empty((n_q, k_out), dtype=torch.float32), gathered.new_empty((n_q, k_out))
+
+
 @torch.library.custom_op(f"{NS}::hybrid_fuse_topk", mutates_args=(), device_types="cuda")
 def hybrid_fuse_topk(bm25_score: Tensor, bm25_id: Tensor, dense_score: Tensor, dense_id: Tensor,
                      k: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:

@@ -254,6 +254,12 @@ int ragb_topk_rows(const float* scores, int32_t n_rows, int64_t n_cols, int32_t 
 int ragb_topk_merge(const float* in_score, const int32_t* in_id, int32_t n_queries, int32_t n_lists,
                     int32_t k_in, int32_t k_out, float* out_score, int32_t* out_id,
                     ragb_stream_t stream);
+/* ragb_topk_merge reading the lists in place from a strided buffer: element j of list l of query q is at
+ * q * query_stride + l * list_stride + j (in elements) of in_score / in_id - e.g. the all-gathered exchange buffer
+ * [ranks, queries, 2, pools] of a sharded search, merged without a transposing copy. */
+int ragb_topk_merge_strided(const float* in_score, const int32_t* in_id, int32_t n_queries, int32_t n_lists,
+                            int32_t k_in, int64_t query_stride, int64_t list_stride, int32_t k_out,
+                            float* out_score, int32_t* out_id, ragb_stream_t stream);
 
 /* ---- pool fusion : HybridRetriever.hybrid_search (rag_uq/streaming_index.py:484-523)
  * Union of the two pools by id, missing score = 0.0, each score divided by the union

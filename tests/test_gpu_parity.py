@@ -106,6 +106,63 @@ def _synthetic_corpus(rq, dev, n, seed_shift=0):
     return vocab, cdf, doc_off, doc_tok
 
 
+def test_topk_merge_gathered_reads_the_exchange_buffer_in_place(rq, dev):
+    """ragb_topk_merge_strided on the all-gathered exchange layout [ranks, B, 2, 2 * pool] == ragb_topk_merge on the
+    transposed contiguous copy the round-1 code made (both sides, empty slots, ties across ranks)."""
+    g = torch.Generator().manual_seed(12)
+    ranks, n_q, pool = 5, 37, 50
+    score = torch.rand(ranks, n_q, 2 * pool, generator=g)
+    score[1, :, 10:20] = score[0, :, 10:20]                       # equal scores on two ranks: lower id wins
+    ids = torch.randperm(ranks * n_q * 2 * pool, generator=g).view(ranks, n_q, 2 * pool).to(torch.int32)
+    ids[2, 3, 40:50] = -1                                         # a short list
+    gathered = torch.stack([score.view(torch.int32), ids], dim=2).contiguous().to(dev)      # [G, B, 2, 2 * pool]
+    for side in (0, 1):
+        got_s, got_i = rq.ops.topk_merge_gathered(gathered, side, pool)
+        sl = slice(side * pool, (side + 1) * pool)
+        want_s, want_i = rq.ops.topk_merge(score[:, :, sl].permute(1, 0, 2).contiguous().to(dev),
+                                           ids[:, :, sl].permute(1, 0, 2).contiguous().to(dev), pool)
+        assert torch.equal(got_s, want_s) and torch.equal(got_i, want_i)
+
+
+def test_reference_checkpoint_loads_through_the_module_alias(rq, dev, golden_dir):
+    """A GENUINE reference checkpoint (tests/golden/router_checkpoint.pt: written by the live RouterTrainer.save_checkpoint,
+    router.py:499-508, with its pickled RouterConfig, Adam state and loss history) loads through the documented module
+    alias, and the B200 router answers what the reference module answered after load_checkpoint - with call-wide statistics
+    (stats_initialized is not part of the state dict) and with the running statistics armed."""
+    import sys
+    import rag_uq_b200.router as router_module
+    had = sys.modules.get("rag_uq.router")
+    pkg = sys.modules.get("rag_uq")
+    sys.modules.setdefault("rag_uq", type(sys)("rag_uq"))
+    sys.modules["rag_uq.router"] = router_module                  # INTEGRATION.md section 1
+    try:
+        ckpt = torch.load(golden_dir / "router_checkpoint.pt", map_location="cpu", weights_only=False)
+    finally:
+        if had is None:
+            sys.modules.pop("rag_uq.router", None)
+        else:
+            sys.modules["rag_uq.router"] = had
+        if pkg is None:
+            sys.modules.pop("rag_uq", None)
+    assert set(ckpt) == {"model_state_dict", "optimizer_state_dict", "config", "train_losses", "val_losses"}
+    assert isinstance(ckpt["config"], rq.RouterConfig) and ckpt["config"].hidden_dim == 32 and ckpt["config"].dropout == 0.2
+    router = rq.RetrievalRouter(ckpt["config"])
+    router.load_state_dict(ckpt["model_state_dict"])
+    router = router.to(dev).eval()
+    exp = np.load(golden_dir / "router_checkpoint_expected.npz")
+    np.testing.assert_allclose([float(router.bm25_mean), float(router.bm25_std), float(router.dense_mean), float(router.dense_std)],
+                               exp["running_stats"], rtol=1e-6)
+    b, d = torch.tensor(exp["bm25"], device=dev), torch.tensor(exp["dense"], device=dev)
+    with torch.no_grad():
+        assert router.stats_initialized is False
+        np.testing.assert_allclose(router(b, d).cpu().numpy(), exp["gate_call"], rtol=1e-5, atol=1e-6)
+        vals, idx = router.hybrid_rerank(b, d, top_k=10)
+        np.testing.assert_allclose(vals.cpu().numpy(), exp["rerank_vals"], rtol=1e-5, atol=1e-5)
+        assert np.array_equal(idx.cpu().numpy(), exp["rerank_idx"])
+        router.stats_initialized = True
+        np.testing.assert_allclose(router(b, d).cpu().numpy(), exp["gate_running"], rtol=1e-5, atol=1e-6)
+
+
 def test_bm25_known_answers_through_dropin_api(rq, golden_dir):
     with open(golden_dir / "bm25_known_answers.json") as fh:
         known = json.load(fh)

@@ -92,6 +92,29 @@ def test_router_state_dict_is_reference_compatible(rq, golden_dir):
         rq.RetrievalRouter(rq.RouterConfig(use_batch_norm=True))
 
 
+def test_reference_checkpoint_unpickles_through_the_module_alias(rq, golden_dir):
+    """tests/golden/router_checkpoint.pt was written by the LIVE reference (RouterTrainer.save_checkpoint): its pickled
+    rag_uq.router.RouterConfig resolves to rag_uq_b200's class through the documented alias and the state dict loads."""
+    import sys
+    import rag_uq_b200.router as router_module
+    saved = {k: sys.modules.get(k) for k in ("rag_uq", "rag_uq.router")}
+    sys.modules.setdefault("rag_uq", type(sys)("rag_uq"))
+    sys.modules["rag_uq.router"] = router_module
+    try:
+        ckpt = torch.load(golden_dir / "router_checkpoint.pt", map_location="cpu", weights_only=False)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    assert type(ckpt["config"]) is rq.RouterConfig and ckpt["config"].hidden_dim == 32
+    router = rq.RetrievalRouter(ckpt["config"])
+    missing, unexpected = router.load_state_dict(ckpt["model_state_dict"], strict=True)
+    assert not missing and not unexpected and len(ckpt["train_losses"]) == 6
+    assert float(router.bm25_std) != 1.0                      # the EMA statistics of the training steps came along
+
+
 def test_synth_is_deterministic_and_shardable(rq):
     from rag_uq_b200 import synth
     a = synth.passage_embeddings(100, 228, 64, "cpu")
