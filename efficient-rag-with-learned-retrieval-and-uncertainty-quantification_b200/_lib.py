@@ -54,10 +54,10 @@ SIGNATURES = {
     "ragb_bm25_build_dense_table": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _p, _i64, _p]),
     "ragb_bm25_build_impact_bounds": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p]),
     "ragb_bm25_topk_workspace_bytes": (_sz, [_i32, _i64, _i32]),
-    "ragb_bm25_score_topk": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _p, _p, _i32, _i32,
+    "ragb_bm25_score_topk": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _i32,
                                        _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "ragb_bm25_stripe_count": (_i32, [_i32, _i64]),
-    "ragb_bm25_score_part": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _p, _p, _i32, _i32,
+    "ragb_bm25_score_part": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _i32,
                                        _i64, _i64, _i32, _p, _i32, _i32, _i64, _p, _sz, _p]),
     "ragb_bm25_score_finish": (C.c_int, [_i32, _i64, _i32, _p, _p, _p, _sz, _p]),
     "ragb_bm25_seed": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _i32, _i32, _i64, _i32, _p, _p]),

@@ -100,6 +100,11 @@ struct Bm25Args {
   int n_dense;
   const __half* dense_imp;   // optional [n_dense, dense_stride]: fp16 UPPER bound of tf / (tf + norm) per (table term, document)
   const float* dense_maximp; // optional [n_dense]: row maxima of dense_imp (a term contributes at most weight * maximp)
+  // optional impact cap of the table rows: every document of row r whose impact bound exceeds dense_cap[r] is listed in
+  // hi_doc[hi_off[r] .. hi_off[r + 1]) (ascending); all others contribute at most weight * dense_cap[r]
+  const float* dense_cap;
+  const int32_t* hi_off;
+  const int32_t* hi_doc;
   int window_mode;           // > 0: hash-window mode for the pruned phase, aiming at this many postings per window
   float* seed_thr;           // [queries] proven lower bound of each query's k-th best score (0 = none)
   int stripe0;               // this launch covers stripes [stripe0, stripe0 + gridDim.y) of n_stripes
@@ -120,7 +125,9 @@ __device__ __forceinline__ float fast_rcp(float x) {
 // U chunks of 32 postings are loaded per pass (all loads independent) plus one "peek" posting
 // right behind them, so a pass that consumes everything it loaded still learns the next
 // document without another round trip to memory.
-template <int U>
+// MARK_ONLY: a marker list (documents of a table row above its impact cap): no term frequencies, nothing is added to
+// the accumulator, the documents are only marked for exact scoring.
+template <int U, bool MARK_ONLY = false>
 __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc,
                                             const uint16_t* __restrict__ post_tf, int64_t& pos, const int64_t end,
                                             const int d0, const int d1, const float weight, float* accw,
@@ -134,7 +141,7 @@ __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc
       const int64_t idx = pos + u * 32 + lane;
       const bool in = idx < end;
       doc[u] = in ? __ldg(post_doc + idx) : INT_MAX;
-      tf[u] = in ? static_cast<unsigned>(__ldg(post_tf + idx)) : 0u;
+      tf[u] = (in && !MARK_ONLY) ? static_cast<unsigned>(__ldg(post_tf + idx)) : 0u;
     }
     const int64_t peek_idx = pos + U * 32;
     int peek = INT_MAX;
@@ -144,9 +151,11 @@ __device__ __forceinline__ void stream_term(const int32_t* __restrict__ post_doc
     for (int u = 0; u < U; ++u) {
       const bool take = doc[u] < d1;
       if (take) {
-        const float f = static_cast<float>(tf[u]);
         const int o = doc[u] - d0;
-        accw[o] = fmaf(weight, f * fast_rcp(f + __ldg(norm + doc[u])), accw[o]);   // same expression in stream_term_hash
+        if (!MARK_ONLY) {
+          const float f = static_cast<float>(tf[u]);
+          accw[o] = fmaf(weight, f * fast_rcp(f + __ldg(norm + doc[u])), accw[o]);   // same expression in stream_term_hash
+        }
         if (touched != nullptr) atomicOr(touched + (o >> 5), 1u << (o & 31));
       }
       taken += __popc(__ballot_sync(0xffffffffu, take));
@@ -184,13 +193,13 @@ constexpr int BM_HASH_MAX = 352;       // inserts stop being attempted beyond th
 constexpr int BM_WINDOW_MAX = 32768;   // documents per window (offsets must also stay well inside int32)
 
 // Returns false when the table would overflow (nothing usable was changed: the caller restores the cursors).
-template <int U>
+template <int U, bool MARK_ONLY = false>
 __device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ post_doc,
                                                  const uint16_t* __restrict__ post_tf, int64_t& pos, const int64_t end,
                                                  const int d0, const int d1, const float weight, int* keys, float* vals,
                                                  unsigned* flags, const bool essential,
                                                  const float* __restrict__ norm, const int lane, int& next_doc,
-                                                 int& n_keys) {
+                                                 int& n_keys, unsigned* mflags = nullptr) {
   static_assert(U * 32 + BM_HASH_MAX < BM_HASH_SLOTS, "a pass must fit behind the fill limit");
   while (true) {
     if (n_keys > BM_HASH_MAX) return false;
@@ -201,7 +210,7 @@ __device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ pos
       const int64_t idx = pos + u * 32 + lane;
       const bool in = idx < end;
       doc[u] = in ? __ldg(post_doc + idx) : INT_MAX;
-      tf[u] = in ? static_cast<unsigned>(__ldg(post_tf + idx)) : 0u;
+      tf[u] = (in && !MARK_ONLY) ? static_cast<unsigned>(__ldg(post_tf + idx)) : 0u;
     }
     const int64_t peek_idx = pos + U * 32;
     int peek = INT_MAX;
@@ -212,8 +221,11 @@ __device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ pos
       const bool take = doc[u] < d1;
       bool fresh = false;
       if (take) {
-        const float f = static_cast<float>(tf[u]);
-        const float x = f * fast_rcp(f + __ldg(norm + doc[u]));
+        float x = 0.0f;
+        if (!MARK_ONLY) {
+          const float f = static_cast<float>(tf[u]);
+          x = f * fast_rcp(f + __ldg(norm + doc[u]));
+        }
         const int key = doc[u] - d0;
         unsigned slot = (static_cast<unsigned>(key) * 0x9E3779B1u) >> 23;   // 9 bits
         int prev;
@@ -224,7 +236,12 @@ __device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ pos
         }
         fresh = prev == -1;
         // documents of one list are distinct, so no other lane works on this slot's value right now
-        vals[slot] = fmaf(weight, x, fresh ? 0.0f : vals[slot]);
+        if (MARK_ONLY) {
+          if (fresh) vals[slot] = 0.0f;
+          atomicOr(mflags + (slot >> 5), 1u << (slot & 31));   // scored exactly whatever its list part is
+        } else {
+          vals[slot] = fmaf(weight, x, fresh ? 0.0f : vals[slot]);
+        }
         if (essential) atomicOr(flags + (slot >> 5), 1u << (slot & 31));
       }
       taken += __popc(__ballot_sync(0xffffffffu, take));
@@ -305,6 +322,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
   const int nt = min(a.q_off[q + 1] - qb, mt);
   int nd = 0, ns = 0;  // dense / sparse term counts (warp-uniform)
   float ub_lane = 0.0f, ubw_lane = 0.0f;  // this lane's share of the table-term bounds (tight / weights only)
+  const bool use_cap = !DENSE_OUT && a.dense_cap != nullptr;
   for (int base = 0; base < nt; base += 32) {
     const int ti = base + lane;
     int t = -1, slot = -1;
@@ -329,15 +347,25 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
       s_drow[o] = a.dense_tf + static_cast<int64_t>(slot) * a.dense_stride;
       s_irow[o] = a.dense_imp != nullptr ? a.dense_imp + static_cast<int64_t>(slot) * a.dense_stride : nullptr;
       s_dwgt[o] = w;
+      s_nxt[o] = slot;   // table row, until the marker lists have been queued below (s_nxt is rewritten afterwards)
       const float wp = fmaxf(w, 0.0f);
       ubw_lane += wp;
-      ub_lane += a.dense_maximp != nullptr ? wp * a.dense_maximp[slot] : wp;
+      // with an impact cap the row contributes at most w * cap to every document that is NOT on its marker list
+      ub_lane += use_cap ? wp * a.dense_cap[slot] : (a.dense_maximp != nullptr ? wp * a.dense_maximp[slot] : wp);
     }
     if (live && slot < 0) s_tmp[ns + __popc(ms & ((1u << lane) - 1))] = t;
     nd += __popc(md);
     ns += __popc(ms);
   }
   __syncwarp();
+  // Impact-capped table: the few documents of a row above its cap are listed separately; such a "marker list" is
+  // queued like a posting list (negative id = -(row + 1)) that adds nothing and only marks its documents for exact
+  // scoring.  Every other document gets at most w * cap from the row, which is what ub_table now promises.
+  if (use_cap) {
+    for (int i = lane; i < nd; i += 32) s_tmp[ns + i] = -(s_nxt[i] + 1);
+    ns += nd;
+    __syncwarp();
+  }
 
   // A document without any posting-list term scores at most ub_table = sum of the positive weights
   // of the table terms (tf / (tf + norm) < 1).  Once the warp's k-th best score exceeds that bound,
@@ -363,16 +391,25 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
   float list_density = 0.0f;  // postings of all list terms per 1024 documents (warp-uniform)
   for (int g = 0; g < ns; g += BM_SEARCH) {
     int64_t lo[BM_SEARCH], hi[BM_SEARCH], te[BM_SEARCH], ts[BM_SEARCH];
+    bool mk[BM_SEARCH];   // marker list (hi_doc) instead of a posting list (post_doc)
     float wg[BM_SEARCH];
 #pragma unroll
     for (int j = 0; j < BM_SEARCH; ++j) {
       lo[j] = hi[j] = te[j] = ts[j] = 0;
       wg[j] = 0.0f;
+      mk[j] = false;
       if (g + j < ns) {
         const int t = s_tmp[g + j];
-        lo[j] = ts[j] = a.term_off[t];
-        hi[j] = te[j] = a.term_off[t + 1];
-        if (hi[j] > lo[j]) wg[j] = a.idf[t] * a.k1p1;
+        if (t >= 0) {
+          lo[j] = ts[j] = a.term_off[t];
+          hi[j] = te[j] = a.term_off[t + 1];
+          if (hi[j] > lo[j]) wg[j] = a.idf[t] * a.k1p1;
+        } else {                                   // marker list of table row -(t + 1)
+          mk[j] = true;
+          lo[j] = ts[j] = a.hi_off[-(t + 1)];
+          hi[j] = te[j] = a.hi_off[-(t + 1) + 1];
+          if (hi[j] > lo[j]) wg[j] = INFINITY;     // never non-essential; nothing is ever multiplied by it
+        }
       }
     }
     const int target = static_cast<int>(w_begin);
@@ -389,7 +426,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
           chunk[j] = (len + 31) >> 5;
           int64_t idx = (lane + 1) * chunk[j] - 1;
           if (idx > len - 1) idx = len - 1;
-          probe[j] = __ldg(a.post_doc + lo[j] + idx);
+          probe[j] = __ldg((mk[j] ? a.hi_doc : a.post_doc) + lo[j] + idx);
         }
       }
       more = false;
@@ -412,10 +449,11 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
     for (int j = 0; j < BM_SEARCH; ++j) {
       if (wg[j] != 0.0f) {  // warp-uniform
         const int64_t idx = lo[j] + lane;
-        const bool below = idx < hi[j] && __ldg(a.post_doc + idx) < target;
+        const int32_t* const plist = mk[j] ? a.hi_doc : a.post_doc;
+        const bool below = idx < hi[j] && __ldg(plist + idx) < target;
         const int64_t cur = lo[j] + __popc(__ballot_sync(0xffffffffu, below));
         int nx = INT_MAX;
-        if (cur < te[j]) nx = __ldg(a.post_doc + cur);
+        if (cur < te[j]) nx = __ldg(plist + cur);
         // expected postings of this term per super-range
         const double per_range = static_cast<double>(te[j] - ts[j]) * BM_SUPER_DOCS / static_cast<double>(a.n_docs);
         list_density += static_cast<float>(per_range);
@@ -424,7 +462,8 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
           s_end[ntv] = te[j];
           s_wgt[ntv] = wg[j];
           s_nxt[ntv] = nx;
-          s_dense[ntv] = per_range < 24.0 ? 0 : (per_range < 56.0 ? 1 : (per_range < 120.0 ? 2 : 3));
+          // chunks per pass by density; class 4 = marker list (sparse by construction, mark-only)
+          s_dense[ntv] = mk[j] ? 4 : (per_range < 24.0 ? 0 : (per_range < 56.0 ? 1 : (per_range < 120.0 ? 2 : 3)));
         }
         ++ntv;
       }
@@ -484,7 +523,8 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
       // ================= window mode: the rest of this warp's documents (see stream_term_hash) =================
       int* const keys = reinterpret_cast<int*>(sacc);
       float* const vals = sacc + BM_HASH_SLOTS;
-      unsigned* const flags = s_bits;
+      unsigned* const flags = s_bits;                              // slot marked by an essential list
+      unsigned* const mflags = s_bits + BM_HASH_SLOTS / 32;        // slot on a marker list: scored whatever its list part
       int64_t d0l = s0l;
       bool fell_back = false;
       while (d0l < w_end) {
@@ -503,7 +543,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
 #pragma unroll
         for (int i = 0; i < BM_HASH_SLOTS / 128; ++i)
           reinterpret_cast<int4*>(keys)[i * 32 + lane] = make_int4(-1, -1, -1, -1);
-        if (lane < BM_HASH_SLOTS / 32) flags[lane] = 0u;
+        s_bits[lane] = 0u;   // flags (words 0-15) and marker flags (words 16-31)
         __syncwarp();
         int n_noness = 0;
         if (maxscore) {
@@ -523,6 +563,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
           switch (s_dense[ti]) {  // chunks per pass sized to the term's density (warp-uniform)
             case 0: ok = stream_term_hash<1>(a.post_doc, a.post_tf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
             case 1: ok = stream_term_hash<2>(a.post_doc, a.post_tf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
+            case 4: ok = stream_term_hash<1, true>(a.hi_doc, nullptr, pos, end, d0, d1, 0.0f, keys, vals, flags, true, a.norm, lane, next_doc, n_keys, mflags); break;
             default: ok = stream_term_hash<4>(a.post_doc, a.post_tf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
           }
           if (ok && lane == 0) {
@@ -554,7 +595,8 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
         for (int base = 0; base < BM_HASH_SLOTS; base += 32) {
           const int key = keys[base + lane];
           const float val = vals[base + lane];
-          const bool valid = key != -1 && ((flags[base >> 5] >> lane) & 1u) != 0u && val >= need;
+          const bool valid = key != -1 && ((flags[base >> 5] >> lane) & 1u) != 0u &&
+                             (val >= need || ((mflags[base >> 5] >> lane) & 1u) != 0u);
           const unsigned m = __ballot_sync(0xffffffffu, valid);
           if (valid) {
             const int j = n_valid + __popc(m & ((1u << lane) - 1u));
@@ -642,6 +684,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
         // a non-essential term adds to the accumulator but marks nothing
         unsigned* const mark = (n_noness > 0 && __shfl_sync(0xffffffffu, my_rank, ti & 31) < n_noness) ? nullptr : touched;
         switch (s_dense[ti]) {  // chunks per pass sized to the term's density (warp-uniform)
+          case 4: stream_term<1, true>(a.hi_doc, nullptr, pos, end, s0, s1, 0.0f, sacc, a.norm, touched, lane, next_doc); break;
           case 0: stream_term<1>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
           case 1: stream_term<2>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
           case 2: stream_term<4>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
@@ -1099,7 +1142,12 @@ static int bm25_stripes(int n_queries, int64_t n_docs, int64_t* stripe_docs_out)
   }();
   const int64_t target_blocks = 148 * per_sm;
   int64_t stripes = ceil_div64(target_blocks, n_queries);
-  const int64_t max_stripes = ceil_div64(n_docs, unit);
+  // ... but no stripe below 256k documents (32k per warp): every warp places its cursors and splits the query's terms
+  // anew, and on a small shard (1.25M documents at 8 GPUs) ten stripes made that set-up a third of the kernel
+  // (measured at 8 GPUs: 10 stripes 2.17 ms, 4 stripes 2.04 ms, 2 stripes 2.25 ms)
+  int64_t max_stripes = ceil_div64(n_docs, unit);
+  const int64_t by_size = n_docs / 262144 > 0 ? n_docs / 262144 : 1;
+  if (max_stripes > by_size && n_queries >= 64) max_stripes = by_size;
   if (stripes > max_stripes) stripes = max_stripes;
   if (stripes < 1) stripes = 1;
   int64_t stripe_docs = ceil_div64(ceil_div64(n_docs, stripes), unit) * unit;
@@ -1281,7 +1329,8 @@ int ragb_bm25_seed(const int64_t* term_off, const int32_t* post_doc, const uint1
 static int bm25_topk_args(const char* who, Bm25Args& a, int* stripes_out, const int64_t* term_off, const int32_t* post_doc,
                           const uint16_t* post_tf, const float* norm, const float* idf, int64_t vocab, double k1,
                           const uint8_t* dense_tf, int64_t dense_stride, const int32_t* dense_terms, int32_t n_dense,
-                          const uint16_t* dense_imp_fp16, const float* dense_max_imp, const int32_t* q_terms,
+                          const uint16_t* dense_imp_fp16, const float* dense_max_imp, const float* dense_cap,
+                          const int32_t* hi_off, const int32_t* hi_doc, const int32_t* q_terms,
                           const int32_t* q_off, int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base,
                           int32_t k, void* workspace, size_t workspace_bytes) {
   int rc = bm25_common_checks(who, term_off, post_doc, post_tf, norm, idf, vocab, q_terms, q_off, n_queries, n_docs,
@@ -1313,6 +1362,12 @@ static int bm25_topk_args(const char* who, Bm25Args& a, int* stripes_out, const 
                RAGB_EINVAL, "%s: dense_imp_fp16 needs the dense table and 16-byte alignment", who);
   a.dense_imp = reinterpret_cast<const __half*>(dense_imp_fp16);
   a.dense_maximp = dense_max_imp;
+  RAGB_REQUIRE((dense_cap != nullptr) == (hi_off != nullptr) && (hi_off != nullptr) == (hi_doc != nullptr), RAGB_EINVAL,
+               "%s: dense_cap, hi_off and hi_doc go together", who);
+  RAGB_REQUIRE(dense_cap == nullptr || n_dense > 0, RAGB_EINVAL, "%s: an impact cap needs the dense table", who);
+  a.dense_cap = dense_cap;
+  a.hi_off = hi_off;
+  a.hi_doc = hi_doc;
   a.k = k;
   a.capacity = warp_topk_capacity(k);
   a.part_keys = static_cast<uint64_t*>(workspace);
@@ -1357,7 +1412,8 @@ static int bm25_launch_stripes(Bm25Args a, int n_queries, int s0, int s1, size_t
 int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
                          const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
                          const int32_t* dense_terms, int32_t n_dense, const uint16_t* dense_imp_fp16,
-                         const float* dense_max_imp, const int32_t* q_terms, const int32_t* q_off,
+                         const float* dense_max_imp, const float* dense_cap, const int32_t* hi_off,
+                         const int32_t* hi_doc, const int32_t* q_terms, const int32_t* q_off,
                          int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          const float* seed_thr, float* out_score, int32_t* out_id, void* workspace,
                          size_t workspace_bytes, ragb_stream_t stream_) {
@@ -1367,7 +1423,8 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   Bm25Args a;
   int stripes = 0;
   int rc = bm25_topk_args("ragb_bm25_score_topk", a, &stripes, term_off, post_doc, post_tf, norm, idf, vocab, k1, dense_tf,
-                          dense_stride, dense_terms, n_dense, dense_imp_fp16, dense_max_imp, q_terms, q_off, n_queries,
+                          dense_stride, dense_terms, n_dense, dense_imp_fp16, dense_max_imp, dense_cap, hi_off, hi_doc, q_terms, q_off,
+                          n_queries,
                           max_query_terms, n_docs, id_base, k, workspace, workspace_bytes);
   if (rc != RAGB_OK) return rc;
   rc = bm25_init_seeds(a, seed_thr, n_queries, stream);
@@ -1386,7 +1443,8 @@ int32_t ragb_bm25_stripe_count(int32_t n_queries, int64_t n_docs) {
 int ragb_bm25_score_part(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
                          const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
                          const int32_t* dense_terms, int32_t n_dense, const uint16_t* dense_imp_fp16,
-                         const float* dense_max_imp, const int32_t* q_terms, const int32_t* q_off,
+                         const float* dense_max_imp, const float* dense_cap, const int32_t* hi_off,
+                         const int32_t* hi_doc, const int32_t* q_terms, const int32_t* q_off,
                          int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          const float* seed_thr, int32_t stripe_begin, int32_t stripe_end, int64_t min_smem_bytes,
                          void* workspace, size_t workspace_bytes, ragb_stream_t stream_) {
@@ -1395,7 +1453,8 @@ int ragb_bm25_score_part(const int64_t* term_off, const int32_t* post_doc, const
   Bm25Args a;
   int stripes = 0;
   int rc = bm25_topk_args("ragb_bm25_score_part", a, &stripes, term_off, post_doc, post_tf, norm, idf, vocab, k1, dense_tf,
-                          dense_stride, dense_terms, n_dense, dense_imp_fp16, dense_max_imp, q_terms, q_off, n_queries,
+                          dense_stride, dense_terms, n_dense, dense_imp_fp16, dense_max_imp, dense_cap, hi_off, hi_doc, q_terms, q_off,
+                          n_queries,
                           max_query_terms, n_docs, id_base, k, workspace, workspace_bytes);
   if (rc != RAGB_OK) return rc;
   RAGB_REQUIRE(0 <= stripe_begin && stripe_begin <= stripe_end && stripe_end <= stripes, RAGB_EINVAL,

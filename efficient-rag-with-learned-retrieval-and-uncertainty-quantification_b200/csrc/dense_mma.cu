@@ -357,7 +357,13 @@ __device__ __forceinline__ void epilogue_scan(const MmaArgs& a, const uint32_t t
     buf ^= 1;
     if (buf == 0) acc_phase ^= 1;
   }
-  st = compact_lists<KPL>(warp_lists, 0xffffffffu, lane, a.k, st);
+  // only lists that hold more than k candidates have to be cut down (a whole-warp sort per list: ~50 us per warp when all
+  // 32 need it); the merge kernel takes its input as a bag, so a seeded list that admitted <= k candidates is written
+  // out as it is - on a small shard that is most of them
+  {
+    const unsigned over = __ballot_sync(0xffffffffu, st.cnt > a.k);
+    if (over) st = compact_lists<KPL>(warp_lists, over, lane, a.k, st);
+  }
   const int cnt = st.cnt;
   if (query < a.n_queries) {
     uint64_t* dst = a.part_keys + (static_cast<int64_t>(query) * a.lists_per_query + group * 2 + half) * a.k;

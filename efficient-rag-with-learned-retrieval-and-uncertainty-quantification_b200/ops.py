@@ -135,6 +135,17 @@ def _dense_table(dense_tf: Tensor, dense_terms: Tensor, n_docs: int):
     return dense_tf.data_ptr(), dense_tf.shape[1], dense_terms.data_ptr(), dense_terms.shape[0]
 
 
+def _impact_cap(dense_cap: Tensor, hi_off: Tensor, hi_doc: Tensor, n_dense: int):
+    """(cap ptr, hi_off ptr, hi_doc ptr) of the optional impact cap; empty tensors disable it."""
+    if not n_dense or dense_cap.numel() == 0 or hi_off.numel() == 0:
+        return None, None, None
+    dense_cap, hi_off, hi_doc = _need(dense_cap, torch.float32, "dense_cap"), _need(hi_off, torch.int32, "hi_off"), \
+        _need(hi_doc, torch.int32, "hi_doc")
+    if dense_cap.shape[0] != n_dense or hi_off.shape[0] != n_dense + 1:
+        raise ValueError("dense_cap must hold one cap per table row and hi_off n_dense + 1 offsets")
+    return dense_cap.data_ptr(), hi_off.data_ptr(), (hi_doc.data_ptr() if hi_doc.numel() else dense_cap.data_ptr())
+
+
 def _bm25_args(term_off, post_doc, post_tf, norm, idf, q_terms, q_off):
     term_off = _need(term_off, torch.int64, "term_off")
     post_doc = _need(post_doc, torch.int32, "post_doc")
@@ -151,11 +162,14 @@ def _bm25_args(term_off, post_doc, post_tf, norm, idf, q_terms, q_off):
 @torch.library.custom_op(f"{NS}::bm25_score_topk", mutates_args=(), device_types="cuda")
 def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
                     dense_tf: Tensor, dense_terms: Tensor, dense_imp: Tensor, dense_maximp: Tensor, q_terms: Tensor,
-                    q_off: Tensor, max_query_terms: int, id_base: int, k: int, seed: Tensor) -> Tuple[Tensor, Tensor]:
+                    q_off: Tensor, max_query_terms: int, id_base: int, k: int, seed: Tensor, dense_cap: Tensor,
+                    hi_off: Tensor, hi_doc: Tensor) -> Tuple[Tensor, Tensor]:
     """dense_imp (float16 [n_dense, stride]) / dense_maximp (float32 [n_dense]): optional impact bounds of the table
     terms (ragb200.h); pass empty tensors to run without them - the results are the same.
     seed (float32 [B] or empty): proven lower bounds of every query's k-th best score (``bm25_seed``, possibly raised
-    to the maximum over all shards); empty = the kernel seeds itself."""
+    to the maximum over all shards); empty = the kernel seeds itself.
+    dense_cap (float32 [n_dense]) / hi_off (int32 [n_dense + 1]) / hi_doc (int32): optional impact cap of the table rows
+    and the marker lists of the documents above it (ragb200.h); empty tensors = none.  Pruning only."""
     term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
                                                                         q_terms, q_off)
     n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
@@ -176,9 +190,11 @@ def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: T
         if seed.numel() != n_q:
             raise ValueError("seed must hold one bound per query")
         seed_ptr = seed.data_ptr()
+    cap, hoff, hdoc = _impact_cap(dense_cap, hi_off, hi_doc, n_dense)
     with torch.cuda.device(dev):
         check(lib.ragb_bm25_score_topk(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf),
-                                       idf.shape[0], k1, dt, stride, dterms, n_dense, imp, maximp, _ptr(q_terms), _ptr(q_off), n_q,
+                                       idf.shape[0], k1, dt, stride, dterms, n_dense, imp, maximp, cap, hoff, hdoc,
+                                       _ptr(q_terms), _ptr(q_off), n_q,
                                        max_query_terms, n_docs, id_base, k, seed_ptr, _ptr(score), _ptr(ids), _ptr(ws),
                                        ws.numel(), _stream()))
     return score, ids
@@ -186,7 +202,7 @@ def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: T
 
 @bm25_score_topk.register_fake
 def _(term_off, post_doc, post_tf, norm, idf, k1, dense_tf, dense_terms, dense_imp, dense_maximp, q_terms, q_off,
-      max_query_terms, id_base, k, seed):
+      max_query_terms, id_base, k, seed, dense_cap, hi_off, hi_doc):
     n_q = q_off.shape[0] - 1
     return norm.new_empty((n_q, k)), norm.new_empty((n_q, k), dtype=torch.int32)
 
@@ -203,7 +219,8 @@ def bm25_workspace(n_queries: int, n_docs: int, k: int, device) -> Tensor:
 @torch.library.custom_op(f"{NS}::bm25_score_part", mutates_args=("workspace",), device_types="cuda")
 def bm25_score_part(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
                     dense_tf: Tensor, dense_terms: Tensor, dense_imp: Tensor, dense_maximp: Tensor, q_terms: Tensor,
-                    q_off: Tensor, max_query_terms: int, id_base: int, k: int, seed: Tensor, stripe_begin: int,
+                    q_off: Tensor, max_query_terms: int, id_base: int, k: int, seed: Tensor, dense_cap: Tensor,
+                    hi_off: Tensor, hi_doc: Tensor, stripe_begin: int,
                     stripe_end: int, min_smem_bytes: int, workspace: Tensor) -> None:
     """Score the stripes [stripe_begin, stripe_end) of the staged BM25 search into ``workspace`` (ragb200.h)."""
     term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
@@ -215,9 +232,10 @@ def bm25_score_part(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: T
         imp = _need(dense_imp, torch.float16, "dense_imp").data_ptr()
         maximp = _need(dense_maximp, torch.float32, "dense_maximp").data_ptr()
     seed_ptr = _need(seed, torch.float32, "seed").data_ptr() if seed.numel() else None
+    cap, hoff, hdoc = _impact_cap(dense_cap, hi_off, hi_doc, n_dense)
     with torch.cuda.device(dev):
         check(lib.ragb_bm25_score_part(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf), idf.shape[0], k1,
-                                       dt, stride, dterms, n_dense, imp, maximp, _ptr(q_terms), _ptr(q_off), n_q,
+                                       dt, stride, dterms, n_dense, imp, maximp, cap, hoff, hdoc, _ptr(q_terms), _ptr(q_off), n_q,
                                        max_query_terms, n_docs, id_base, k, seed_ptr, stripe_begin, stripe_end,
                                        min_smem_bytes, _ptr(workspace), workspace.numel(), _stream()))
 

@@ -91,6 +91,11 @@ int ragb_bm25_build_impact_bounds(const uint8_t* dense_tf, int64_t dense_stride,
  * fp16 UPPER bound of tf / (tf + norm[d]) (0 where the term is absent; 16-byte aligned), dense_max_imp[r] = the
  * largest value of row r.  They only prune work (a tighter bound on what the table terms can add, and a cheap
  * fp16 pass that marks the documents worth scoring exactly); results are identical with and without them.
+ * Optional impact cap of the table rows (all three or none; needs the table): dense_cap[r] and the ascending local
+ * rows hi_doc[hi_off[r] .. hi_off[r + 1]) of EVERY document whose tf / (tf + norm) for row r exceeds dense_cap[r].
+ * A document that is on no such "marker list" gets at most weight * dense_cap[r] from row r - a much tighter promise
+ * than the row maximum, which a handful of documents set - so far more queries can skip the documents no posting
+ * list touches; the listed documents are always scored exactly.  Pruning only: results are identical.
  * max_query_terms (<= RAGB_MAX_QUERY_TERMS) is the caller's bound on the longest query;
  * it sizes the per-warp cursor table and longer queries are cut to it.
  * score = sum idf[t] * tf * (k1 + 1) / (tf + norm[d]).   Only score > 0 is returned
@@ -101,6 +106,7 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
                          const uint8_t* dense_tf, int64_t dense_stride,
                          const int32_t* dense_terms, int32_t n_dense,
                          const uint16_t* dense_imp_fp16, const float* dense_max_imp,
+                         const float* dense_cap, const int32_t* hi_off, const int32_t* hi_doc,
                          const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
                          int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          const float* seed_thr, float* out_score, int32_t* out_id,
@@ -129,6 +135,7 @@ int ragb_bm25_score_part(const int64_t* term_off, const int32_t* post_doc, const
                          const uint8_t* dense_tf, int64_t dense_stride,
                          const int32_t* dense_terms, int32_t n_dense,
                          const uint16_t* dense_imp_fp16, const float* dense_max_imp,
+                         const float* dense_cap, const int32_t* hi_off, const int32_t* hi_doc,
                          const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
                          int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          const float* seed_thr, int32_t stripe_begin, int32_t stripe_end, int64_t min_smem_bytes,

@@ -261,6 +261,30 @@ def test_bm25_impact_bounds_only_prune(rq, dev, n, n_q, k):
     without_s, without_i = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
     shard.dense_imp, shard.dense_maximp = keep
     assert torch.equal(with_i, without_i) and torch.equal(with_s, without_s)
+    # the impact cap + marker lists (every document above a row's cap is listed; everybody else stays at or below it)
+    assert shard.dense_cap.shape[0] == shard.dense_terms.shape[0] and shard.hi_off.shape[0] == shard.dense_terms.shape[0] + 1
+    hi_off = shard.hi_off.tolist()
+    for r in range(0, shard.dense_terms.shape[0], 7):
+        listed = shard.hi_doc[hi_off[r]:hi_off[r + 1]].long()
+        assert bool((listed[1:] > listed[:-1]).all())                                     # ascending, distinct
+        below = torch.ones(n, dtype=torch.bool, device=dev)
+        below[listed] = False
+        assert bool((shard.dense_imp[r, :n][below].float() <= shard.dense_cap[r]).all())   # the promise the kernel relies on
+        assert bool((exact[r][below] <= shard.dense_cap[r]).all())
+    cap = shard.dense_cap, shard.hi_off, shard.hi_doc
+    shard.dense_cap = shard.hi_off = shard.hi_doc = None
+    nocap_s, nocap_i = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+    shard.dense_cap, shard.hi_off, shard.hi_doc = cap
+    assert torch.equal(with_i, nocap_i) and torch.equal(with_s, nocap_s)
+    # an aggressive cap (1 % of every row listed) and a degenerate one (a single marker document per row)
+    from rag_uq_b200 import sparse as sparse_module
+    for tail in (0.01, 1.0 / n):
+        old_tail, sparse_module.IMPACT_CAP_TAIL = sparse_module.IMPACT_CAP_TAIL, tail
+        shard._build_impact_cap()
+        sparse_module.IMPACT_CAP_TAIL = old_tail
+        s2, i2 = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+        assert torch.equal(with_i, i2) and torch.equal(with_s, s2)
+    shard.dense_cap, shard.hi_off, shard.hi_doc = cap
     full = shard.scores(qb.q_terms, qb.q_off, qb.max_terms)
     want_s, want_i = torch.topk(full, k, dim=1)
     torch.testing.assert_close(with_s, want_s, rtol=0, atol=0)
