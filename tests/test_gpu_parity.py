@@ -428,7 +428,7 @@ def test_bm25_staged_search_and_two_stream_overlap_equal_the_serial_path(rq, dev
     ragb_bm25_score_topk bit for bit; HybridEngine.local_pools(overlap=True) - BM25 blocks co-resident with the 4-stage
     tcgen05 kernel on a second, higher-priority stream - returns exactly what the serial path returns."""
     from rag_uq_b200 import synth
-    n, n_q, k = 400_000, 300, 50
+    n, n_q, k = 1_000_000, 300, 50
     engine, cdf = synth.build_synthetic_engine(n, 768, dev)
     sh = engine.sparse
     qb = synth.make_queries(n_q, n, 768, cdf, dev)
