@@ -1237,6 +1237,23 @@ static int mma_sample_tiles(int n_tiles) {
   return n_tiles / div;
 }
 
+// How the sampled prefix is searched.  On a large shard (mode 2) it is searched exactly, its merged list joins the final
+// merge and the seeded phase covers only the remaining tiles: no tile is searched twice.  But un-seeded lists pay a fixed
+// warm-up - four or five whole-warp sorts per query thread, ~0.4 ms per launch whatever the number of tiles - which on a
+// small shard (1.25M rows: 1.5 ms of seeded search) is a quarter of the kernel.  There (mode 1) the prefix only ESTABLISHES
+// the bound: every list keeps just its 8 best (tiny lists, one cheap sort), the k-th best of the 36 x 8 merged candidates is
+// still a proven lower bound of the final k-th best (k real passages reach it) and in practice the sample's true k-th best;
+// the seeded phase then covers ALL tiles (3 % more FLOPs) and the prefix list is not merged again.
+static int mma_prefix_mode(int n_tiles) {
+  if (mma_sample_tiles(n_tiles) == 0) return 0;
+  static const int exact_from = [] {
+    const char* e = getenv("RAGB_MMA_EXACT_PREFIX_TILES");  // tuning aid: shards of at least this many tiles use mode 2
+    return e ? atoi(e) : 16384;
+  }();
+  return n_tiles >= exact_from ? 2 : 1;
+}
+constexpr int MM_BOUND_ONLY_K = 8;
+
 struct MmaWorkspace {
   int* progress;
   uint64_t* lists;
@@ -1304,13 +1321,16 @@ static int mma_sample_phase(const void* passages, int64_t n_rows, int dim, const
                             float* min_out = nullptr) {
   const int n_tiles = static_cast<int>(ceil_div64(n_rows, mma_tile_rows(variant)));
   const int ts = mma_sample_tiles(n_tiles);
-  if (ts == 0)   // no prefix: merging zero lists leaves an empty sample list and the bound -inf for every query
+  const int mode = mma_prefix_mode(n_tiles);
+  if (mode == 0)   // no prefix: merging zero lists leaves an empty sample list and the bound -inf for every query
     return launch_merge_keys_ex(w.part, n_queries, 0, k, nullptr, 0, k, nullptr, nullptr, w.sample_keys, thr_out, stream);
+  const int kp = (mode == 1 && k > MM_BOUND_ONLY_K) ? MM_BOUND_ONLY_K : k;   // bound-only prefix: short lists
   const MmaPlan plan = mma_plan(mma_uses_pairs(variant, n_queries), n_queries, ts, device_sm_count());
-  const MmaRange r{0, ts, nullptr, min_out, w.part, 2 * plan.n_groups};
-  int rc = mma_dispatch(variant, passages, n_rows, dim, queries, n_queries, k, id_base, r, w, stream);
+  const MmaRange r{0, ts, nullptr, mode == 2 ? min_out : nullptr, w.part, 2 * plan.n_groups};
+  int rc = mma_dispatch(variant, passages, n_rows, dim, queries, n_queries, kp, id_base, r, w, stream);
   if (rc != RAGB_OK) return rc;
-  return launch_merge_keys_ex(w.part, n_queries, 2 * plan.n_groups, k, nullptr, 0, k, nullptr, nullptr, w.sample_keys, thr_out,
+  // the k-th best of the merged candidates (-inf while there are fewer than k) is the bound in either mode
+  return launch_merge_keys_ex(w.part, n_queries, 2 * plan.n_groups, kp, nullptr, 0, k, nullptr, nullptr, w.sample_keys, thr_out,
                               stream);
 }
 
@@ -1319,13 +1339,14 @@ static int mma_seeded_phase(const void* passages, int64_t n_rows, int dim, const
                             int64_t id_base, int variant, const float* thr, float* out_score, int32_t* out_id,
                             const MmaWorkspace& w, cudaStream_t stream, float* min_out = nullptr) {
   const int n_tiles = static_cast<int>(ceil_div64(n_rows, mma_tile_rows(variant)));
-  const int ts = mma_sample_tiles(n_tiles);
-  const MmaPlan plan = mma_plan(mma_uses_pairs(variant, n_queries), n_queries, n_tiles - ts, device_sm_count());
-  const MmaRange r{ts, n_tiles, thr, min_out, w.part, 2 * plan.n_groups};
+  const int mode = mma_prefix_mode(n_tiles);
+  const int first = mode == 2 ? mma_sample_tiles(n_tiles) : 0;    // modes 0 / 1: the seeded phase covers every tile
+  const MmaPlan plan = mma_plan(mma_uses_pairs(variant, n_queries), n_queries, n_tiles - first, device_sm_count());
+  const MmaRange r{first, n_tiles, thr, min_out, w.part, 2 * plan.n_groups};
   int rc = mma_dispatch(variant, passages, n_rows, dim, queries, n_queries, k, id_base, r, w, stream);
   if (rc != RAGB_OK) return rc;
-  return launch_merge_keys_ex(w.part, n_queries, 2 * plan.n_groups, k, w.sample_keys, k, k, out_score, out_id, nullptr, nullptr,
-                              stream);
+  return launch_merge_keys_ex(w.part, n_queries, 2 * plan.n_groups, k, mode == 2 ? w.sample_keys : nullptr, k, k, out_score,
+                              out_id, nullptr, nullptr, stream);
 }
 
 }  // namespace ragb
