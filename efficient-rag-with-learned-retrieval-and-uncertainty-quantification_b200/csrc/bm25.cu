@@ -90,7 +90,7 @@ struct Bm25Args {
   int max_terms;
   int k;
   int capacity;
-  uint64_t* part_keys;  // [queries, stripes, 8 warps, k]   (top-k mode)
+  uint64_t* part_keys;  // [queries, stripes, k]            (top-k mode)
   float* out_scores;    // [queries, out_ld]                (dense mode)
   int64_t out_ld;       // row stride of out_scores in floats (>= n_docs); tiled: query rows per tile
   int out_tiled;        // 1: out_scores[(d / 256) * out_ld + q][d % 256] (256-document tiles, query rows inside a tile)
@@ -502,13 +502,13 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
     window = max(BM_SUPER_DOCS, want / BM_SUPER_DOCS * BM_SUPER_DOCS);
   }
 
-  // The admission threshold is shared between all warps of a query (8 x stripes of them) through seed_thr[q] in L2:
-  // a warp publishes its own k-th best score whenever it has risen (atomicMax: a proven lower bound of the query's
-  // final k-th best) and picks the current maximum up once per visit.  Warps of later stripes therefore start where
-  // the best earlier warp stands instead of warming their own top-k up from the seed.  The value is
+  // The admission threshold is shared between all blocks of a query through seed_thr[q] in L2: every block that
+  // finishes publishes the k-th best score of its stripe (atomicMax below) - a proven lower bound of the query's
+  // final k-th best - and every warp picks the current value up once per visit.  Blocks of later stripes therefore
+  // start where the best earlier stripe ended instead of warming their own top-k up from the seed.  The value is
   // requested one visit ahead so its L2 latency hides behind the work of the visit.  It only prunes: results do
   // not depend on which blocks ran first.
-  float pending_thr = seed_dbg;   // the shared value as last read (the seed to begin with)
+  float pending_thr = 0.0f;
   const int j0 = lane * 8;  // the 8 documents of a range this lane owns
   for (int sup = 0; sup < n_super; ++sup) {
     const int64_t s0l = w_begin + static_cast<int64_t>(sup) * BM_SUPER_DOCS;
@@ -516,9 +516,6 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
     const int s1 = static_cast<int>(min(w_end, s0l + BM_SUPER_DOCS));
     if (s1 <= s0) break;  // warp-uniform; nothing below synchronises the block
     if (!DENSE_OUT) {
-      // this warp has proven more than the shared value it last saw: let the other 8 x stripes warps of the query know
-      if (lane == 0 && tk.thr_score > pending_thr && tk.thr_score > 0.0f)
-        atomicMax(reinterpret_cast<int*>(a.seed_thr + q), __float_as_int(tk.thr_score));
       tk.raise(pending_thr);
       pending_thr = __ldcg(a.seed_thr + q);
     }
@@ -533,8 +530,6 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
       while (d0l < w_end) {
         const int d0 = static_cast<int>(d0l);
         const int d1 = static_cast<int>(min(w_end, d0l + window));
-        if (lane == 0 && tk.thr_score > pending_thr && tk.thr_score > 0.0f)
-          atomicMax(reinterpret_cast<int*>(a.seed_thr + q), __float_as_int(tk.thr_score));
         tk.raise(pending_thr);
         pending_thr = __ldcg(a.seed_thr + q);
         unsigned act = __ballot_sync(0xffffffffu, lane < ntv && s_nxt[lane] < d1);
@@ -871,14 +866,34 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
     __syncwarp();  // the next super-range clears sacc
   }
   if (!DENSE_OUT) {
-    // Every warp hands its own list to the cross-stripe merge (8 lists per block): folding them here cost a block-wide
-    // bitonic sort behind a barrier at which seven warps waited for the slowest one - 10 % of the kernel on a small shard.
+    // fold the 8 warp lists of this block into one (8k <= 2048 keys, one bitonic sort), so the
+    // cross-stripe merge sees one list per block
     tk.flush(lane);
-    uint64_t* dst = a.part_keys + ((static_cast<int64_t>(q) * a.n_stripes + stripe) * BM_WARPS + warp) * a.k;
-    for (int i = lane; i < a.k; i += 32) dst[i] = s_keys[i];   // sorted best-first, zero = empty
-    // publish what this warp has proven (positive floats order like their bit patterns)
-    if (lane == 0 && tk.thr_score > pending_thr && tk.thr_score > 0.0f)
-      atomicMax(reinterpret_cast<int*>(a.seed_thr + q), __float_as_int(tk.thr_score));
+    __syncthreads();
+    uint64_t* all_keys = s_keys - warp * a.capacity;  // [BM_WARPS][capacity], each sorted in its first k slots
+    int n = 2;
+    while (n < BM_WARPS * a.k) n <<= 1;               // <= BM_WARPS * capacity because k <= capacity / 2
+    uint64_t mine[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = r * BM_THREADS + tid;
+      mine[r] = e < BM_WARPS * a.k ? all_keys[(e / a.k) * a.capacity + (e % a.k)] : 0ull;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = r * BM_THREADS + tid;
+      if (e < n) all_keys[e] = mine[r];
+    }
+    __syncthreads();
+    bitonic_sort_desc<BM_THREADS>(all_keys, n);
+    uint64_t* dst = a.part_keys + (static_cast<int64_t>(q) * a.n_stripes + stripe) * a.k;
+    for (int i = tid; i < a.k; i += BM_THREADS) dst[i] = all_keys[i];
+    // publish this stripe's k-th best score (positive floats order like their bit patterns)
+    if (tid == 0 && all_keys[a.k - 1] != 0ull) {
+      const float kth = key_score(all_keys[a.k - 1]);
+      if (kth > 0.0f) atomicMax(reinterpret_cast<int*>(a.seed_thr + q), __float_as_int(kth));
+    }
   }
 }
 
@@ -1272,7 +1287,7 @@ size_t ragb_bm25_topk_workspace_bytes(int32_t n_queries, int64_t n_docs, int32_t
   if (n_queries <= 0 || n_docs <= 0 || k <= 0) return 0;
   int64_t stripe_docs;
   const int stripes = bm25_stripes(n_queries, n_docs, &stripe_docs);
-  return static_cast<size_t>(n_queries) * stripes * BM_WARPS * k * sizeof(uint64_t) + static_cast<size_t>(n_queries) * sizeof(float);
+  return static_cast<size_t>(n_queries) * stripes * k * sizeof(uint64_t) + static_cast<size_t>(n_queries) * sizeof(float);
 }
 
 int ragb_bm25_seed(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
@@ -1359,7 +1374,7 @@ static int bm25_topk_args(const char* who, Bm25Args& a, int* stripes_out, const 
   a.out_scores = nullptr;
   const int stripes = bm25_stripes(n_queries, n_docs, &a.stripe_docs);
   a.n_stripes = stripes;
-  a.seed_thr = reinterpret_cast<float*>(a.part_keys + static_cast<size_t>(n_queries) * stripes * BM_WARPS * k);
+  a.seed_thr = reinterpret_cast<float*>(a.part_keys + static_cast<size_t>(n_queries) * stripes * k);
   static const int debug_flag = [] { const char* e = getenv("RAGB_BM25_DEBUG"); return e ? atoi(e) : 0; }();
   a.debug = debug_flag;
   // postings aimed at per window (0 turns window mode off); tuning aid, the default is what was measured best
@@ -1420,7 +1435,7 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   if (rc != RAGB_OK) return rc;
   rc = bm25_launch_stripes(a, n_queries, 0, stripes, 0, stream);
   if (rc != RAGB_OK) return rc;
-  return launch_merge_keys(a.part_keys, n_queries, stripes * BM_WARPS, k, k, out_score, out_id, stream);
+  return launch_merge_keys(a.part_keys, n_queries, stripes, k, k, out_score, out_id, stream);
 }
 
 int32_t ragb_bm25_stripe_count(int32_t n_queries, int64_t n_docs) {
@@ -1466,7 +1481,7 @@ int ragb_bm25_score_finish(int32_t n_queries, int64_t n_docs, int32_t k, float* 
                "ragb_bm25_score_finish: workspace too small");
   int64_t stripe_docs;
   const int stripes = bm25_stripes(n_queries, n_docs, &stripe_docs);
-  return launch_merge_keys(static_cast<const uint64_t*>(workspace), n_queries, stripes * BM_WARPS, k, k, out_score, out_id, stream);
+  return launch_merge_keys(static_cast<const uint64_t*>(workspace), n_queries, stripes, k, k, out_score, out_id, stream);
 }
 
 int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uint16_t* post_tf, const float* norm,
