@@ -13,8 +13,9 @@
 #   torchrun:<N>[:<args>]      the driver's multi-GPU launch of bench.py on N GPUs
 #   launches[:<extra args>]    ncu launch list (gpu__time_duration.sum) of bench.py --steps 2 --warmup 1 <args>,
 #                              restricted to the NVTX range bench_timed
-#   ncu:<kernel regex>[:<args>] one `ncu --set full` capture of the first matching launch inside bench_timed, exported as
-#                              <tag>_ncu_<regex>.ncu-rep plus a raw CSV page
+#   ncu:<kernel regex>[:<args>] one `ncu --set full` capture of the first matching launch(es) inside bench_timed (env
+#                              NCU_COUNT launches, default 1: the dense kernel runs twice per step, sampled prefix then the
+#                              seeded search), exported as <tag>_ncu_<regex>.ncu-rep plus a raw CSV page
 #   py:<script and args>       python <script and args>           (scripts/*.py micro-benchmarks)
 set -u
 cd "$(dirname "$0")/.."
@@ -55,7 +56,7 @@ for step in "$@"; do
     ncu)
       kern=${rest%%:*}; args=""; [[ "$rest" == *:* ]] && args=${rest#*:}
       # shellcheck disable=SC2086
-      ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "bench_timed/" -k "regex:${kern}" -c 1 \
+      ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "bench_timed/" -k "regex:${kern}" -c "${NCU_COUNT:-1}" \
         -o "gpurun_out/${tag}_ncu_${kern}" -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --verify 0 $args \
         > "gpurun_out/${tag}_ncu_${kern}.log" 2>&1
       rc=$?
