@@ -504,8 +504,9 @@ def run_ours(args):
                                      f"gate + fusion, proven stopping bound; exhaustive epilogue for queries where it does not hold"))
                                    + f"; {args.passages} passages x {DIM} "
                                    f"bf16 row-sharded over {world} GPU(s), batch {args.batch} queries x 8 terms",
-                       "l2": "inputs exceed L2 (embedding shard %.1f GB, postings %.1f GB per GPU); 4 rotating query batches"
-                             % (n_local * DIM * 2 / 1e9, engine.sparse.nnz * 6 / 1e9),
+                       "l2": "inputs exceed L2 (embedding shard %.1f GB, postings incl. baked impacts %.1f GB per GPU); 4 rotating query batches"
+                             % (n_local * DIM * 2 / 1e9,
+                                engine.sparse.nnz * (6 + (4 if getattr(engine.sparse, "post_imp", None) is not None else 0)) / 1e9),
                        "streams": ("ONE CUDA graph per step (%d library kernels): BM25 chain and GEMV as parallel branches; the "
                                    "per-kernel times are from eager steps outside the timed region" % graphed.kernels_per_replay
                                    if graphed is not None else

@@ -6,10 +6,12 @@ time, and every entry point refuses devices that are not sm_100.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libragb200.so"
+# RAGB_LIB_NAME: diagnostics only (an instrumented build of the same sources, e.g. libragb200_prof.so)
+LIB_PATH = PKG_DIR / os.environ.get("RAGB_LIB_NAME", "libragb200.so")
 
 RAGB_OK, RAGB_EINVAL, RAGB_EARCH, RAGB_ECUDA, RAGB_ELIMIT, RAGB_ENOSPC = 0, -1, -2, -3, -4, -5
 MAX_TOPK = 256
@@ -53,11 +55,12 @@ SIGNATURES = {
     "ragb_bm25_term_max_tf": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
     "ragb_bm25_build_dense_table": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _p, _i64, _p]),
     "ragb_bm25_build_impact_bounds": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p]),
+    "ragb_bm25_build_posting_impacts": (C.c_int, [_p, _p, _p, _i64, _p, _p]),
     "ragb_bm25_topk_workspace_bytes": (_sz, [_i32, _i64, _i32]),
-    "ragb_bm25_score_topk": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _i32,
+    "ragb_bm25_score_topk": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32,
                                        _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "ragb_bm25_stripe_count": (_i32, [_i32, _i64]),
-    "ragb_bm25_score_part": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _i32,
+    "ragb_bm25_score_part": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32,
                                        _i64, _i64, _i32, _p, _i32, _i32, _i64, _p, _sz, _p]),
     "ragb_bm25_score_finish": (C.c_int, [_i32, _i64, _i32, _p, _p, _p, _sz, _p]),
     "ragb_bm25_seed": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _p, _i64, _p, _i32, _p, _p, _i32, _i32, _i64, _i32, _p, _p]),

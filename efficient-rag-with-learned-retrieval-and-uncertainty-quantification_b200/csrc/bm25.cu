@@ -73,6 +73,18 @@ constexpr int BM_APPROX_MAX = 320;  // fp16 bound pass: fall back to the exact t
 // [3] documents scored in pruned mode, [4] queries seeded, [5] queries with seed > table bound,
 // [6] super-ranges decided by the fp16 bound pass, [7] bound passes that fell back to the exact table path
 __device__ unsigned long long g_bm25_dbg[8];
+#ifdef RAGB_BM25_PROFILE
+// Profiling build only (scripts/profile_bm25_queries.py): warp cycles per query and phase, [phase][query]:
+// 0 set-up (term split, cursor placement), 1 window mode, 2 dense-accumulator / bound-pass super-ranges, 3 block fold,
+// inside window mode: 4 posting streaming + hash inserts, 5 compaction, 6 scoring of the marked documents, 7 windows visited.
+constexpr int BM_PROF_QUERIES = 4096;
+__device__ unsigned long long g_bm25_prof[8][BM_PROF_QUERIES];
+#define BM_PROF_T(var) const long long var = clock64()
+#define BM_PROF_ADD(phase, q, cycles) do { if (lane == 0 && (q) < BM_PROF_QUERIES) atomicAdd(&g_bm25_prof[phase][q], static_cast<unsigned long long>(cycles)); } while (0)
+#else
+#define BM_PROF_T(var)
+#define BM_PROF_ADD(phase, q, cycles)
+#endif
 
 struct Bm25Args {
   const int64_t* term_off;
@@ -105,6 +117,10 @@ struct Bm25Args {
   const float* dense_cap;
   const int32_t* hi_off;
   const int32_t* hi_doc;
+  // optional [nnz]: post_imp[i] = tf / (tf + norm[doc]) of posting i, evaluated with the kernel's own expression (see
+  // posting_impacts_kernel), so reading it gives the bits the tf + norm path computes.  With it the window phase
+  // reads (document, impact) pairs and drops the dependent gather of norm[doc] and the reciprocal from its chain.
+  const float* post_imp;
   int window_mode;           // > 0: hash-window mode for the pruned phase, aiming at this many postings per window
   float* seed_thr;           // [queries] proven lower bound of each query's k-th best score (0 = none)
   int stripe0;               // this launch covers stripes [stripe0, stripe0 + gridDim.y) of n_stripes
@@ -193,7 +209,7 @@ constexpr int BM_HASH_MAX = 352;       // inserts stop being attempted beyond th
 constexpr int BM_WINDOW_MAX = 32768;   // documents per window (offsets must also stay well inside int32)
 
 // Returns false when the table would overflow (nothing usable was changed: the caller restores the cursors).
-template <int U, bool MARK_ONLY = false>
+template <int U, bool MARK_ONLY = false, bool IMP = false>   // IMP: post_tf is really post_imp (float): baked impacts
 __device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ post_doc,
                                                  const uint16_t* __restrict__ post_tf, int64_t& pos, const int64_t end,
                                                  const int d0, const int d1, const float weight, int* keys, float* vals,
@@ -210,7 +226,8 @@ __device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ pos
       const int64_t idx = pos + u * 32 + lane;
       const bool in = idx < end;
       doc[u] = in ? __ldg(post_doc + idx) : INT_MAX;
-      tf[u] = (in && !MARK_ONLY) ? static_cast<unsigned>(__ldg(post_tf + idx)) : 0u;
+      if (IMP) tf[u] = (in && !MARK_ONLY) ? __ldg(reinterpret_cast<const unsigned*>(post_tf) + idx) : 0u;
+      else tf[u] = (in && !MARK_ONLY) ? static_cast<unsigned>(__ldg(post_tf + idx)) : 0u;
     }
     const int64_t peek_idx = pos + U * 32;
     int peek = INT_MAX;
@@ -223,8 +240,12 @@ __device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ pos
       if (take) {
         float x = 0.0f;
         if (!MARK_ONLY) {
-          const float f = static_cast<float>(tf[u]);
-          x = f * fast_rcp(f + __ldg(norm + doc[u]));
+          if (IMP) {
+            x = __uint_as_float(tf[u]);   // the bits the expression below produced when the impacts were baked
+          } else {
+            const float f = static_cast<float>(tf[u]);
+            x = f * fast_rcp(f + __ldg(norm + doc[u]));
+          }
         }
         const int key = doc[u] - d0;
         unsigned slot = (static_cast<unsigned>(key) * 0x9E3779B1u) >> 23;   // 9 bits
@@ -265,11 +286,27 @@ __device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ pos
   }
 }
 
-template <bool DENSE_OUT>
+
+// post_imp[i] = tf / (tf + norm[doc]) with the expression of stream_term / stream_term_hash (one MUFU.RCP, one
+// multiply): the window phase adds weight * post_imp[i] and gets the very bits the tf + norm path computes, without
+// the gather of norm[doc] behind every load of postings (a dependent round trip) and the convert / add / reciprocal.
+__global__ void __launch_bounds__(256) posting_impacts_kernel(const int32_t* __restrict__ post_doc,
+                                                              const uint16_t* __restrict__ post_tf,
+                                                              const float* __restrict__ norm, int64_t nnz,
+                                                              float* __restrict__ post_imp) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float f = static_cast<float>(__ldg(post_tf + i));
+    post_imp[i] = f * fast_rcp(f + __ldg(norm + __ldg(post_doc + i)));
+  }
+}
+
+template <bool DENSE_OUT, bool IMP = false>   // IMP: the window phase reads baked impacts (Bm25Args::post_imp)
 __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm25_kernel(const Bm25Args a) {   // get_scores streams: occupancy first
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = a.max_terms;
+  BM_PROF_T(prof_t0);
   // carve shared memory
   unsigned char* sp = smem_raw;
   int64_t* s_pos = reinterpret_cast<int64_t*>(sp) + warp * mt;
@@ -296,8 +333,9 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
   int* s_tmp = reinterpret_cast<int*>(sp) + warp * mt;        // term ids while the cursors are placed
   sp += sizeof(int) * BM_WARPS * mt;
   unsigned char* s_dense = sp + warp * mt;                    // chunks per pass class of each sparse term
-
-  __shared__ int s_dterms[BM_MAX_DENSE];
+  sp += (static_cast<size_t>(BM_WARPS) * mt + 15) & ~static_cast<size_t>(15);
+  int* const s_dterms = reinterpret_cast<int*>(sp);           // table directory (block-wide, a.n_dense entries)
+  sp += (sizeof(int) * a.n_dense + 15) & ~static_cast<size_t>(15);
 
   const int q = blockIdx.x;
   const int stripe = a.stripe0 + static_cast<int>(blockIdx.y);
@@ -510,6 +548,11 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
   // not depend on which blocks ran first.
   float pending_thr = 0.0f;
   const int j0 = lane * 8;  // the 8 documents of a range this lane owns
+  BM_PROF_T(prof_t1);
+  BM_PROF_ADD(0, blockIdx.x, prof_t1 - prof_t0);
+#ifdef RAGB_BM25_PROFILE
+  long long prof_win = 0, prof_stream = 0, prof_compact = 0, prof_score = 0, prof_visits = 0;
+#endif
   for (int sup = 0; sup < n_super; ++sup) {
     const int64_t s0l = w_begin + static_cast<int64_t>(sup) * BM_SUPER_DOCS;
     const int s0 = static_cast<int>(s0l < w_end ? s0l : w_end);
@@ -527,6 +570,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
       unsigned* const mflags = s_bits + BM_HASH_SLOTS / 32;        // slot on a marker list: scored whatever its list part
       int64_t d0l = s0l;
       bool fell_back = false;
+      BM_PROF_T(prof_w0);
       while (d0l < w_end) {
         const int d0 = static_cast<int>(d0l);
         const int d1 = static_cast<int>(min(w_end, d0l + window));
@@ -552,6 +596,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
         }
         int n_keys = 0;
         bool ok = true;
+        BM_PROF_T(prof_s0);
         while (act != 0u && ok) {
           const int ti = __ffs(act) - 1;
           act &= act - 1u;
@@ -560,11 +605,12 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
           const float w = s_wgt[ti];
           const bool essential = !(n_noness > 0 && __shfl_sync(0xffffffffu, my_rank, ti) < n_noness);
           int next_doc = INT_MAX;
+          const uint16_t* const ptf = IMP ? reinterpret_cast<const uint16_t*>(a.post_imp) : a.post_tf;
           switch (s_dense[ti]) {  // chunks per pass sized to the term's density (warp-uniform)
-            case 0: ok = stream_term_hash<1>(a.post_doc, a.post_tf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
-            case 1: ok = stream_term_hash<2>(a.post_doc, a.post_tf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
+            case 0: ok = stream_term_hash<1, false, IMP>(a.post_doc, ptf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
+            case 1: ok = stream_term_hash<2, false, IMP>(a.post_doc, ptf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
             case 4: ok = stream_term_hash<1, true>(a.hi_doc, nullptr, pos, end, d0, d1, 0.0f, keys, vals, flags, true, a.norm, lane, next_doc, n_keys, mflags); break;
-            default: ok = stream_term_hash<4>(a.post_doc, a.post_tf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
+            default: ok = stream_term_hash<4, false, IMP>(a.post_doc, ptf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
           }
           if (ok && lane == 0) {
             s_pos[ti] = pos;
@@ -591,6 +637,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
         // document whose list part plus everything the table terms could add stays below thr is dropped here,
         // before any of its table bytes is gathered (most marked documents match a single light list term).
         const float need = (tk.thr_score - 2e-5f * fabsf(tk.thr_score)) - ub_table;
+        BM_PROF_T(prof_s1);
         int n_valid = 0;
         for (int base = 0; base < BM_HASH_SLOTS; base += 32) {
           const int key = keys[base + lane];
@@ -611,6 +658,7 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
           atomicAdd(&g_bm25_dbg[3], static_cast<unsigned long long>(n_valid));
         }
         // ... and score them: table terms first, in query order, then the list part - as in the dense mode
+        BM_PROF_T(prof_s2);
         for (int i0 = 0; i0 < n_valid; i0 += 32) {
           const bool valid = i0 + lane < n_valid;
           float total = 0.0f;
@@ -638,7 +686,16 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
         }
         __syncwarp();
         d0l += window;
+#ifdef RAGB_BM25_PROFILE
+        prof_stream += prof_s1 - prof_s0;
+        prof_compact += prof_s2 - prof_s1;
+        prof_score += clock64() - prof_s2;
+        prof_visits += 1;
+#endif
       }
+#ifdef RAGB_BM25_PROFILE
+      prof_win += clock64() - prof_w0;
+#endif
       if (!fell_back) break;   // this warp is done
       window_ok = false;
       sup = static_cast<int>((d0l - w_begin) / BM_SUPER_DOCS) - 1;   // resume the dense-accumulator loop at d0l
@@ -865,6 +922,15 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
     }
     __syncwarp();  // the next super-range clears sacc
   }
+  BM_PROF_T(prof_t2);
+#ifdef RAGB_BM25_PROFILE
+  BM_PROF_ADD(1, blockIdx.x, prof_win);
+  BM_PROF_ADD(4, blockIdx.x, prof_stream);
+  BM_PROF_ADD(5, blockIdx.x, prof_compact);
+  BM_PROF_ADD(6, blockIdx.x, prof_score);
+  BM_PROF_ADD(7, blockIdx.x, prof_visits);
+  BM_PROF_ADD(2, blockIdx.x, prof_t2 - prof_t1 - prof_win);
+#endif
   if (!DENSE_OUT) {
     // fold the 8 warp lists of this block into one (8k <= 2048 keys, one bitonic sort), so the
     // cross-stripe merge sees one list per block
@@ -895,6 +961,9 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
       if (kth > 0.0f) atomicMax(reinterpret_cast<int*>(a.seed_thr + q), __float_as_int(kth));
     }
   }
+#ifdef RAGB_BM25_PROFILE
+  BM_PROF_ADD(3, blockIdx.x, clock64() - prof_t2);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1156,15 +1225,18 @@ static int bm25_stripes(int n_queries, int64_t n_docs, int64_t* stripe_docs_out)
   return static_cast<int>(stripes);
 }
 
-static size_t bm25_smem_bytes(int max_terms, int capacity, bool dense_out) {
+static size_t bm25_smem_bytes(int max_terms, int capacity, bool dense_out, int n_dense) {
+  const size_t r16 = ~static_cast<size_t>(15);
   size_t b = 0;
   b += 2 * sizeof(int64_t) * BM_WARPS * max_terms;
   if (!dense_out) b += sizeof(uint64_t) * capacity * BM_WARPS;
   b += 2 * sizeof(void*) * BM_WARPS * max_terms;
   b += sizeof(float) * BM_WARPS * BM_SUPER_DOCS;
   b += sizeof(unsigned) * BM_WARPS * (BM_SUPER_DOCS / 32);
-  b += (2 * sizeof(float) + 2 * sizeof(int) + 1) * BM_WARPS * max_terms;
-  return (b + 15) & ~static_cast<size_t>(15);
+  b += (2 * sizeof(float) + 2 * sizeof(int)) * BM_WARPS * max_terms;
+  b += (static_cast<size_t>(BM_WARPS) * max_terms + 15) & r16;   // s_dense
+  b += (sizeof(int) * n_dense + 15) & r16;                       // table directory
+  return (b + 15) & r16;
 }
 
 static int bm25_common_checks(const char* who, const int64_t* term_off, const int32_t* post_doc,
@@ -1202,6 +1274,17 @@ int ragb_debug_bm25_counters(unsigned long long* out8) {
   if (cudaMemcpyToSymbol(g_bm25_dbg, zero, sizeof(zero)) != cudaSuccess) return RAGB_ECUDA;
   return RAGB_OK;
 }
+
+#ifdef RAGB_BM25_PROFILE
+// Profiling build only: copy and clear the per-query phase cycles, out[8][4096].
+int ragb_debug_bm25_profile(unsigned long long* out) {
+  if (cudaMemcpyFromSymbol(out, g_bm25_prof, sizeof(unsigned long long) * 8 * BM_PROF_QUERIES) != cudaSuccess) return RAGB_ECUDA;
+  void* p = nullptr;
+  if (cudaGetSymbolAddress(&p, g_bm25_prof) != cudaSuccess) return RAGB_ECUDA;
+  if (cudaMemset(p, 0, sizeof(unsigned long long) * 8 * BM_PROF_QUERIES) != cudaSuccess) return RAGB_ECUDA;
+  return RAGB_OK;
+}
+#endif
 
 size_t ragb_bm25_idf_scratch_bytes(int64_t) { return 2 * IDF_BLOCKS * sizeof(double); }
 
@@ -1283,6 +1366,19 @@ int ragb_bm25_build_impact_bounds(const uint8_t* dense_tf, int64_t dense_stride,
   return RAGB_OK;
 }
 
+int ragb_bm25_build_posting_impacts(const int32_t* post_doc, const uint16_t* post_tf, const float* norm, int64_t nnz,
+                                    float* post_imp_out, ragb_stream_t stream_) {
+  RAGB_ENTRY();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RAGB_REQUIRE(post_doc && post_tf && norm && post_imp_out, RAGB_EINVAL, "ragb_bm25_build_posting_impacts: null pointer");
+  RAGB_REQUIRE(nnz > 0, RAGB_EINVAL, "ragb_bm25_build_posting_impacts: empty index");
+  int64_t blocks = ceil_div64(nnz, 256 * 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  posting_impacts_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(post_doc, post_tf, norm, nnz, post_imp_out);
+  RAGB_AFTER_LAUNCH(1);
+  return RAGB_OK;
+}
+
 size_t ragb_bm25_topk_workspace_bytes(int32_t n_queries, int64_t n_docs, int32_t k) {
   if (n_queries <= 0 || n_docs <= 0 || k <= 0) return 0;
   int64_t stripe_docs;
@@ -1330,7 +1426,7 @@ static int bm25_topk_args(const char* who, Bm25Args& a, int* stripes_out, const 
                           const uint16_t* post_tf, const float* norm, const float* idf, int64_t vocab, double k1,
                           const uint8_t* dense_tf, int64_t dense_stride, const int32_t* dense_terms, int32_t n_dense,
                           const uint16_t* dense_imp_fp16, const float* dense_max_imp, const float* dense_cap,
-                          const int32_t* hi_off, const int32_t* hi_doc, const int32_t* q_terms,
+                          const int32_t* hi_off, const int32_t* hi_doc, const float* post_imp, const int32_t* q_terms,
                           const int32_t* q_off, int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base,
                           int32_t k, void* workspace, size_t workspace_bytes) {
   int rc = bm25_common_checks(who, term_off, post_doc, post_tf, norm, idf, vocab, q_terms, q_off, n_queries, n_docs,
@@ -1368,6 +1464,7 @@ static int bm25_topk_args(const char* who, Bm25Args& a, int* stripes_out, const 
   a.dense_cap = dense_cap;
   a.hi_off = hi_off;
   a.hi_doc = hi_doc;
+  a.post_imp = post_imp;
   a.k = k;
   a.capacity = warp_topk_capacity(k);
   a.part_keys = static_cast<uint64_t*>(workspace);
@@ -1398,17 +1495,20 @@ static int bm25_init_seeds(const Bm25Args& a, const float* seed_thr, int n_queri
 // the scoring kernel over stripes [s0, s1); shared memory per block padded to at least min_smem bytes (0 = natural)
 static int bm25_launch_stripes(Bm25Args a, int n_queries, int s0, int s1, size_t min_smem, cudaStream_t stream) {
   if (s1 <= s0) return RAGB_OK;
-  size_t smem = bm25_smem_bytes(a.max_terms, a.capacity, false);
+  static const int imp_flag = [] { const char* e = getenv("RAGB_BM25_IMPACTS"); return e ? atoi(e) : 1; }();   // 0: ignore post_imp
+  const bool with_imp = a.post_imp != nullptr && a.window_mode != 0 && imp_flag != 0;
+  size_t smem = bm25_smem_bytes(a.max_terms, a.capacity, false, a.n_dense);
   if (min_smem > smem) smem = min_smem;
   RAGB_REQUIRE(smem <= 200 * 1024, RAGB_ELIMIT, "ragb_bm25_score_part: shared-memory padding %zu too large", smem);
   a.stripe0 = s0;
-  RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  auto kernel = with_imp ? bm25_kernel<false, true> : bm25_kernel<false, false>;
+  RAGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   // the maximal carve-out only when a caller pads the blocks to share SMs with another kernel: it leaves 28 KB of L1,
   // and the kernel's gathers (norm, table bytes) want the L1 the default split gives them (measured: +8 % with it)
-  RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  RAGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  min_smem > 0 ? static_cast<int>(cudaSharedmemCarveoutMaxShared)
                                               : static_cast<int>(cudaSharedmemCarveoutDefault)));
-  bm25_kernel<false><<<dim3(n_queries, s1 - s0), BM_THREADS, smem, stream>>>(a);
+  kernel<<<dim3(n_queries, s1 - s0), BM_THREADS, smem, stream>>>(a);
   RAGB_AFTER_LAUNCH(1);
   return RAGB_OK;
 }
@@ -1417,7 +1517,7 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
                          const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
                          const int32_t* dense_terms, int32_t n_dense, const uint16_t* dense_imp_fp16,
                          const float* dense_max_imp, const float* dense_cap, const int32_t* hi_off,
-                         const int32_t* hi_doc, const int32_t* q_terms, const int32_t* q_off,
+                         const int32_t* hi_doc, const float* post_imp, const int32_t* q_terms, const int32_t* q_off,
                          int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          const float* seed_thr, float* out_score, int32_t* out_id, void* workspace,
                          size_t workspace_bytes, ragb_stream_t stream_) {
@@ -1427,7 +1527,7 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
   Bm25Args a;
   int stripes = 0;
   int rc = bm25_topk_args("ragb_bm25_score_topk", a, &stripes, term_off, post_doc, post_tf, norm, idf, vocab, k1, dense_tf,
-                          dense_stride, dense_terms, n_dense, dense_imp_fp16, dense_max_imp, dense_cap, hi_off, hi_doc, q_terms, q_off,
+                          dense_stride, dense_terms, n_dense, dense_imp_fp16, dense_max_imp, dense_cap, hi_off, hi_doc, post_imp, q_terms, q_off,
                           n_queries,
                           max_query_terms, n_docs, id_base, k, workspace, workspace_bytes);
   if (rc != RAGB_OK) return rc;
@@ -1448,7 +1548,7 @@ int ragb_bm25_score_part(const int64_t* term_off, const int32_t* post_doc, const
                          const float* idf, int64_t vocab, double k1, const uint8_t* dense_tf, int64_t dense_stride,
                          const int32_t* dense_terms, int32_t n_dense, const uint16_t* dense_imp_fp16,
                          const float* dense_max_imp, const float* dense_cap, const int32_t* hi_off,
-                         const int32_t* hi_doc, const int32_t* q_terms, const int32_t* q_off,
+                         const int32_t* hi_doc, const float* post_imp, const int32_t* q_terms, const int32_t* q_off,
                          int32_t n_queries, int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          const float* seed_thr, int32_t stripe_begin, int32_t stripe_end, int64_t min_smem_bytes,
                          void* workspace, size_t workspace_bytes, ragb_stream_t stream_) {
@@ -1457,7 +1557,7 @@ int ragb_bm25_score_part(const int64_t* term_off, const int32_t* post_doc, const
   Bm25Args a;
   int stripes = 0;
   int rc = bm25_topk_args("ragb_bm25_score_part", a, &stripes, term_off, post_doc, post_tf, norm, idf, vocab, k1, dense_tf,
-                          dense_stride, dense_terms, n_dense, dense_imp_fp16, dense_max_imp, dense_cap, hi_off, hi_doc, q_terms, q_off,
+                          dense_stride, dense_terms, n_dense, dense_imp_fp16, dense_max_imp, dense_cap, hi_off, hi_doc, post_imp, q_terms, q_off,
                           n_queries,
                           max_query_terms, n_docs, id_base, k, workspace, workspace_bytes);
   if (rc != RAGB_OK) return rc;
@@ -1521,7 +1621,7 @@ int ragb_bm25_scores(const int64_t* term_off, const int32_t* post_doc, const uin
   a.out_scores = out_scores;
   a.out_ld = out_ld;
   a.out_tiled = tiled;
-  const size_t smem = bm25_smem_bytes(a.max_terms, 0, true);
+  const size_t smem = bm25_smem_bytes(a.max_terms, 0, true, a.n_dense);
   RAGB_CUDA(cudaFuncSetAttribute(bm25_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   bm25_kernel<true><<<dim3(n_queries, stripes), BM_THREADS, smem, stream>>>(a);
   RAGB_AFTER_LAUNCH(1);

@@ -202,7 +202,8 @@ struct WarpTopK {
   }
 };
 
-__host__ __device__ constexpr int warp_topk_capacity(int k) { return k <= 100 ? 256 : 512; }
+// (a list needs room for k kept keys plus at least one round of 32 appended ones)
+__host__ __device__ constexpr int warp_topk_capacity(int k) { return k <= 64 ? 128 : (k <= 100 ? 256 : 512); }
 
 // Capacity used for a given k (entries of 8 bytes).
 __host__ __device__ constexpr int topk_capacity(int k) { return k <= 64 ? 1024 : 2048; }

@@ -146,6 +146,28 @@ def _impact_cap(dense_cap: Tensor, hi_off: Tensor, hi_doc: Tensor, n_dense: int)
     return dense_cap.data_ptr(), hi_off.data_ptr(), (hi_doc.data_ptr() if hi_doc.numel() else dense_cap.data_ptr())
 
 
+def _posting_impacts(post_imp: Tensor, post_doc: Tensor):
+    if post_imp is None or post_imp.numel() == 0:
+        return None
+    post_imp = _need(post_imp, torch.float32, "post_imp")
+    if post_imp.shape[0] != post_doc.shape[0]:
+        raise ValueError("post_imp must hold one impact per posting")
+    return post_imp.data_ptr()
+
+
+def bm25_build_posting_impacts(post_doc: Tensor, post_tf: Tensor, norm: Tensor) -> Tensor:
+    """post_imp[i] = tf / (tf + norm[doc]) of every posting, with the search kernel's own expression (ragb200.h)."""
+    post_doc = _need(post_doc, torch.int32, "post_doc")
+    post_tf = _need(post_tf, torch.int16, "post_tf")
+    norm = _need(norm, torch.float32, "norm")
+    out = torch.empty(post_doc.shape[0], dtype=torch.float32, device=post_doc.device)
+    if post_doc.shape[0]:
+        with torch.cuda.device(post_doc.device):
+            check(lib.ragb_bm25_build_posting_impacts(_ptr(post_doc), _ptr(post_tf), _ptr(norm), post_doc.shape[0], _ptr(out),
+                                                      _stream()))
+    return out
+
+
 def _bm25_args(term_off, post_doc, post_tf, norm, idf, q_terms, q_off):
     term_off = _need(term_off, torch.int64, "term_off")
     post_doc = _need(post_doc, torch.int32, "post_doc")
@@ -163,13 +185,14 @@ def _bm25_args(term_off, post_doc, post_tf, norm, idf, q_terms, q_off):
 def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
                     dense_tf: Tensor, dense_terms: Tensor, dense_imp: Tensor, dense_maximp: Tensor, q_terms: Tensor,
                     q_off: Tensor, max_query_terms: int, id_base: int, k: int, seed: Tensor, dense_cap: Tensor,
-                    hi_off: Tensor, hi_doc: Tensor) -> Tuple[Tensor, Tensor]:
+                    hi_off: Tensor, hi_doc: Tensor, post_imp: Tensor) -> Tuple[Tensor, Tensor]:
     """dense_imp (float16 [n_dense, stride]) / dense_maximp (float32 [n_dense]): optional impact bounds of the table
     terms (ragb200.h); pass empty tensors to run without them - the results are the same.
     seed (float32 [B] or empty): proven lower bounds of every query's k-th best score (``bm25_seed``, possibly raised
     to the maximum over all shards); empty = the kernel seeds itself.
     dense_cap (float32 [n_dense]) / hi_off (int32 [n_dense + 1]) / hi_doc (int32): optional impact cap of the table rows
-    and the marker lists of the documents above it (ragb200.h); empty tensors = none.  Pruning only."""
+    and the marker lists of the documents above it (ragb200.h); empty tensors = none.  Pruning only.
+    post_imp (float32 [nnz] or empty): baked impacts of the postings (``bm25_build_posting_impacts``); speed only."""
     term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
                                                                         q_terms, q_off)
     n_q, n_docs, dev = q_off.shape[0] - 1, norm.shape[0], norm.device
@@ -191,9 +214,10 @@ def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: T
             raise ValueError("seed must hold one bound per query")
         seed_ptr = seed.data_ptr()
     cap, hoff, hdoc = _impact_cap(dense_cap, hi_off, hi_doc, n_dense)
+    pimp = _posting_impacts(post_imp, post_doc)
     with torch.cuda.device(dev):
         check(lib.ragb_bm25_score_topk(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf),
-                                       idf.shape[0], k1, dt, stride, dterms, n_dense, imp, maximp, cap, hoff, hdoc,
+                                       idf.shape[0], k1, dt, stride, dterms, n_dense, imp, maximp, cap, hoff, hdoc, pimp,
                                        _ptr(q_terms), _ptr(q_off), n_q,
                                        max_query_terms, n_docs, id_base, k, seed_ptr, _ptr(score), _ptr(ids), _ptr(ws),
                                        ws.numel(), _stream()))
@@ -202,7 +226,7 @@ def bm25_score_topk(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: T
 
 @bm25_score_topk.register_fake
 def _(term_off, post_doc, post_tf, norm, idf, k1, dense_tf, dense_terms, dense_imp, dense_maximp, q_terms, q_off,
-      max_query_terms, id_base, k, seed, dense_cap, hi_off, hi_doc):
+      max_query_terms, id_base, k, seed, dense_cap, hi_off, hi_doc, post_imp):
     n_q = q_off.shape[0] - 1
     return norm.new_empty((n_q, k)), norm.new_empty((n_q, k), dtype=torch.int32)
 
@@ -220,7 +244,7 @@ def bm25_workspace(n_queries: int, n_docs: int, k: int, device) -> Tensor:
 def bm25_score_part(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: Tensor, idf: Tensor, k1: float,
                     dense_tf: Tensor, dense_terms: Tensor, dense_imp: Tensor, dense_maximp: Tensor, q_terms: Tensor,
                     q_off: Tensor, max_query_terms: int, id_base: int, k: int, seed: Tensor, dense_cap: Tensor,
-                    hi_off: Tensor, hi_doc: Tensor, stripe_begin: int,
+                    hi_off: Tensor, hi_doc: Tensor, post_imp: Tensor, stripe_begin: int,
                     stripe_end: int, min_smem_bytes: int, workspace: Tensor) -> None:
     """Score the stripes [stripe_begin, stripe_end) of the staged BM25 search into ``workspace`` (ragb200.h)."""
     term_off, post_doc, post_tf, norm, idf, q_terms, q_off = _bm25_args(term_off, post_doc, post_tf, norm, idf,
@@ -233,9 +257,10 @@ def bm25_score_part(term_off: Tensor, post_doc: Tensor, post_tf: Tensor, norm: T
         maximp = _need(dense_maximp, torch.float32, "dense_maximp").data_ptr()
     seed_ptr = _need(seed, torch.float32, "seed").data_ptr() if seed.numel() else None
     cap, hoff, hdoc = _impact_cap(dense_cap, hi_off, hi_doc, n_dense)
+    pimp = _posting_impacts(post_imp, post_doc)
     with torch.cuda.device(dev):
         check(lib.ragb_bm25_score_part(_ptr(term_off), _ptr(post_doc), _ptr(post_tf), _ptr(norm), _ptr(idf), idf.shape[0], k1,
-                                       dt, stride, dterms, n_dense, imp, maximp, cap, hoff, hdoc, _ptr(q_terms), _ptr(q_off), n_q,
+                                       dt, stride, dterms, n_dense, imp, maximp, cap, hoff, hdoc, pimp, _ptr(q_terms), _ptr(q_off), n_q,
                                        max_query_terms, n_docs, id_base, k, seed_ptr, stripe_begin, stripe_end,
                                        min_smem_bytes, _ptr(workspace), workspace.numel(), _stream()))
 

@@ -32,6 +32,7 @@ MAX_DENSE_TERMS = 1024          # rows the kernel's table directory can hold
 DENSE_MIN_FRACTION = int(os.environ.get("RAGB_DENSE_MIN_FRACTION", "16"))  # a term gets a row when df >= N / this ...
 DENSE_TABLE_BYTES = 8 << 30     # ... while the table stays under this many bytes per shard
 IMPACT_TABLE_BYTES = 12 << 30   # the fp16 impact bounds of the table rows are optional: skipped above this size
+POSTING_IMPACTS = int(os.environ.get("RAGB_POSTING_IMPACTS", "1"))   # bake tf / (tf + norm) per posting (4 bytes each) for the window phase of the search
 IMPACT_CAP_TAIL = float(os.environ.get("RAGB_IMPACT_CAP_TAIL", "0.001"))   # share of a row's documents listed above its cap (0 = no cap)
 
 
@@ -59,7 +60,9 @@ class SparseShard:
     dense_cap: Optional[Tensor] = None     # float32 [n_dense]: impact cap of each row (all but the marker documents stay below)
     hi_off: Optional[Tensor] = None        # int32 [n_dense + 1]
     hi_doc: Optional[Tensor] = None        # int32: ascending local rows of the documents above the cap, row by row
+    post_imp: Optional[Tensor] = None      # float32 [nnz]: tf / (tf + norm[doc]) of every posting (derived; rebuilt by finalize)
     use_dense_table: bool = True
+    bake_impacts: bool = True              # SegmentedIndex turns it off: its refresh stays O(V + N), not O(nnz)
     df_global: Optional[Tensor] = None     # document frequencies summed over all shards (set by finalize)
 
     @property
@@ -78,6 +81,10 @@ class SparseShard:
         self.norm = ops.bm25_build_norm(self.doc_len, self.avgdl, self.k1, self.b)
         self._build_dense_table(df_global, group)
         self._build_impact_bounds()
+        # baked impacts: norm moves with the global statistics, so they are rebuilt here (one streaming kernel)
+        self.post_imp = None
+        if POSTING_IMPACTS and self.bake_impacts and self.nnz > 0 and self.post_doc.is_cuda:
+            self.post_imp = ops.bm25_build_posting_impacts(self.post_doc, self.post_tf, self.norm)
         return self
 
     def _build_impact_bounds(self) -> None:
@@ -164,7 +171,12 @@ class SparseShard:
         cap, hoff, hdoc = self._cap_tensors()
         return ops.bm25_score_topk(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1,
                                    self.dense_tf, self.dense_terms, self.dense_imp, self.dense_maximp, q_terms, q_off,
-                                   max_terms, self.id_base, k, seed, cap, hoff, hdoc)
+                                   max_terms, self.id_base, k, seed, cap, hoff, hdoc, self._impacts())
+
+    def _impacts(self) -> Tensor:
+        if self.post_imp is None:
+            return torch.empty(0, dtype=torch.float32, device=self.post_doc.device)
+        return self.post_imp
 
     def _cap_tensors(self):
         if self.dense_cap is None or self.hi_off is None or self.hi_doc is None:
@@ -181,7 +193,7 @@ class SparseShard:
         cap, hoff, hdoc = self._cap_tensors()
         ops.bm25_score_part(self.term_off, self.post_doc, self.post_tf, self.norm, self.idf, self.k1, self.dense_tf,
                             self.dense_terms, self.dense_imp, self.dense_maximp, q_terms, q_off, max_terms, self.id_base, k,
-                            seed, cap, hoff, hdoc, stripe_begin, stripe_end, min_smem_bytes, workspace)
+                            seed, cap, hoff, hdoc, self._impacts(), stripe_begin, stripe_end, min_smem_bytes, workspace)
 
     def score_docs(self, q_terms: Tensor, q_off: Tensor, max_terms: int, cand_ids: Tensor) -> Tensor:
         """Exact BM25 scores [B, C] of chosen passages (global ids, -1 = none): ragb_bm25_score_docs."""
@@ -323,6 +335,7 @@ class SegmentedIndex:
     def append(self, doc_off: Tensor, doc_tok: Tensor, vocab: int) -> None:
         seg = build_shard(doc_off, doc_tok, vocab, id_base=self.n_docs, k1=self.k1, b=self.b, epsilon=self.epsilon)
         seg.use_dense_table = self.use_dense_table
+        seg.bake_impacts = False
         self.vocab = max(self.vocab, vocab)
         self.segments.append(seg)
         self.n_docs += seg.n_docs
@@ -333,6 +346,7 @@ class SegmentedIndex:
             for s in (self.segments[i], self.segments[i + 1]):
                 grow_vocab(s, self.vocab)
             self.segments[i:i + 2] = [merge_adjacent(self.segments[i], self.segments[i + 1])]
+            self.segments[i].bake_impacts = False
         self.refresh()
 
     def refresh(self) -> None:

@@ -75,6 +75,12 @@ int ragb_bm25_build_dense_table(const int64_t* term_off, const int32_t* post_doc
 int ragb_bm25_build_impact_bounds(const uint8_t* dense_tf, int64_t dense_stride, int32_t n_dense, const float* norm,
                                   int64_t n_docs, uint16_t* dense_imp_fp16_out, float* dense_max_imp_out,
                                   ragb_stream_t stream);
+/* ragb_bm25_build_posting_impacts: post_imp_out[i] = tf / (tf + norm[post_doc[i]]) of posting i, float32, evaluated
+ *   with the scoring kernel's own expression (so the search adds the very bits the tf + norm path computes): the
+ *   per-document part of a posting's contribution, which rank_bm25 get_scores recomputes for every query
+ *   (streaming_index.py:169).  Must be rebuilt whenever norm changes (global statistics).  See ragb_bm25_score_topk. */
+int ragb_bm25_build_posting_impacts(const int32_t* post_doc, const uint16_t* post_tf, const float* norm, int64_t nnz,
+                                    float* post_imp_out, ragb_stream_t stream);
 
 /* ---- BM25 scoring : rank_bm25 BM25Okapi.get_scores + BM25Index.search
  *      (rag_uq/streaming_index.py:165-179) --------------------------------------------
@@ -96,6 +102,10 @@ int ragb_bm25_build_impact_bounds(const uint8_t* dense_tf, int64_t dense_stride,
  * A document that is on no such "marker list" gets at most weight * dense_cap[r] from row r - a much tighter promise
  * than the row maximum, which a handful of documents set - so far more queries can skip the documents no posting
  * list touches; the listed documents are always scored exactly.  Pruning only: results are identical.
+ * Optional baked impacts post_imp[nnz] (ragb_bm25_build_posting_impacts; NULL = none): with them a posting is
+ * self-contained (document, impact) and the pruned phase of the search reads the pair instead of chaining a gather
+ * of norm[doc], a convert and a reciprocal behind every load of postings.  Speed only: results are bit-identical
+ * with and without them.
  * max_query_terms (<= RAGB_MAX_QUERY_TERMS) is the caller's bound on the longest query;
  * it sizes the per-warp cursor table and longer queries are cut to it.
  * score = sum idf[t] * tf * (k1 + 1) / (tf + norm[d]).   Only score > 0 is returned
@@ -107,6 +117,7 @@ int ragb_bm25_score_topk(const int64_t* term_off, const int32_t* post_doc, const
                          const int32_t* dense_terms, int32_t n_dense,
                          const uint16_t* dense_imp_fp16, const float* dense_max_imp,
                          const float* dense_cap, const int32_t* hi_off, const int32_t* hi_doc,
+                         const float* post_imp,
                          const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
                          int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          const float* seed_thr, float* out_score, int32_t* out_id,
@@ -136,6 +147,7 @@ int ragb_bm25_score_part(const int64_t* term_off, const int32_t* post_doc, const
                          const int32_t* dense_terms, int32_t n_dense,
                          const uint16_t* dense_imp_fp16, const float* dense_max_imp,
                          const float* dense_cap, const int32_t* hi_off, const int32_t* hi_doc,
+                         const float* post_imp,
                          const int32_t* q_terms, const int32_t* q_off, int32_t n_queries,
                          int32_t max_query_terms, int64_t n_docs, int64_t id_base, int32_t k,
                          const float* seed_thr, int32_t stripe_begin, int32_t stripe_end, int64_t min_smem_bytes,

@@ -292,6 +292,38 @@ def test_bm25_impact_bounds_only_prune(rq, dev, n, n_q, k):
     assert bool((same | (with_s == want_s)).all())      # ids may differ only inside exact score ties
 
 
+@pytest.mark.parametrize("n,n_q,k", [(600_000, 256, 50), (300_000, 128, 10), (70_001, 33, 100)])
+def test_bm25_baked_impacts_bit_identical(rq, dev, n, n_q, k):
+    """Baked impacts (ragb_bm25_build_posting_impacts), read by the window phase instead of tf + norm[doc], are a speed
+    device only: post_imp holds the bits the tf + norm path computes, and ids and scores are identical with and
+    without them (and equal the exhaustive get_scores ranking)."""
+    from rag_uq_b200 import synth
+    vocab, cdf, doc_off, doc_tok = _synthetic_corpus(rq, dev, n)
+    shard = rq.build_shard(doc_off, doc_tok, vocab).finalize()
+    assert shard.post_imp is not None and shard.post_imp.shape[0] == shard.nnz
+    tf = (shard.post_tf.to(torch.int32) & 0xFFFF).float()
+    want_imp = tf / (tf + shard.norm[shard.post_doc.long()])
+    torch.testing.assert_close(shard.post_imp, want_imp, rtol=3e-7, atol=0)      # rcp.approx: 1 ulp
+    qb = synth.make_queries(n_q, n, 64, cdf, dev)
+    with_s, with_i = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+    keep, shard.post_imp = shard.post_imp, None
+    without_s, without_i = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+    shard.post_imp = keep
+    assert torch.equal(with_i, without_i) and torch.equal(with_s, without_s)
+    # also without the impact cap (no marker lists) and without the table (every term is a posting list)
+    cap = shard.dense_cap, shard.hi_off, shard.hi_doc
+    shard.dense_cap = shard.hi_off = shard.hi_doc = None
+    s2, i2 = shard.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k)
+    shard.dense_cap, shard.hi_off, shard.hi_doc = cap
+    assert torch.equal(with_i, i2) and torch.equal(with_s, s2)
+    full = shard.scores(qb.q_terms, qb.q_off, qb.max_terms)
+    want_s, want_i = torch.topk(full, k, dim=1)
+    want_s = torch.where(want_s > 0, want_s, torch.zeros_like(want_s))
+    torch.testing.assert_close(with_s, want_s, rtol=0, atol=0)
+    same = (with_i.long() == want_i) | (with_s == 0)
+    assert bool((same | (with_s == want_s)).all())
+
+
 _WINDOW_STRESS = r"""
 import sys, torch
 sys.path.insert(0, sys.argv[1])
