@@ -209,7 +209,7 @@ constexpr int BM_HASH_MAX = 352;       // inserts stop being attempted beyond th
 constexpr int BM_WINDOW_MAX = 32768;   // documents per window (offsets must also stay well inside int32)
 
 // Returns false when the table would overflow (nothing usable was changed: the caller restores the cursors).
-template <int U, bool MARK_ONLY = false, bool IMP = false>   // IMP: post_tf is really post_imp (float): baked impacts
+template <int U, bool MARK_ONLY = false, bool IMP = false>   // IMP: post_tf is really post_imp (float): baked impacts   // IMP: post_tf is really post_imp (float): baked impacts
 __device__ __forceinline__ bool stream_term_hash(const int32_t* __restrict__ post_doc,
                                                  const uint16_t* __restrict__ post_tf, int64_t& pos, const int64_t end,
                                                  const int d0, const int d1, const float weight, int* keys, float* vals,
@@ -301,41 +301,45 @@ __global__ void __launch_bounds__(256) posting_impacts_kernel(const int32_t* __r
   }
 }
 
+// per-warp shared-memory region: [accumulator / hash window 4 KB][touched bits 128 B][per-term arrays 49 B x max_terms]
+constexpr int BM_REGION_BITS = sizeof(float) * BM_SUPER_DOCS;
+constexpr int BM_REGION_TERMS = BM_REGION_BITS + sizeof(unsigned) * (BM_SUPER_DOCS / 32);
+__host__ __device__ constexpr size_t bm25_warp_region_bytes(int max_terms) {
+  return (static_cast<size_t>(BM_REGION_TERMS) + 49u * max_terms + 15u) & ~static_cast<size_t>(15);
+}
+
 template <bool DENSE_OUT, bool IMP = false>   // IMP: the window phase reads baked impacts (Bm25Args::post_imp)
 __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm25_kernel(const Bm25Args a) {   // get_scores streams: occupancy first
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // read once: a volatile asm is not re-executed, so the thread index (and what hangs on it) stays in registers
+  // instead of being re-derived from S2R at every use under the register cap
+  unsigned tid_u;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_u));
+  const int tid = static_cast<int>(tid_u), warp = tid >> 5, lane = tid & 31;
   const int mt = a.max_terms;
   BM_PROF_T(prof_t0);
-  // carve shared memory
-  unsigned char* sp = smem_raw;
-  int64_t* s_pos = reinterpret_cast<int64_t*>(sp) + warp * mt;
-  sp += sizeof(int64_t) * BM_WARPS * mt;
-  int64_t* s_end = reinterpret_cast<int64_t*>(sp) + warp * mt;
-  sp += sizeof(int64_t) * BM_WARPS * mt;
+  // Carve shared memory, warp-major: everything a warp touches in its main loop lives in ONE region behind one base
+  // pointer, at offsets that are multiples of max_terms (a kernel parameter, i.e. a constant-bank operand), so an
+  // address costs one multiply-add from the base instead of a chain that starts at threadIdx (under the 80-register
+  // budget the compiler re-materialised those chains - S2R included - all over the window loop: 7 % of the
+  // instructions).  Only the candidate keys stay array-major: the fold at the end of the block reads all warps' lists.
+  unsigned char* const wb = smem_raw + static_cast<size_t>(warp) * bm25_warp_region_bytes(mt);
+  float* const sacc = reinterpret_cast<float*>(wb);                                  // posting-list contributions of a super-range
+  unsigned* const s_bits = reinterpret_cast<unsigned*>(wb + BM_REGION_BITS);         // documents touched by a posting
+  unsigned* const touched = DENSE_OUT ? nullptr : s_bits;
+  int64_t* const s_pos = reinterpret_cast<int64_t*>(wb + BM_REGION_TERMS);           // cursor of each sparse term
+  int64_t* const s_end = reinterpret_cast<int64_t*>(wb + BM_REGION_TERMS + 8 * mt);
+  const uint8_t** const s_drow = reinterpret_cast<const uint8_t**>(wb + BM_REGION_TERMS + 16 * mt);  // dense-table row of each dense term
+  const __half** const s_irow = reinterpret_cast<const __half**>(wb + BM_REGION_TERMS + 24 * mt);    // its row of fp16 impact bounds
+  float* const s_wgt = reinterpret_cast<float*>(wb + BM_REGION_TERMS + 32 * mt);     // sparse term weights
+  float* const s_dwgt = reinterpret_cast<float*>(wb + BM_REGION_TERMS + 36 * mt);    // dense-table term weights
+  int* const s_nxt = reinterpret_cast<int*>(wb + BM_REGION_TERMS + 40 * mt);         // next document of each sparse term
+  int* const s_tmp = reinterpret_cast<int*>(wb + BM_REGION_TERMS + 44 * mt);         // term ids while the cursors are placed
+  unsigned char* const s_dense = wb + BM_REGION_TERMS + 48 * mt;                     // chunks per pass class of each sparse term
+  unsigned char* sp = smem_raw + static_cast<size_t>(BM_WARPS) * bm25_warp_region_bytes(mt);
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(sp) + warp * a.capacity;  // this warp's candidate keys
   if (!DENSE_OUT) sp += sizeof(uint64_t) * a.capacity * BM_WARPS;
-  const uint8_t** s_drow = reinterpret_cast<const uint8_t**>(sp) + warp * mt;  // dense-table row of each dense term
-  sp += sizeof(uint8_t*) * BM_WARPS * mt;
-  const __half** s_irow = reinterpret_cast<const __half**>(sp) + warp * mt;     // its row of fp16 impact bounds
-  sp += sizeof(__half*) * BM_WARPS * mt;
-  float* sacc = reinterpret_cast<float*>(sp) + warp * BM_SUPER_DOCS;  // posting-list contributions of a super-range
-  sp += sizeof(float) * BM_WARPS * BM_SUPER_DOCS;
-  unsigned* s_bits = reinterpret_cast<unsigned*>(sp) + warp * (BM_SUPER_DOCS / 32);  // documents touched by a posting
-  sp += sizeof(unsigned) * BM_WARPS * (BM_SUPER_DOCS / 32);
-  unsigned* const touched = DENSE_OUT ? nullptr : s_bits;
-  float* s_wgt = reinterpret_cast<float*>(sp) + warp * mt;    // sparse term weights
-  sp += sizeof(float) * BM_WARPS * mt;
-  float* s_dwgt = reinterpret_cast<float*>(sp) + warp * mt;   // dense-table term weights
-  sp += sizeof(float) * BM_WARPS * mt;
-  int* s_nxt = reinterpret_cast<int*>(sp) + warp * mt;        // next document of each sparse term
-  sp += sizeof(int) * BM_WARPS * mt;
-  int* s_tmp = reinterpret_cast<int*>(sp) + warp * mt;        // term ids while the cursors are placed
-  sp += sizeof(int) * BM_WARPS * mt;
-  unsigned char* s_dense = sp + warp * mt;                    // chunks per pass class of each sparse term
-  sp += (static_cast<size_t>(BM_WARPS) * mt + 15) & ~static_cast<size_t>(15);
   int* const s_dterms = reinterpret_cast<int*>(sp);           // table directory (block-wide, a.n_dense entries)
-  sp += (sizeof(int) * a.n_dense + 15) & ~static_cast<size_t>(15);
 
   const int q = blockIdx.x;
   const int stripe = a.stripe0 + static_cast<int>(blockIdx.y);
@@ -606,12 +610,13 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
           const bool essential = !(n_noness > 0 && __shfl_sync(0xffffffffu, my_rank, ti) < n_noness);
           int next_doc = INT_MAX;
           const uint16_t* const ptf = IMP ? reinterpret_cast<const uint16_t*>(a.post_imp) : a.post_tf;
-          switch (s_dense[ti]) {  // chunks per pass sized to the term's density (warp-uniform)
-            case 0: ok = stream_term_hash<1, false, IMP>(a.post_doc, ptf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
-            case 1: ok = stream_term_hash<2, false, IMP>(a.post_doc, ptf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
-            case 4: ok = stream_term_hash<1, true>(a.hi_doc, nullptr, pos, end, d0, d1, 0.0f, keys, vals, flags, true, a.norm, lane, next_doc, n_keys, mflags); break;
-            default: ok = stream_term_hash<4, false, IMP>(a.post_doc, ptf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys); break;
-          }
+          // One instantiation for every posting list (two 32-posting chunks per pass) and one for the marker lists: the
+          // density-specific variants (1 / 2 / 4 chunks per pass) measured 7 % SLOWER - the kernel is ~125 KB of code,
+          // warps of a block sit in different phases, and ncu charged 11 % of the stalls to instruction fetch.
+          if (s_dense[ti] == 4)   // warp-uniform
+            ok = stream_term_hash<1, true>(a.hi_doc, nullptr, pos, end, d0, d1, 0.0f, keys, vals, flags, true, a.norm, lane, next_doc, n_keys, mflags);
+          else
+            ok = stream_term_hash<2, false, IMP>(a.post_doc, ptf, pos, end, d0, d1, w, keys, vals, flags, essential, a.norm, lane, next_doc, n_keys);
           if (ok && lane == 0) {
             s_pos[ti] = pos;
             s_nxt[ti] = next_doc;
@@ -742,10 +747,18 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
         unsigned* const mark = (n_noness > 0 && __shfl_sync(0xffffffffu, my_rank, ti & 31) < n_noness) ? nullptr : touched;
         switch (s_dense[ti]) {  // chunks per pass sized to the term's density (warp-uniform)
           case 4: stream_term<1, true>(a.hi_doc, nullptr, pos, end, s0, s1, 0.0f, sacc, a.norm, touched, lane, next_doc); break;
-          case 0: stream_term<1>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
-          case 1: stream_term<2>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
-          case 2: stream_term<4>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
-          default: stream_term<8>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
+          default:
+            if (DENSE_OUT) {   // get_scores streams every list: chunks per pass by density
+              switch (s_dense[ti]) {
+                case 0: stream_term<1>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
+                case 1: stream_term<2>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
+                case 2: stream_term<4>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
+                default: stream_term<8>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc); break;
+              }
+            } else {           // top-k search: this phase is the minority, one variant keeps the kernel's code small
+              stream_term<4>(a.post_doc, a.post_tf, pos, end, s0, s1, w, sacc, a.norm, mark, lane, next_doc);
+            }
+            break;
         }
         if (lane == 0) {
           s_pos[ti] = pos;
@@ -1226,17 +1239,10 @@ static int bm25_stripes(int n_queries, int64_t n_docs, int64_t* stripe_docs_out)
 }
 
 static size_t bm25_smem_bytes(int max_terms, int capacity, bool dense_out, int n_dense) {
-  const size_t r16 = ~static_cast<size_t>(15);
-  size_t b = 0;
-  b += 2 * sizeof(int64_t) * BM_WARPS * max_terms;
+  size_t b = BM_WARPS * bm25_warp_region_bytes(max_terms);
   if (!dense_out) b += sizeof(uint64_t) * capacity * BM_WARPS;
-  b += 2 * sizeof(void*) * BM_WARPS * max_terms;
-  b += sizeof(float) * BM_WARPS * BM_SUPER_DOCS;
-  b += sizeof(unsigned) * BM_WARPS * (BM_SUPER_DOCS / 32);
-  b += (2 * sizeof(float) + 2 * sizeof(int)) * BM_WARPS * max_terms;
-  b += (static_cast<size_t>(BM_WARPS) * max_terms + 15) & r16;   // s_dense
-  b += (sizeof(int) * n_dense + 15) & r16;                       // table directory
-  return (b + 15) & r16;
+  b += sizeof(int) * n_dense;                                    // table directory
+  return (b + 15) & ~static_cast<size_t>(15);
 }
 
 static int bm25_common_checks(const char* who, const int64_t* term_off, const int32_t* post_doc,
