@@ -7,12 +7,14 @@
 // Data layout: passages [n_rows, dim] bf16 row-major (unit rows), queries [B, dim] bf16.
 // Algorithmic bytes: n_rows * dim * 2 per call (queries and candidates are noise).
 //
-// Kernel shape: persistent grid (SMs x 4 blocks of 256 threads).  A warp owns 4 rows at a
+// Kernel shape: one resident wave (SMs x the blocks of 256 threads that fit per SM, at most 4).  A warp owns 4 rows at a
 // time: each lane issues 4 x (dim/256) independent 16-byte streaming loads (L1 bypass), so
 // a full SM keeps ~100 KB in flight, multiplies against the queries held in shared memory
 // as fp32, and reduces with shuffles.  Scores go straight into the block's running top-k
 // (one per query); the score vector never exists in memory.
 #include <cstdlib>
+
+#include <algorithm>
 
 #include "common.cuh"
 #include "topk.cuh"
@@ -182,8 +184,6 @@ __global__ void __launch_bounds__(256) dense_scores_kernel(const uint4* __restri
   }
 }
 
-static int gemv_grid() { return device_sm_count() * 4; }
-
 template <int NQ>
 static int launch_gemv(const void* passages, int64_t row_first, int64_t n_rows, int dim, const void* queries, int k,
                        int64_t id_base, const float* seed_thr, uint64_t* part, int grid, cudaStream_t stream) {
@@ -217,6 +217,30 @@ static int launch_gemv(const void* passages, int64_t row_first, int64_t n_rows, 
   return RAGB_OK;
 }
 
+// Resident blocks per SM of the instantiation launch_gemv<NQ> picks for this shape (0 = unsupported shape).
+template <int NQ>
+static int gemv_blocks_per_sm(int dim, int k) {
+  const size_t smem = sizeof(float) * NQ * dim + sizeof(uint64_t) * NQ * topk_capacity(k);
+  int n = 0;
+#define RAGB_GEMV_OCC(C)                                                                                               \
+  case C:                                                                                                              \
+    if (cudaFuncSetAttribute(gemv_topk_kernel<NQ, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                             static_cast<int>(smem)) != cudaSuccess ||                                                 \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gemv_topk_kernel<NQ, C>, GV_THREADS, smem) != cudaSuccess)   \
+      n = 0;                                                                                                           \
+    break;
+  switch ((dim + 255) / 256) {
+    RAGB_GEMV_OCC(1)
+    RAGB_GEMV_OCC(2)
+    RAGB_GEMV_OCC(3)
+    RAGB_GEMV_OCC(4)
+    RAGB_GEMV_OCC(8)
+    default: break;
+  }
+#undef RAGB_GEMV_OCC
+  return n;
+}
+
 }  // namespace ragb
 
 using namespace ragb;
@@ -233,7 +257,16 @@ size_t ragb_dense_gemv_workspace_bytes(int32_t n_queries, int32_t k) {
 // one pass over rows [row_first, row_last) for all queries (groups of 4 / 2 / 1: register budget); -> grid used
 static int gemv_pass(const void* passages, int64_t row_first, int64_t row_last, int dim, const __nv_bfloat16* q, int n_queries,
                      int k, int64_t id_base, const float* seed_thr, uint64_t* part, int* grid_out, cudaStream_t stream) {
-  int grid = gemv_grid();
+  // One wave of blocks, all resident: the rows are split evenly between the blocks, so a grid of SMs x 4 with only
+  // 3 blocks per SM resident (76 registers at dim 768, batch 1) ran a quarter of the rows in a second wave at a
+  // third of the occupancy (ncu at 1M rows: 0.30 ms, 20 of 64 warps active on average).  The grid is SMs x the
+  // residency of the slowest-fitting instantiation this pass launches.
+  int per_sm = 4;
+  if (n_queries >= 4) per_sm = std::min(per_sm, gemv_blocks_per_sm<4>(dim, k));
+  if ((n_queries & 3) >= 2) per_sm = std::min(per_sm, gemv_blocks_per_sm<2>(dim, k));
+  if (n_queries & 1) per_sm = std::min(per_sm, gemv_blocks_per_sm<1>(dim, k));
+  if (per_sm < 1) per_sm = 1;
+  int grid = device_sm_count() * per_sm;
   if (grid > 148 * 4) grid = 148 * 4;
   const int64_t max_blocks = ceil_div64(row_last - row_first, GV_WARPS * GV_ROWS_PER_WARP);
   if (grid > max_blocks) grid = static_cast<int>(max_blocks);

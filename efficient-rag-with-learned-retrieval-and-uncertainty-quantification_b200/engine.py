@@ -201,7 +201,7 @@ class HybridEngine:
             d1 = mark() if events is not None else None
         b0 = mark() if events is not None else None
         cur.wait_event(prefix_done)
-        self.sparse.score_part(q_terms, q_off, max_terms, pool, ws, 0, first, OVERLAP_SMEM_PAD if first < stripes else 0)
+        self.sparse.score_part(q_terms, q_off, max_terms, pool, ws, 0, first, OVERLAP_SMEM_PAD)
         bmid = mark() if events is not None else None
         cur.wait_stream(side)
         if first < stripes:
