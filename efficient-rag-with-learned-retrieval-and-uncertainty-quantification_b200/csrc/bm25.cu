@@ -76,7 +76,8 @@ __device__ unsigned long long g_bm25_dbg[8];
 #ifdef RAGB_BM25_PROFILE
 // Profiling build only (scripts/profile_bm25_queries.py): warp cycles per query and phase, [phase][query]:
 // 0 set-up (term split, cursor placement), 1 window mode, 2 dense-accumulator / bound-pass super-ranges, 3 block fold,
-// inside window mode: 4 posting streaming + hash inserts, 5 compaction, 6 scoring of the marked documents, 7 windows visited.
+// inside window mode: 4 posting streaming + hash inserts, 5 compaction, 6 scoring of the marked documents; 7 the part of
+// the fold spent waiting for the slowest warp of the block.
 constexpr int BM_PROF_QUERIES = 4096;
 __device__ unsigned long long g_bm25_prof[8][BM_PROF_QUERIES];
 #define BM_PROF_T(var) const long long var = clock64()
@@ -941,7 +942,6 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
   BM_PROF_ADD(4, blockIdx.x, prof_stream);
   BM_PROF_ADD(5, blockIdx.x, prof_compact);
   BM_PROF_ADD(6, blockIdx.x, prof_score);
-  BM_PROF_ADD(7, blockIdx.x, prof_visits);
   BM_PROF_ADD(2, blockIdx.x, prof_t2 - prof_t1 - prof_win);
 #endif
   if (!DENSE_OUT) {
@@ -949,6 +949,9 @@ __global__ void __launch_bounds__(BM_THREADS, DENSE_OUT ? 4 : BM_MIN_BLOCKS) bm2
     // cross-stripe merge sees one list per block
     tk.flush(lane);
     __syncthreads();
+#ifdef RAGB_BM25_PROFILE
+    BM_PROF_ADD(7, blockIdx.x, clock64() - prof_t2);   // of the fold: the wait for the block's slowest warp
+#endif
     uint64_t* all_keys = s_keys - warp * a.capacity;  // [BM_WARPS][capacity], each sorted in its first k slots
     int n = 2;
     while (n < BM_WARPS * a.k) n <<= 1;               // <= BM_WARPS * capacity because k <= capacity / 2

@@ -32,10 +32,9 @@ s, _ = engine.sparse.score_topk(qb.q_terms, qb.q_off, qb.max_terms, 50)
 torch.cuda.synchronize()
 assert lib.ragb_debug_bm25_profile(buf) == 0
 c = np.frombuffer(buf, dtype=np.uint64).reshape(8, 4096)[:, :1024].astype(np.float64)
-names = ["setup", "window", "dense_or_bound", "fold", "win_stream", "win_compact", "win_score"]
+names = ["setup", "window", "dense_or_bound", "fold", "win_stream", "win_compact", "win_score", "fold_wait_for_slowest_warp"]
 total = c[:4].sum()
-out = {"passages": n, "warp_cycles_total": total, "share": {names[i]: c[i].sum() / total for i in range(7)},
-       "windows_visited": c[7].sum()}
+out = {"passages": n, "warp_cycles_total": total, "share": {names[i]: c[i].sum() / total for i in range(8)}}
 per_q = c[:4].sum(axis=0)
 order = np.argsort(-per_q)
 cum = np.cumsum(per_q[order]) / total

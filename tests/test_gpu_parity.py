@@ -453,6 +453,21 @@ def test_bm25_shards_with_global_statistics_equal_unsharded(rq, dev):
     parts = [sh.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k, seeds) for sh in shards]
     ms2, mi2 = rq.ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1), k)
     assert torch.equal(mi2, wi) and torch.equal(ms2, ws)
+    # ... and with every shard seeding only ITS slice of the batch (q_off sliced, offsets absolute), the others' entries 0:
+    # the MAX then hands each query the bound of the one shard that seeded it (HybridEngine.local_pools, world > 1)
+    n_q = qb.q_off.shape[0] - 1
+    per = -(-n_q // len(shards))
+    sliced = torch.zeros(n_q, dtype=torch.float32, device=dev)
+    for r, sh in enumerate(shards):
+        q0, q1 = min(n_q, r * per), min(n_q, (r + 1) * per)
+        part = sh.seed(qb.q_terms, qb.q_off[q0:q1 + 1], qb.max_terms, k)
+        full = sh.seed(qb.q_terms, qb.q_off, qb.max_terms, k)
+        assert torch.equal(part, full[q0:q1])                      # a sliced call seeds exactly those queries
+        sliced[q0:q1] = part
+    assert bool((sliced <= seeds).all()) and bool((sliced > 0).any())
+    parts = [sh.score_topk(qb.q_terms, qb.q_off, qb.max_terms, k, sliced) for sh in shards]
+    ms3, mi3 = rq.ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1), k)
+    assert torch.equal(mi3, wi) and torch.equal(ms3, ws)
 
 
 def test_bm25_staged_search_and_two_stream_overlap_equal_the_serial_path(rq, dev):
