@@ -15,7 +15,7 @@
 //
 //  1. Dense accumulator (1024-document super-ranges, the only phase of the get_scores variant).  Two ways a
 //     term reaches the accumulator:
-//     * the terms that occur in more than 1/16 of all documents (~150; they carry >95% of all postings) are
+//     * the terms that occur in more than 1/24 of all documents (~220; they carry >95% of all postings) are
 //       ALSO stored as a dense row of uint8 term frequencies; a lane loads its 8 bytes with one 64-bit load
 //       per term and accumulates in registers - no document ids, no cursor, no compare;
 //     * every other term streams its posting list: lists are sorted by document, so a warp continues reading

@@ -29,7 +29,7 @@ from torch import Tensor
 from . import ops
 
 MAX_DENSE_TERMS = 1024          # rows the kernel's table directory can hold
-DENSE_MIN_FRACTION = int(os.environ.get("RAGB_DENSE_MIN_FRACTION", "16"))  # a term gets a row when df >= N / this ...
+DENSE_MIN_FRACTION = int(os.environ.get("RAGB_DENSE_MIN_FRACTION", "24"))  # a term gets a row when df >= N / this ...
 DENSE_TABLE_BYTES = 8 << 30     # ... while the table stays under this many bytes per shard
 IMPACT_TABLE_BYTES = 12 << 30   # the fp16 impact bounds of the table rows are optional: skipped above this size
 POSTING_IMPACTS = int(os.environ.get("RAGB_POSTING_IMPACTS", "1"))   # bake tf / (tf + norm) per posting (4 bytes each) for the window phase of the search
