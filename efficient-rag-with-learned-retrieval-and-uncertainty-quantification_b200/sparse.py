@@ -33,7 +33,7 @@ DENSE_MIN_FRACTION = int(os.environ.get("RAGB_DENSE_MIN_FRACTION", "24"))  # a t
 DENSE_TABLE_BYTES = 8 << 30     # ... while the table stays under this many bytes per shard
 IMPACT_TABLE_BYTES = 12 << 30   # the fp16 impact bounds of the table rows are optional: skipped above this size
 POSTING_IMPACTS = int(os.environ.get("RAGB_POSTING_IMPACTS", "1"))   # bake tf / (tf + norm) per posting (4 bytes each) for the window phase of the search
-IMPACT_CAP_TAIL = float(os.environ.get("RAGB_IMPACT_CAP_TAIL", "0.001"))   # share of a row's documents listed above its cap (0 = no cap)
+IMPACT_CAP_TAIL = float(os.environ.get("RAGB_IMPACT_CAP_TAIL", "0.0001"))   # share of a row's documents listed above its cap (0 = no cap)
 
 
 @dataclass
