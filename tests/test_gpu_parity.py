@@ -292,6 +292,56 @@ def test_bm25_impact_bounds_only_prune(rq, dev, n, n_q, k):
     assert bool((same | (with_s == want_s)).all())      # ids may differ only inside exact score ties
 
 
+def test_bm25_extreme_document_lengths(rq, dev):
+    """rcp.approx (csrc/bm25.cu fast_rcp) outside the synthetic 20-300 token range: one-token passages (norm 0.38 of
+    the usual), a 40 000-token passage, term frequencies of 1, 255, 256 (first value that cannot use the byte table),
+    3 000 and 60 000 (near the uint16 limit of post_tf) - get_scores within 1e-5 of the float64 rank_bm25 arithmetic
+    and the same top-k, with and without the table, with and without baked impacts."""
+    g = torch.Generator().manual_seed(99)
+    vocab, n = 400, 6_000
+    docs = []
+    for d in range(n):
+        kind = d % 6
+        if kind == 0:
+            docs.append(torch.randint(0, vocab, (1,), generator=g))                       # one token
+        elif kind == 1:
+            docs.append(torch.randint(0, vocab, (3,), generator=g))
+        else:
+            docs.append(torch.randint(0, vocab, (int(torch.randint(20, 300, (1,), generator=g)),), generator=g))
+    docs[7] = torch.cat([torch.full((255,), 5), torch.randint(0, vocab, (50,), generator=g)])
+    docs[8] = torch.cat([torch.full((256,), 5), torch.randint(0, vocab, (50,), generator=g)])
+    docs[9] = torch.cat([torch.full((3000,), 6), torch.full((2000,), 5), torch.randint(0, vocab, (35_000,), generator=g)])
+    docs[10] = torch.cat([torch.full((60_000,), 7), torch.randint(0, vocab, (10,), generator=g)])
+    docs[11] = torch.full((1,), 7)
+    lens = torch.tensor([t.numel() for t in docs])
+    doc_off = torch.zeros(n + 1, dtype=torch.int64)
+    doc_off[1:] = torch.cumsum(lens, 0)
+    doc_tok = torch.cat(docs).to(torch.int32)
+    ref = bm25_okapi.OkapiCsr(doc_off.numpy(), doc_tok.numpy(), vocab)
+    queries = [[5, 6, 7], [7], [5], [6, 1, 2, 3], [0, 5, 9, 7, 6, 11, 13, 17]]
+    q_off = torch.tensor([0] + list(np.cumsum([len(q) for q in queries])), dtype=torch.int32, device=dev)
+    q_terms = torch.tensor([t for q in queries for t in q], dtype=torch.int32, device=dev)
+    for table in (True, False):
+        shard = rq.build_shard(doc_off.to(dev), doc_tok.to(dev), vocab)
+        shard.use_dense_table = table
+        shard.finalize()
+        full = shard.scores(q_terms, q_off, 8).cpu().numpy()
+        for qi, q in enumerate(queries):
+            want = ref.get_scores(np.asarray(q))
+            np.testing.assert_allclose(full[qi], want, rtol=1e-5, atol=1e-9)
+        for use_imp in (True, False):
+            keep = shard.post_imp
+            if not use_imp:
+                shard.post_imp = None
+            for k in (10, 100):
+                score, ids = shard.score_topk(q_terms, q_off, 8, k)
+                ts, ti = torch.topk(torch.from_numpy(full).to(dev), k, dim=1)
+                ts = torch.where(ts > 0, ts, torch.zeros_like(ts))
+                assert torch.equal(score, ts), (table, use_imp, k)
+                assert bool(((ids.long() == ti) | (score == 0) | (score == torch.roll(score, 1, 1)) | (score == torch.roll(score, -1, 1))).all())
+            shard.post_imp = keep
+
+
 @pytest.mark.parametrize("n,n_q,k", [(600_000, 256, 50), (300_000, 128, 10), (70_001, 33, 100)])
 def test_bm25_baked_impacts_bit_identical(rq, dev, n, n_q, k):
     """Baked impacts (ragb_bm25_build_posting_impacts), read by the window phase instead of tf + norm[doc], are a speed
