@@ -380,8 +380,9 @@ class HybridEngine:
                 sub_off = torch.cat([sub_off, sub_off[-1] + (torch.arange(1, pad + 1, device=q_off.device, dtype=torch.int32) * int(lens[0]))])
             else:
                 sub_emb = q_emb[redo].contiguous()
+            # the batch's own (b_cap, d_hi) grid: valid for any subset of it, and the same cached bound table every step
             fv, fi = self._full_fusion_exhaustive(sub_terms.contiguous(), sub_off.contiguous(), max_terms, sub_emb, router, k,
-                                                  None, None, None, None, merge=False)
+                                                  None, None, None, None, merge=False, bounds=(b_cap, d_hi))
             val[redo], ids[redo] = fv[:n_redo, :kk], fi[:n_redo, :kk]
         if events is not None:
             events.setdefault("bm25", []).append((e0, e1))
@@ -391,7 +392,8 @@ class HybridEngine:
 
     def _full_fusion_exhaustive(self, q_terms: Tensor, q_off: Tensor, max_terms: int, q_emb: Tensor, router, k: int = 10,
                                 query_chunk: Optional[int] = None, fused: Optional[bool] = None,
-                                counters: Optional[Tensor] = None, events=None, merge: bool = True):
+                                counters: Optional[Tensor] = None, events=None, merge: bool = True,
+                                bounds: Optional[Tuple[float, float]] = None):
         """Gate evaluated for EVERY (query, passage) pair on the true scores ("full-fusion").
 
         Oracle: ``RetrievalRouter.hybrid_rerank(bm25_full[B,N], dense_full[B,N], k)`` (router.py:179-202).
@@ -422,12 +424,24 @@ class HybridEngine:
         out_s, out_i = [], []
         q_off_host = q_off.tolist()
         if fused:
-            b_cap = self.bm25_score_cap(q_terms, q_off)
-            b_cap = float(min(64.0, 2.0 ** max(0, int(b_cap - 1e-9).bit_length()))) if b_cap > 0 else 1.0
-            d_hi = self._max_passage_norm() * float(q_emb.float().norm(dim=1).max()) * 1.002 + 1e-3
-            d_hi = float(-(-d_hi * 64 // 1) / 64)   # round up to 1/64 so the cached table is reused across batches
+            if bounds is not None:      # a caller that already bounded a superset of these queries
+                b_cap, d_hi = bounds
+            else:
+                b_cap = self.bm25_score_cap(q_terms, q_off)
+                b_cap = float(min(64.0, 2.0 ** max(0, int(b_cap - 1e-9).bit_length()))) if b_cap > 0 else 1.0
+                d_hi = self._max_passage_norm() * float(q_emb.float().norm(dim=1).max()) * 1.002 + 1e-3
+                d_hi = float(-(-d_hi * 64 // 1) / 64)   # round up to 1/64 so the cached table is reused across batches
             gate_bounds = router.full_fusion_table(b_cap, d_hi)
-            bm = torch.empty((tiles, min(query_chunk, n_q), ops.SCORE_TILE), dtype=torch.float32, device=q_emb.device)
+            # the tiled BM25 matrix of a chunk is kept between calls when it is small (the fallback of the threshold search
+            # asks for the same ~360 MB every step; a fresh allocation while the previous step is still in flight
+            # occasionally cost a cudaMalloc of tens of milliseconds)
+            shape = (tiles, min(query_chunk, n_q), ops.SCORE_TILE)
+            keep = getattr(self, "_ff_bm", None)
+            if keep is not None and tuple(keep.shape) == shape and keep.device == q_emb.device:
+                bm = keep
+            else:
+                bm = torch.empty(shape, dtype=torch.float32, device=q_emb.device)
+                self._ff_bm = bm if bm.numel() * 4 <= (1 << 30) else None
             if counters is None:
                 counters = torch.empty(0, dtype=torch.int64, device=q_emb.device)
         for lo in range(0, n_q, query_chunk):

@@ -162,7 +162,10 @@ class RetrievalRouter(nn.Module):
         key = (float(b_cap), float(d_hi), int(n_b), int(n_d), tuple((t.data_ptr(), t._version) for t in tensors))
         cache = self.__dict__.setdefault("_ff_cache", {})
         if key not in cache:
-            cache.clear()
+            # entries of other (b_cap, d_hi) grids stay (the fallback of the threshold search alternates between a few);
+            # entries of older weights or statistics go
+            for stale in [c for c in cache if c[-1] != key[-1]] + (list(cache)[:1] if len(cache) >= 16 else []):
+                cache.pop(stale, None)
             w1, b1, w2, b2, stats = (t.detach().cpu().numpy() for t in self._weights())
             cache[key] = torch.from_numpy(full_fusion_bounds(w1, b1, w2, b2, stats, b_cap, d_hi, n_b, n_d)).to(
                 self.scorer[0].weight.device)
@@ -175,7 +178,8 @@ class RetrievalRouter(nn.Module):
         key = ("env", float(b_cap), float(d_hi), int(n_b), int(n_d), tuple((t.data_ptr(), t._version) for t in tensors))
         cache = self.__dict__.setdefault("_env_cache", {})
         if key not in cache:
-            cache.clear()
+            for stale in [c for c in cache if c[-1] != key[-1]] + (list(cache)[:1] if len(cache) >= 16 else []):
+                cache.pop(stale, None)
             w1, b1, w2, b2, stats = (t.detach().cpu().numpy() for t in self._weights())
             cache[key] = torch.from_numpy(full_fusion_envelope(w1, b1, w2, b2, stats, b_cap, d_hi, n_b, n_d)).to(
                 self.scorer[0].weight.device)
