@@ -416,9 +416,12 @@ class HybridEngine:
         tiles = -(-n_local // ops.SCORE_TILE)
         ld = tiles * ops.SCORE_TILE
         if query_chunk is None:
-            free, _ = torch.cuda.mem_get_info(q_emb.device)
             per_query = ld * 4 * (1 if fused else 3)
-            query_chunk = max(1, min(n_q, int(free * 0.6) // per_query))
+            if n_q * per_query <= (1 << 30):
+                query_chunk = n_q        # small (the fallback of the threshold search): no cudaMemGetInfo, which was seen to
+            else:                        # take 5-50 ms now and then when called between kernels
+                free, _ = torch.cuda.mem_get_info(q_emb.device)
+                query_chunk = max(1, min(n_q, int(free * 0.6) // per_query))
             if fused and query_chunk >= 128:
                 query_chunk = query_chunk // 128 * 128
         out_s, out_i = [], []
