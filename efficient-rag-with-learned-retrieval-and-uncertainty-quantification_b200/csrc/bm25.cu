@@ -19,9 +19,10 @@
 //       ALSO stored as a dense row of uint8 term frequencies; a lane loads its 8 bytes with one 64-bit load
 //       per term and accumulates in registers - no document ids, no cursor, no compare;
 //     * every other term streams its posting list: lists are sorted by document, so a warp continues reading
-//       where it stopped (one cursor per term, placed once by a 32-ary search), 128-byte coalesced, 1 to 8
-//       independent 32-posting chunks per pass sized to the list's density, into a shared-memory accumulator
-//       that covers the super-range.  All documents inside one chunk are distinct, so the update is a plain
+//       where it stopped (one cursor per term, placed once by a 32-ary search), 128-byte coalesced, several
+//       independent 32-posting chunks per pass (1 to 8 by the list's density in the get_scores variant; ONE variant
+//       per phase in the top-k kernel, whose ~125 KB of code made instruction fetch a measurable stall), into a
+//       shared-memory accumulator that covers the super-range.  All documents inside one chunk are distinct, so the update is a plain
 //       read-modify-write: no atomics on scores.  Terms whose next posting lies beyond the super-range are
 //       skipped with one ballot.
 //  2. fp16 bound pass (top-k variant, while thr is a sizeable fraction of what the table terms can add):
@@ -30,7 +31,8 @@
 //     touched get the exact arithmetic.  With it the exact table path of phase 1 is never taken at 10M x 1024.
 //  3. Window mode (once thr exceeds the table bound): only documents a posting list touches matter - ~3% of
 //     the corpus per query - so the warp covers up to 32k documents per visit and keeps the accumulator as an
-//     open-addressing hash table in the same 4 KB of shared memory (see stream_term_hash).  MaxScore marks
+//     open-addressing hash table in the same 4 KB of shared memory (see stream_term_hash).  With baked impacts
+//     (Bm25Args::post_imp) a posting is a (document, impact) pair and nothing is gathered behind it.  MaxScore marks
 //     only documents of essential (heavy, rare) lists, and marked documents whose list part plus the table bound
 //     cannot reach thr are dropped before any table byte is gathered.
 //
