@@ -577,8 +577,10 @@ def run_ours(args):
         else:
             bm25_roof["basis"] = ("un-pruned algorithmic bytes / live time (NOT a bandwidth fraction: exact pruning skips most of "
                                   "these bytes; no matching ncu capture under profiles/ for this workload)")
-        # the roofline object describes the kernel that takes most of the step
-        line["roofline"], line["roofline_secondary"] = (dense_roof, bm25_roof) if dense_avg >= bm25_avg else (bm25_roof, dense_roof)
+        # the roofline object describes the kernel that takes most of the step - the BM25 kernel only when its fraction
+        # rests on MEASURED bytes (an un-pruned "fraction" above 1 is a throughput, not a roofline, and stays secondary)
+        bm25_first = bm25_avg > dense_avg and bm25_roof.get("traffic") is not None
+        line["roofline"], line["roofline_secondary"] = (bm25_roof, dense_roof) if bm25_first else (dense_roof, bm25_roof)
         if not args.no_cpu_baseline and world == 1:
             ref = CpuReference(args, max(1, min(os.cpu_count() or 1, 64)))
             ref.step()                                   # warm-up pass
