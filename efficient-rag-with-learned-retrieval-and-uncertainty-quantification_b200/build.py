@@ -45,8 +45,14 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every .cu for sm_100a and link the shared library.  Returns its path."""
+def build(force: bool = False, verbose: bool = False, profile: bool = False) -> Path:
+    """Compile every .cu for sm_100a and link the shared library.  Returns its path.
+
+    ``profile``: the instrumented diagnostics build (-DRAGB_BM25_PROFILE: per-query / per-phase cycle counters in
+    bm25_kernel) as ``libragb200_prof.so`` next to the product library; load it with RAGB_LIB_NAME=libragb200_prof.so
+    (scripts/profile_bm25_queries.py does).  Never the default: the counters cost registers."""
+    if profile:
+        return _build_profile(verbose)
     stamp = OBJ_DIR / "fingerprint"
     fp = _fingerprint()
     if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == fp:
@@ -77,5 +83,28 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+def _build_profile(verbose: bool = False) -> Path:
+    out_dir = PKG_DIR / "build_prof"
+    out_dir.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+    flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-DRAGB_BM25_PROFILE"]
+    objs = []
+    for src in SOURCES:
+        obj = out_dir / (src[:-3] + ".o")
+        r = subprocess.run([nvcc, *flags, "-I", str(INCLUDE), "-I", str(CSRC), "-c", str(CSRC / src), "-o", str(obj)],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        objs.append(str(obj))
+    lib = PKG_DIR / "libragb200_prof.so"
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *objs],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, profile="--profile" in sys.argv))

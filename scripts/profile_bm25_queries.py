@@ -1,7 +1,8 @@
 """Where does bm25_kernel spend its warp cycles, per query and per phase?  (diagnostic, B200 box)
 
-Needs the instrumented build (-DRAGB_BM25_PROFILE):
-  RAGB_LIB_NAME=libragb200_prof.so python scripts/profile_bm25_queries.py [passages]
+Needs the instrumented build (-DRAGB_BM25_PROFILE; build it HERE first, it travels with the snapshot):
+  python efficient-rag-with-learned-retrieval-and-uncertainty-quantification_b200/build.py --profile
+  gpurun -- 'python scripts/profile_bm25_queries.py [passages]'        (loads libragb200_prof.so via RAGB_LIB_NAME)
 Prints the share of each phase and how the cost is distributed over the 1024 queries of one batch.
 """
 import ctypes
