@@ -84,6 +84,13 @@ def exchange_pools(bs: Tensor, bi: Tensor, ds: Tensor, di: Tensor, group=None):
     return gbs, gbi, gds, gdi
 
 
+def seed_slice(n_queries: int, rank: int, world: int) -> Tuple[int, int]:
+    """Queries [q0, q1) of a batch that shard ``rank`` of ``world`` seeds before the bound exchange: contiguous slices of
+    ceil(n / world) that cover every query exactly once (trailing shards may get none)."""
+    per = -(-n_queries // max(1, world))
+    return min(n_queries, rank * per), min(n_queries, (rank + 1) * per)
+
+
 class HybridEngine:
     def __init__(self, sparse: Optional[SparseShard], passages: Optional[Tensor], id_base: int = 0, group=None,
                  mma_variant: int = 3):
@@ -156,8 +163,7 @@ class HybridEngine:
             # for the whole corpus.  So each shard seeds only its slice of the batch (q_off is sliced, its offsets stay
             # absolute) and the MAX all-reduce below hands every query the bound of the shard that seeded it.
             n_q = q_off.shape[0] - 1
-            per = -(-n_q // self.world)
-            q0, q1 = min(n_q, self.rank * per), min(n_q, (self.rank + 1) * per)
+            q0, q1 = seed_slice(n_q, self.rank, self.world)
             b_seed = torch.zeros(n_q, dtype=torch.float32, device=q_emb.device)
             if SLICE_SEEDS and q1 > q0:
                 b_seed[q0:q1] = self.sparse.seed(q_terms, q_off[q0:q1 + 1], max_terms, pool)

@@ -191,6 +191,37 @@ def test_shard_rows_partition():
         assert max(sizes) - min(sizes) <= 1
 
 
+def test_seed_slices_cover_every_query_once():
+    """HybridEngine.local_pools at world > 1: every shard seeds one contiguous slice of the batch, the MAX all-reduce
+    distributes the bounds - so the slices must partition [0, n) for any batch size and world size."""
+    from rag_uq_b200.engine import seed_slice
+    for n in (0, 1, 7, 8, 1024, 1025):
+        for world in (1, 2, 3, 8, 16):
+            slices = [seed_slice(n, r, world) for r in range(world)]
+            covered = [q for q0, q1 in slices for q in range(q0, q1)]
+            assert covered == list(range(n)), (n, world, slices)
+            assert all(0 <= q0 <= q1 <= n for q0, q1 in slices)
+
+
+def test_bound_table_cache_keeps_several_grids(rq):
+    """router.full_fusion_table / full_fusion_envelope: the fallback of the threshold search alternates between a few
+    (b_cap, d_hi) grids; each stays cached until a weight or statistic changes (a one-entry cache recomputed the host
+    table - tens of milliseconds - on every alternation)."""
+    torch.manual_seed(3)
+    router = rq.RetrievalRouter()
+    router.bm25_mean.fill_(8.0); router.bm25_std.fill_(6.0); router.dense_mean.fill_(0.2); router.dense_std.fill_(0.3)
+    router.stats_initialized = True
+    a = router.full_fusion_table(32.0, 1.0)
+    b = router.full_fusion_table(64.0, 1.015625)
+    assert router.full_fusion_table(32.0, 1.0) is a and router.full_fusion_table(64.0, 1.015625) is b
+    e = router.full_fusion_envelope(32.0, 1.0, 64, 32)
+    assert router.full_fusion_envelope(32.0, 1.0, 64, 32) is e
+    router.bm25_mean.fill_(9.0)                                   # a statistic moved: every cached grid is stale
+    c = router.full_fusion_table(32.0, 1.0)
+    assert c is not a and len(router.__dict__["_ff_cache"]) == 1
+    assert not torch.equal(c, a)
+
+
 def test_streaming_index_checkpoint_and_resume(rq, tmp_path):
     """StreamingIndex keeps the reference's checkpoint semantics (streaming_index.py:593-679)."""
 
